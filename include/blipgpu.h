@@ -1,0 +1,180 @@
+/*
+ * blipgpu.h -- C ABI of libblipgpu.so: the B200 (sm_100a) implementation of
+ * pyblip's multi-chain Gibbs samplers and candidate-group PIP counting.
+ *
+ * This is the drop-in boundary.  Every entry point names the reference
+ * interface it replaces (paths relative to amspector100/pyblip v0.4.2).  The
+ * reference reaches its hot path through Python -> Cython calls
+ * (`apply_pool(fn, ...)` in pyblip/utilities.py:63-139 mapping one Cython call
+ * per chain); a maintainer binds these symbols with ctypes instead (see
+ * INTEGRATION.md).  Plain pointers and sizes only; no torch / numpy types.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a BLIPGPU_ERR_* code otherwise;
+ *     blipgpu_last_error() returns a thread-local message for the last failure;
+ *   - host pointers are borrowed for the duration of the call only;
+ *   - handles are opaque and freed by the matching *_free;
+ *   - "device pointer" arguments must belong to the context's device.
+ */
+#ifndef BLIPGPU_H
+#define BLIPGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BLIPGPU_ABI_VERSION 1
+
+#define BLIPGPU_OK 0
+#define BLIPGPU_ERR_CUDA 1
+#define BLIPGPU_ERR_ARG 2
+#define BLIPGPU_ERR_NOMEM 3
+#define BLIPGPU_ERR_NUMERIC 4      /* reference raises RuntimeError / ValueError */
+#define BLIPGPU_ERR_UNSUPPORTED 5
+
+typedef struct blipgpu_ctx blipgpu_ctx;         /* one device + its streams        */
+typedef struct blipgpu_design blipgpu_design;   /* X resident in HBM (+ Gram)      */
+typedef struct blipgpu_samples blipgpu_samples; /* posterior samples kept on device */
+typedef struct blipgpu_bits blipgpu_bits;       /* bit-packed indicator matrix      */
+
+int blipgpu_abi_version(void);
+const char* blipgpu_last_error(void);
+int blipgpu_device_count(int* count);
+
+/* ---- context ----------------------------------------------------------- */
+int blipgpu_ctx_create(int device, blipgpu_ctx** out);
+int blipgpu_ctx_destroy(blipgpu_ctx* ctx);
+int blipgpu_ctx_synchronize(blipgpu_ctx* ctx);
+/* Elapsed device milliseconds (CUDA events on the context's stream) spent in
+ * sweep kernels / counting kernels since the last reset; used by bench.py. */
+int blipgpu_ctx_timing(blipgpu_ctx* ctx, double* sweep_ms, int64_t* sweep_launches,
+                       double* other_ms, int64_t* other_launches, int reset);
+
+/* ---- design matrix ----------------------------------------------------- */
+#define BLIPGPU_DESIGN_DENSE 0        /* X given, column-major copy kept in HBM   */
+#define BLIPGPU_DESIGN_CHANGEPOINT 1  /* X[i][j] = 1{i >= j}, never materialised
+                                         (pyblip/changepoint.py:33-35)           */
+/* Replaces `XT = np.ascontiguousarray(X.T)` and `Xl2 = (X**2).sum(0)`
+ * (pyblip/linear/_linear.pyx:73-74).  X is n x p row-major (C-contiguous) float64
+ * on the HOST. */
+int blipgpu_design_upload(blipgpu_ctx* ctx, const double* X, int64_t n, int64_t p,
+                          blipgpu_design** out);
+int blipgpu_design_changepoint(blipgpu_ctx* ctx, int64_t T, blipgpu_design** out);
+/* Builds the p x p Gram matrix X^T X on the device (fp64 tensor cores); replaces
+ * `np.dot(X.T, X)` (pyblip/linear/_linear_multi.pyx:379).  Idempotent. */
+int blipgpu_design_build_gram(blipgpu_design* d);
+/* Debug / test access: copy the Gram block rows [r0, r1) x all columns to host. */
+int blipgpu_design_get_gram(blipgpu_design* d, int64_t r0, int64_t r1, double* out);
+int blipgpu_design_get_xl2(blipgpu_design* d, double* out);
+int blipgpu_design_free(blipgpu_design* d);
+
+/* ---- spike-and-slab sampler -------------------------------------------- */
+/* Scalars of `_sample_spikeslab` (pyblip/linear/_linear.pyx:34-53), 1:1. */
+typedef struct blipgpu_spikeslab_config {
+    double tau2;   int32_t update_tau2;   double tau2_a0, tau2_b0;
+    double sigma2; int32_t update_sigma2; double sigma2_a0, sigma2_b0;
+    double p0;     int32_t update_p0;     double min_p0, p0_a0, p0_b0;
+} blipgpu_spikeslab_config;
+
+/* Optional injected random stream (HOST arrays, chain-major).  A NULL member
+ * means "use the keyed Philox stream for that slot".  Indices: c chain (local),
+ * i sweep in [0, n_sweeps_total), s position in the sweep's visiting order. */
+typedef struct blipgpu_streams {
+    const int32_t* perm;      /* [chains][sweeps][p]  visiting order              */
+    const double* u;          /* [chains][sweeps][p]  spike/slab uniform at s     */
+    const double* z;          /* [chains][sweeps][p]  slab normal at s            */
+    const double* invgamma;   /* [chains][sweeps]     InvGamma(n/2+sigma2_a0)     */
+    const double* p0_draw;    /* [chains][sweeps][nprop] Beta variates            */
+    const double* gamma_draw; /* [chains][sweeps]     Gamma(tau2_a0+k/2) variates */
+    int32_t nprop;            /* 1, or 100 when min_p0 > 0                        */
+} blipgpu_streams;
+
+#define BLIPGPU_MODE_AUTO 0
+#define BLIPGPU_MODE_RESIDUAL 1  /* state r = y - X beta; one X column per update  */
+#define BLIPGPU_MODE_GRAM 2      /* state q = X^T r; one Gram column per change    */
+
+typedef struct blipgpu_sample_options {
+    int32_t mode;            /* BLIPGPU_MODE_*                                     */
+    int32_t chunk_sweeps;    /* sweeps per kernel launch (0 = default)             */
+    int32_t keep_latents;    /* probit: keep Z on the device                       */
+    int32_t gram_refresh;    /* gram mode: rebuild q every this many sweeps (0=def) */
+    int32_t reserved[4];
+} blipgpu_sample_options;
+
+/* Replaces `apply_pool(_sample_spikeslab, constant_inputs, N=[N+burn]*chains)`
+ * (pyblip/linear/linear.py:159-164, pyblip/probit/probit.py:89-94): all chains in
+ * one call.  `y` is the response (linear) and ignored when probit != 0; `z` are
+ * the 0/1 labels (probit; 1 => latent < 0).  Chains get global ids
+ * chain_offset .. chain_offset+chains-1 (the Philox key), so a multi-GPU run
+ * that shards chains produces the same draws as a single-GPU run.
+ * The first `burn` sweeps are run but not recorded. */
+int blipgpu_sample_spikeslab(blipgpu_ctx* ctx, blipgpu_design* design,
+                             const blipgpu_spikeslab_config* cfg,
+                             const double* y, const int64_t* z, int32_t probit,
+                             int64_t chains, int64_t chain_offset,
+                             int64_t n_keep, int64_t burn, uint64_t seed,
+                             const blipgpu_streams* streams,
+                             const blipgpu_sample_options* opts,
+                             blipgpu_samples** out);
+
+/* ---- samples handle ---------------------------------------------------- */
+typedef struct blipgpu_samples_info {
+    int64_t rows;        /* chains * n_keep, chain-major like linear.py:165-168   */
+    int64_t p, n, chains, n_keep;
+    int64_t nnz;         /* total non-zero coefficients stored                   */
+    int64_t n_events;    /* probit: total latent redraw events                   */
+    int32_t has_latents, mode;
+    double sweep_ms;     /* device time in sweep kernels for this call           */
+    int64_t sweep_launches;
+    int64_t bytes_device;
+} blipgpu_samples_info;
+
+int blipgpu_samples_info_get(blipgpu_samples* s, blipgpu_samples_info* info);
+/* p0s / tau2s / sigma2s, each [rows] float64 on the host. */
+int blipgpu_samples_hyper(blipgpu_samples* s, double* p0s, double* tau2s, double* sigma2s);
+/* Dense betas rows [row0, row1) -> out[(row1-row0)][p] float64 host
+ * (what `np.concatenate([x['betas'][burn:] ...])` returns, linear.py:165). */
+int blipgpu_samples_dense(blipgpu_samples* s, int64_t row0, int64_t row1, double* out);
+/* CSR export: indptr[rows+1], then indices/values[nnz] (host). */
+int blipgpu_samples_csr(blipgpu_samples* s, int64_t* indptr, int32_t* indices, double* values);
+/* Probit latents Z rows [row0,row1) -> out[..][n] (probit.py:99). */
+int blipgpu_samples_latents(blipgpu_samples* s, int64_t row0, int64_t row1, double* out);
+int blipgpu_samples_free(blipgpu_samples* s);
+
+/* ---- candidate-group PIP counting -------------------------------------- */
+/* Bit-packed (samples != 0).  Replaces `samples = samples != 0`
+ * (pyblip/create_groups.py:104, 322, 435). */
+int blipgpu_bits_from_samples(blipgpu_samples* s, int32_t zero_first_column, blipgpu_bits** out);
+#define BLIPGPU_DTYPE_F64 0
+#define BLIPGPU_DTYPE_U8 1
+/* host (N x p) row-major array of float64 or uint8/bool */
+int blipgpu_bits_from_dense(blipgpu_ctx* ctx, const void* samples, int32_t dtype, int64_t N,
+                            int64_t p, blipgpu_bits** out);
+int blipgpu_bits_shape(blipgpu_bits* b, int64_t* N, int64_t* p);
+/* samples[:, cols]  (create_groups.py:117) -- compacted index space */
+int blipgpu_bits_select_columns(blipgpu_bits* b, const int64_t* cols, int64_t ncols,
+                                blipgpu_bits** out);
+/* Unpack to a host uint8 (N x p) matrix (tests / fallbacks). */
+int blipgpu_bits_to_dense(blipgpu_bits* b, uint8_t* out);
+
+/* counts[j] = #rows with samples[:, j] != 0      (create_groups.py:105-106).
+ * If out_is_device != 0, `counts` is a device pointer (e.g. a torch tensor that
+ * is all-reduced with NCCL afterwards); otherwise a host pointer. */
+int blipgpu_count_columns(blipgpu_bits* b, int64_t* counts, int32_t out_is_device);
+/* zero_counts[m][j] = #rows whose columns j..j+m are all zero, m < max_size,
+ * j < p - m; entries with j >= p - m are 0.  Layout [max_size][p].
+ * (create_groups.py:321-332: cum_diffs == 0 summed over rows.) */
+int blipgpu_count_sequential(blipgpu_bits* b, int32_t max_size, int64_t* zero_counts,
+                             int32_t out_is_device);
+/* any_counts[g] = #rows with any(samples[:, members[offsets[g]:offsets[g+1]]])
+ * (create_groups.py:459, blip.py:270-275).  offsets/members are host arrays. */
+int blipgpu_count_groups(blipgpu_bits* b, const int64_t* offsets, const int64_t* members,
+                         int64_t n_groups, int64_t* any_counts, int32_t out_is_device);
+int blipgpu_bits_free(blipgpu_bits* b);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BLIPGPU_H */

@@ -1,0 +1,439 @@
+"""ctypes binding of libblipgpu.so (the C ABI declared in include/blipgpu.h).
+
+There is no CPU fallback: if the library is missing or no B200 is visible the
+calls below raise.  The Python objects here are thin RAII wrappers around the
+opaque handles; the reference-facing API lives in ``linear/``, ``probit/``,
+``changepoint.py`` and ``create_groups.py``.
+"""
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "_C", "libblipgpu.so")
+
+MODE_AUTO, MODE_RESIDUAL, MODE_GRAM = 0, 1, 2
+DESIGN_DENSE, DESIGN_CHANGEPOINT = 0, 1
+DTYPE_F64, DTYPE_U8 = 0, 1
+ERR_NUMERIC, ERR_NOMEM, ERR_ARG, ERR_UNSUPPORTED = 4, 3, 2, 5
+
+# every symbol include/blipgpu.h declares (checked by tests/test_abi.py)
+SYMBOLS = [
+    "blipgpu_abi_version", "blipgpu_last_error", "blipgpu_device_count",
+    "blipgpu_ctx_create", "blipgpu_ctx_destroy", "blipgpu_ctx_synchronize", "blipgpu_ctx_timing",
+    "blipgpu_design_upload", "blipgpu_design_changepoint", "blipgpu_design_build_gram",
+    "blipgpu_design_get_gram", "blipgpu_design_get_xl2", "blipgpu_design_free",
+    "blipgpu_sample_spikeslab",
+    "blipgpu_samples_info_get", "blipgpu_samples_hyper", "blipgpu_samples_dense",
+    "blipgpu_samples_csr", "blipgpu_samples_latents", "blipgpu_samples_free",
+    "blipgpu_bits_from_samples", "blipgpu_bits_from_dense", "blipgpu_bits_shape",
+    "blipgpu_bits_select_columns", "blipgpu_bits_to_dense",
+    "blipgpu_count_columns", "blipgpu_count_sequential", "blipgpu_count_groups",
+    "blipgpu_bits_free",
+]
+
+
+class SpikeSlabConfig(C.Structure):
+    """``blipgpu_spikeslab_config``: scalars of ``_sample_spikeslab``
+    (/root/reference/pyblip/linear/_linear.pyx:34-53)."""
+    _fields_ = [
+        ("tau2", C.c_double), ("update_tau2", C.c_int32),
+        ("tau2_a0", C.c_double), ("tau2_b0", C.c_double),
+        ("sigma2", C.c_double), ("update_sigma2", C.c_int32),
+        ("sigma2_a0", C.c_double), ("sigma2_b0", C.c_double),
+        ("p0", C.c_double), ("update_p0", C.c_int32),
+        ("min_p0", C.c_double), ("p0_a0", C.c_double), ("p0_b0", C.c_double),
+    ]
+
+
+class Streams(C.Structure):
+    _fields_ = [
+        ("perm", C.c_void_p), ("u", C.c_void_p), ("z", C.c_void_p),
+        ("invgamma", C.c_void_p), ("p0_draw", C.c_void_p), ("gamma_draw", C.c_void_p),
+        ("nprop", C.c_int32),
+    ]
+
+
+class SampleOptions(C.Structure):
+    _fields_ = [
+        ("mode", C.c_int32), ("chunk_sweeps", C.c_int32), ("keep_latents", C.c_int32),
+        ("gram_refresh", C.c_int32), ("reserved", C.c_int32 * 4),
+    ]
+
+
+class SamplesInfo(C.Structure):
+    _fields_ = [
+        ("rows", C.c_int64), ("p", C.c_int64), ("n", C.c_int64), ("chains", C.c_int64),
+        ("n_keep", C.c_int64), ("nnz", C.c_int64), ("n_events", C.c_int64),
+        ("has_latents", C.c_int32), ("mode", C.c_int32),
+        ("sweep_ms", C.c_double), ("sweep_launches", C.c_int64), ("bytes_device", C.c_int64),
+    ]
+
+
+class BlipGpuError(RuntimeError):
+    pass
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load():
+    """Load libblipgpu.so; raise loudly if it has not been built."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: run `python -m pyblip_b200.build` (needs nvcc). "
+                "pyblip_b200 has no CPU fallback.")
+        lib = C.CDLL(LIB_PATH)
+        lib.blipgpu_last_error.restype = C.c_char_p
+        for name in SYMBOLS:
+            fn = getattr(lib, name)
+            if name not in ("blipgpu_last_error",):
+                fn.restype = C.c_int
+        _lib = lib
+        return lib
+
+
+def check(rc):
+    if rc == 0:
+        return
+    msg = load().blipgpu_last_error().decode("utf-8", "replace")
+    if rc == ERR_NOMEM:
+        raise MemoryError(msg)
+    if rc == ERR_ARG:
+        raise ValueError(msg)
+    if rc == ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise BlipGpuError(f"libblipgpu error {rc}: {msg}")
+
+
+def device_count():
+    n = C.c_int(0)
+    check(load().blipgpu_device_count(C.byref(n)))
+    return n.value
+
+
+class Context:
+    """One CUDA device (``blipgpu_ctx``)."""
+    _cache = {}
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        check(load().blipgpu_ctx_create(C.c_int(device), C.byref(self._h)))
+        self.device = device
+
+    @classmethod
+    def get(cls, device=None):
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0"))
+            try:
+                ndev = device_count()
+            except Exception:
+                ndev = 0
+            if ndev > 0:
+                device %= ndev
+        ctx = cls._cache.get(device)
+        if ctx is None:
+            ctx = cls._cache[device] = Context(device)
+        return ctx
+
+    def synchronize(self):
+        check(load().blipgpu_ctx_synchronize(self._h))
+
+    def timing(self, reset=False):
+        sm, ol = C.c_double(), C.c_double()
+        sl, oo = C.c_int64(), C.c_int64()
+        check(load().blipgpu_ctx_timing(self._h, C.byref(sm), C.byref(sl), C.byref(ol), C.byref(oo),
+                                        C.c_int(int(reset))))
+        return dict(sweep_ms=sm.value, sweep_launches=sl.value, other_ms=ol.value,
+                    other_launches=oo.value)
+
+
+class Design:
+    """X resident on the device (``blipgpu_design``)."""
+
+    def __init__(self, ctx, handle, n, p, kind):
+        self.ctx, self._h, self.n, self.p, self.kind = ctx, handle, n, p, kind
+
+    @classmethod
+    def upload(cls, X, ctx=None):
+        ctx = ctx or Context.get()
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        if X.ndim != 2:
+            raise ValueError("X must be a 2-D array")
+        h = C.c_void_p()
+        check(load().blipgpu_design_upload(ctx._h, C.c_void_p(X.ctypes.data), C.c_int64(X.shape[0]),
+                                           C.c_int64(X.shape[1]), C.byref(h)))
+        return cls(ctx, h, X.shape[0], X.shape[1], DESIGN_DENSE)
+
+    @classmethod
+    def changepoint(cls, T, ctx=None):
+        ctx = ctx or Context.get()
+        h = C.c_void_p()
+        check(load().blipgpu_design_changepoint(ctx._h, C.c_int64(T), C.byref(h)))
+        return cls(ctx, h, T, T, DESIGN_CHANGEPOINT)
+
+    def build_gram(self):
+        check(load().blipgpu_design_build_gram(self._h))
+
+    def gram(self, r0=0, r1=None):
+        r1 = self.p if r1 is None else r1
+        out = np.empty((r1 - r0, self.p))
+        check(load().blipgpu_design_get_gram(self._h, C.c_int64(r0), C.c_int64(r1),
+                                             C.c_void_p(out.ctypes.data)))
+        return out
+
+    def xl2(self):
+        out = np.empty(self.p)
+        check(load().blipgpu_design_get_xl2(self._h, C.c_void_p(out.ctypes.data)))
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load().blipgpu_design_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _opt_array(a, dtype, shape):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(a, dtype=dtype)
+    if a.shape != tuple(shape):
+        raise ValueError(f"injected stream has shape {a.shape}, expected {tuple(shape)}")
+    return a
+
+
+class Samples:
+    """Posterior samples kept on the device (``blipgpu_samples``)."""
+
+    def __init__(self, ctx, handle):
+        self.ctx, self._h = ctx, handle
+        self._info = None
+
+    @property
+    def info(self):
+        if self._info is None:
+            inf = SamplesInfo()
+            check(load().blipgpu_samples_info_get(self._h, C.byref(inf)))
+            self._info = inf
+        return self._info
+
+    @property
+    def shape(self):
+        return (self.info.rows, self.info.p)
+
+    def hyper(self):
+        rows = self.info.rows
+        p0s, tau2s, sigma2s = np.empty(rows), np.empty(rows), np.empty(rows)
+        check(load().blipgpu_samples_hyper(self._h, C.c_void_p(p0s.ctypes.data),
+                                           C.c_void_p(tau2s.ctypes.data),
+                                           C.c_void_p(sigma2s.ctypes.data)))
+        return p0s, tau2s, sigma2s
+
+    def dense(self, row0=0, row1=None):
+        row1 = self.info.rows if row1 is None else row1
+        out = np.empty((row1 - row0, self.info.p))
+        check(load().blipgpu_samples_dense(self._h, C.c_int64(row0), C.c_int64(row1),
+                                           C.c_void_p(out.ctypes.data)))
+        return out
+
+    def csr(self):
+        rows = self.info.rows
+        indptr = np.empty(rows + 1, dtype=np.int64)
+        nnz = self.info.nnz
+        indices = np.empty(max(nnz, 1), dtype=np.int32)
+        values = np.empty(max(nnz, 1), dtype=np.float64)
+        check(load().blipgpu_samples_csr(self._h, C.c_void_p(indptr.ctypes.data),
+                                         C.c_void_p(indices.ctypes.data),
+                                         C.c_void_p(values.ctypes.data)))
+        return indptr, indices[:nnz], values[:nnz]
+
+    def latents(self, row0=0, row1=None):
+        row1 = self.info.rows if row1 is None else row1
+        out = np.empty((row1 - row0, self.info.n))
+        check(load().blipgpu_samples_latents(self._h, C.c_int64(row0), C.c_int64(row1),
+                                             C.c_void_p(out.ctypes.data)))
+        return out
+
+    def bits(self, zero_first_column=False):
+        h = C.c_void_p()
+        check(load().blipgpu_bits_from_samples(self._h, C.c_int32(int(zero_first_column)),
+                                               C.byref(h)))
+        return Bits(self.ctx, h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load().blipgpu_samples_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def sample_spikeslab(design, cfg, y=None, z=None, probit=False, chains=1, chain_offset=0,
+                     n_keep=1, burn=0, seed=0, streams=None, mode=MODE_AUTO, chunk_sweeps=0,
+                     keep_latents=True, gram_refresh=0):
+    """All chains of this rank in one call (``blipgpu_sample_spikeslab``)."""
+    n, p = design.n, design.p
+    n_total = n_keep + burn
+    keep = []
+    if probit:
+        z = np.ascontiguousarray(z, dtype=np.int64)
+        if z.shape != (n,):
+            raise ValueError("z must have shape (n,)")
+        yptr, zptr = None, z.ctypes.data
+    else:
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        if y.shape != (n,):
+            raise ValueError("y must have shape (n,)")
+        yptr, zptr = y.ctypes.data, None
+    st_ptr = None
+    if streams:
+        perm = _opt_array(streams.get("perm"), np.int32, (chains, n_total, p))
+        u = _opt_array(streams.get("u"), np.float64, (chains, n_total, p))
+        zn = _opt_array(streams.get("z"), np.float64, (chains, n_total, p))
+        ig = _opt_array(streams.get("invgamma"), np.float64, (chains, n_total))
+        gd = _opt_array(streams.get("gamma_draw"), np.float64, (chains, n_total))
+        p0d = streams.get("p0_draw")
+        nprop = 1
+        if p0d is not None:
+            p0d = np.ascontiguousarray(p0d, dtype=np.float64)
+            if p0d.ndim == 2:
+                p0d = p0d[:, :, None]
+            if p0d.shape[:2] != (chains, n_total):
+                raise ValueError("p0_draw must have shape (chains, sweeps[, nprop])")
+            p0d = np.ascontiguousarray(p0d)
+            nprop = p0d.shape[2]
+        keep += [perm, u, zn, ig, gd, p0d]
+        ptr = lambda a: None if a is None else a.ctypes.data  # noqa: E731
+        st = Streams(ptr(perm), ptr(u), ptr(zn), ptr(ig), ptr(p0d), ptr(gd), nprop)
+        st_ptr = C.byref(st)
+    opts = SampleOptions(int(mode), int(chunk_sweeps), int(bool(keep_latents)), int(gram_refresh))
+    h = C.c_void_p()
+    check(load().blipgpu_sample_spikeslab(
+        design.ctx._h, design._h, C.byref(cfg), C.c_void_p(yptr), C.c_void_p(zptr),
+        C.c_int32(int(bool(probit))), C.c_int64(chains), C.c_int64(chain_offset),
+        C.c_int64(n_keep), C.c_int64(burn), C.c_uint64(seed), st_ptr, C.byref(opts), C.byref(h)))
+    del keep
+    return Samples(design.ctx, h)
+
+
+class Bits:
+    """Bit-packed ``samples != 0`` on the device (``blipgpu_bits``)."""
+
+    def __init__(self, ctx, handle):
+        self.ctx, self._h = ctx, handle
+        N, p = C.c_int64(), C.c_int64()
+        check(load().blipgpu_bits_shape(self._h, C.byref(N), C.byref(p)))
+        self.N, self.p = N.value, p.value
+
+    @property
+    def shape(self):
+        return (self.N, self.p)
+
+    @classmethod
+    def from_dense(cls, samples, ctx=None):
+        ctx = ctx or Context.get()
+        samples = np.asarray(samples)
+        if samples.ndim != 2:
+            raise ValueError("samples must be 2-D")
+        if samples.dtype == np.bool_ or samples.dtype == np.uint8:
+            arr = np.ascontiguousarray(samples).view(np.uint8)
+            dt = DTYPE_U8
+        elif samples.dtype == np.float64:
+            arr = np.ascontiguousarray(samples)
+            dt = DTYPE_F64
+        else:
+            arr = np.ascontiguousarray(samples != 0).view(np.uint8)
+            dt = DTYPE_U8
+        h = C.c_void_p()
+        check(load().blipgpu_bits_from_dense(ctx._h, C.c_void_p(arr.ctypes.data), C.c_int32(dt),
+                                             C.c_int64(arr.shape[0]), C.c_int64(arr.shape[1]),
+                                             C.byref(h)))
+        return cls(ctx, h)
+
+    def select_columns(self, cols):
+        cols = np.ascontiguousarray(cols, dtype=np.int64)
+        h = C.c_void_p()
+        check(load().blipgpu_bits_select_columns(self._h, C.c_void_p(cols.ctypes.data),
+                                                 C.c_int64(cols.shape[0]), C.byref(h)))
+        return Bits(self.ctx, h)
+
+    def to_dense(self):
+        out = np.empty((self.N, self.p), dtype=np.uint8)
+        check(load().blipgpu_bits_to_dense(self._h, C.c_void_p(out.ctypes.data)))
+        return out.view(np.bool_)
+
+    def _out(self, shape, device_out):
+        if device_out is not None:
+            return device_out, 1
+        out = np.zeros(shape, dtype=np.int64)
+        return out, 0
+
+    def count_columns(self, device_ptr=None):
+        """#rows with a non-zero in each column (int64[p])."""
+        if device_ptr is not None:
+            check(load().blipgpu_count_columns(self._h, C.c_void_p(device_ptr), C.c_int32(1)))
+            return None
+        out = np.zeros(self.p, dtype=np.int64)
+        check(load().blipgpu_count_columns(self._h, C.c_void_p(out.ctypes.data), C.c_int32(0)))
+        return out
+
+    def count_sequential(self, max_size, device_ptr=None):
+        """zero_counts[m, j] = #rows with columns j..j+m all zero (int64[max_size, p])."""
+        if device_ptr is not None:
+            check(load().blipgpu_count_sequential(self._h, C.c_int32(max_size),
+                                                  C.c_void_p(device_ptr), C.c_int32(1)))
+            return None
+        out = np.zeros((max_size, self.p), dtype=np.int64)
+        check(load().blipgpu_count_sequential(self._h, C.c_int32(max_size),
+                                              C.c_void_p(out.ctypes.data), C.c_int32(0)))
+        return out
+
+    def count_groups(self, groups, device_ptr=None):
+        """#rows with any non-zero among each group's columns (int64[len(groups)])."""
+        G = len(groups)
+        offsets = np.zeros(G + 1, dtype=np.int64)
+        for i, g in enumerate(groups):
+            offsets[i + 1] = offsets[i] + len(g)
+        members = np.fromiter((int(j) for g in groups for j in g), dtype=np.int64,
+                              count=int(offsets[-1]))
+        if members.size == 0:
+            members = np.zeros(1, dtype=np.int64)
+        if device_ptr is not None:
+            check(load().blipgpu_count_groups(self._h, C.c_void_p(offsets.ctypes.data),
+                                              C.c_void_p(members.ctypes.data), C.c_int64(G),
+                                              C.c_void_p(device_ptr), C.c_int32(1)))
+            return None
+        out = np.zeros(G, dtype=np.int64)
+        if G:
+            check(load().blipgpu_count_groups(self._h, C.c_void_p(offsets.ctypes.data),
+                                              C.c_void_p(members.ctypes.data), C.c_int64(G),
+                                              C.c_void_p(out.ctypes.data), C.c_int32(0)))
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load().blipgpu_bits_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

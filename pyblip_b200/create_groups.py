@@ -1,0 +1,401 @@
+"""Candidate groups from posterior samples, with the PIP counting on the B200.
+
+Drop-in for the counting entry points of /root/reference/pyblip/create_groups.py:
+
+  ``sequential_groups``   (:272-383)  contiguous groups; counting :321-332
+  ``hierarchical_groups`` (:386-469)  tree groups;       counting :459
+  ``all_cand_groups``     (:56-149)   marginal PIPs :105-106 + the two above on
+                                      prefiltered columns :111-143
+
+``samples`` may be what the reference accepts -- an ``(N, p)`` array where a
+non-zero marks a signal -- or a device-resident handle: a fitted
+``LinearSpikeSlab`` / ``ProbitSpikeSlab`` (its ``samples_handle``), a
+``_lib.Samples`` or a ``_lib.Bits``; then the indicators never leave the GPU.
+All array math over the sample axis is integer counting in libblipgpu
+(``count_columns`` / ``count_sequential`` / ``count_groups``); a PEP is one float64
+divide ``count / N`` and therefore bit-identical to the reference's ``np.mean``.
+Under ``torchrun`` every rank counts its own chains and one SUM all-reduce merges
+the int64 counts.  Tree building, pre-narrowing and purity filtering are host
+logic (small, sequential) and keep the reference's ordering conventions.
+"""
+import numpy as np
+import scipy.cluster.hierarchy as hierarchy
+import scipy.spatial.distance as ssd
+
+from . import _lib, dist
+
+MIN_PEP = 1e-15  # for numerical stability (susie branch)
+
+
+class CandidateGroup():
+    """
+    A single candidate group as an input to BLiP.  Discovering a group asserts
+    there is at least one signal in the group (create_groups.py:13-53).
+
+    Parameters
+    ----------
+    group : list or set
+        Set of locations in the group.
+    pep : float
+        Posterior error probability (1 - PIP) for the group.
+    data : dict
+        Miscellaneous other attributes to associate with the group.
+    """
+
+    def __init__(self, group, pep, data=None):
+        self.group = set(group)
+        self.pep = pep
+        self.data = dict() if data is None else data
+
+    def __str__(self):
+        return f"CandidateGroup(group={self.group}, pep={self.pep}, data={self.data})"
+
+    __repr__ = __str__
+
+    def to_dict(self):
+        out = {'group': list(self.group), 'pep': self.pep}
+        for key, val in self.data.items():
+            out[key] = list(val) if isinstance(val, set) else val
+        return out
+
+
+# ---------------------------------------------------------------------------
+# device plumbing
+# ---------------------------------------------------------------------------
+class _DeviceSamples:
+    """Bit-packed indicators on the device plus the global row count."""
+
+    def __init__(self, bits, owned):
+        self.bits = bits
+        self.owned = owned
+        self.N_local = bits.N
+        self.N = dist.allreduce_scalar(bits.N) if dist.world()[1] > 1 else bits.N
+        self.p = bits.p
+
+    def select(self, cols):
+        return _DeviceSamples(self.bits.select_columns(cols), True)
+
+    def column_counts(self):
+        return dist.allreduce_counts(self.bits.count_columns())
+
+    def sequential_counts(self, max_size):
+        return dist.allreduce_counts(self.bits.count_sequential(max_size))
+
+    def group_counts(self, groups):
+        if len(groups) == 0:
+            return np.zeros(0, dtype=np.int64)
+        return dist.allreduce_counts(self.bits.count_groups(groups))
+
+    def to_dense(self):
+        return self.bits.to_dense()
+
+    def close(self):
+        if self.owned:
+            self.bits.close()
+
+
+def _as_device(samples, zero_first_column=False):
+    """Accepts an array, a fitted sampler, a Samples handle or Bits."""
+    if isinstance(samples, _DeviceSamples):
+        return samples
+    if isinstance(samples, _lib.Bits):
+        return _DeviceSamples(samples, False)
+    handle = getattr(samples, "samples_handle", None)
+    if handle is not None:
+        samples = handle
+    if isinstance(samples, _lib.Samples):
+        return _DeviceSamples(samples.bits(zero_first_column=zero_first_column), True)
+    arr = np.asarray(samples)
+    if arr.ndim != 2:
+        raise ValueError("samples must be an (N, p) array")
+    if zero_first_column:
+        arr = arr != 0
+        arr[:, 0] = False
+    return _DeviceSamples(_lib.Bits.from_dense(arr), True)
+
+
+# ---------------------------------------------------------------------------
+# purity filter (create_groups.py:543-577) -- host, only active if min_purity > 0
+# ---------------------------------------------------------------------------
+def filter_by_purity(cand_groups, min_purity=0, corr_matrix=None, X=None):
+    """Keeps the groups whose minimum absolute pairwise correlation is at least
+    ``min_purity``."""
+    if min_purity == 0:
+        return cand_groups
+    if corr_matrix is None and X is None:
+        raise ValueError("To filter by purity, either corr_matrix or X (design matrix) must be provided.")
+    if corr_matrix is None:
+        corr_matrix = np.corrcoef(X.T)
+    absC = np.abs(corr_matrix)
+    kept = []
+    for cg in cand_groups:
+        members = np.array(list(cg.group))
+        cg.data['purity'] = 1 if len(members) == 1 else absC[np.ix_(members, members)].min()
+        if cg.data['purity'] >= min_purity:
+            kept.append(cg)
+    return kept
+
+
+# ---------------------------------------------------------------------------
+# sequential groups
+# ---------------------------------------------------------------------------
+def _sequential_peps_from_counts(zero_counts, N, p, max_size):
+    """all_PEPs[m][j] = (#rows with columns j..j+m all zero) / N, j < p - m."""
+    return {m: zero_counts[m, :p - m] / N for m in range(max_size)}
+
+
+def _sequential_peps_susie(susie_alphas, max_size):
+    # SuSiE branch (:333-343): L x p alphas, L is tiny -> plain host arithmetic
+    L, p = susie_alphas.shape
+    cumalphas = np.zeros((L, p + 1))
+    cumalphas[:, 1:] = np.cumsum(susie_alphas, axis=1)
+    peps = {}
+    for m in range(max_size):
+        window = 1 - (cumalphas[:, (m + 1):] - cumalphas[:, :p - m])
+        window[window < MIN_PEP] = MIN_PEP
+        peps[m] = np.exp(np.log(window).sum(axis=0))
+    return peps
+
+
+def sequential_groups(
+    samples=None,
+    susie_alphas=None,
+    q=0,
+    max_pep=0.25,
+    max_size=25,
+    prenarrow=False,
+    min_purity=0.0,
+    X=None,
+    corr_matrix=None,
+):
+    """
+    Calculates all sequential candidate groups below max_size.
+
+    Same parameters and return value as the reference
+    (create_groups.py:272-320): a list of ``CandidateGroup`` objects for every
+    contiguous window ``{j, ..., j+m}``, ``m < max_size``, with ``pep < max_pep``.
+    """
+    if samples is not None:
+        dev = _as_device(samples)
+        try:
+            p = dev.p
+            max_size = min(max_size, p)
+            zero_counts = dev.sequential_counts(max_size)
+            all_PEPs = _sequential_peps_from_counts(zero_counts, dev.N, p, max_size)
+        finally:
+            if dev is not samples:
+                dev.close()
+    elif susie_alphas is not None:
+        p = susie_alphas.shape[1]
+        max_size = min(max_size, p)
+        all_PEPs = _sequential_peps_susie(susie_alphas, max_size)
+    else:
+        raise ValueError("Either samples or susie_alphas must be specified.")
+
+    # start index of every admissible window of size m+1 (strict <, :350)
+    active_inds = {m: np.where(all_PEPs[m] < max_pep)[0] for m in range(max_size)}
+
+    if prenarrow:
+        # A window is redundant once a sub-window already has PEP < q/2 (:356-368).
+        # Set expressions are kept in the reference's form so the resulting order of
+        # the surviving indices (a Python-set order) is the same.
+        elim_inds = set(np.where(all_PEPs[0] < q / 2)[0].tolist())
+        for m in range(1, max_size):
+            elim_inds = elim_inds.union(set([x - 1 for x in elim_inds]))
+            update = set(active_inds[m].tolist()) - elim_inds
+            active_inds[m] = np.array(list(update))
+            elim_inds = elim_inds.union(set(np.where(all_PEPs[m] < q / 2)[0].tolist()))
+
+    cand_groups = []
+    for m in range(max_size):
+        for ind in active_inds[m]:
+            cand_groups.append(CandidateGroup(
+                group=set(range(ind, ind + m + 1)), pep=all_PEPs[m][ind]))
+
+    return filter_by_purity(cand_groups, min_purity=min_purity, X=X, corr_matrix=corr_matrix)
+
+
+# ---------------------------------------------------------------------------
+# hierarchical groups
+# ---------------------------------------------------------------------------
+def _dedup_list_of_lists(x):
+    return list(set(tuple(sorted(i)) for i in x))
+
+
+def _tree_groups(link, p):
+    """Leaf sets of every node of a scipy linkage, in the breadth-first order
+    (root first, left child before right) in which the reference visits the tree
+    (create_groups.py:471-486), built bottom-up from the linkage matrix instead of
+    calling ``pre_order()`` on every node."""
+    nnode = 2 * p - 1
+    leaves = [None] * nnode
+    for i in range(p):
+        leaves[i] = [i]
+    left = np.full(nnode, -1, dtype=np.int64)
+    right = np.full(nnode, -1, dtype=np.int64)
+    for k in range(p - 1):
+        a, b = int(link[k, 0]), int(link[k, 1])
+        left[p + k], right[p + k] = a, b
+        leaves[p + k] = leaves[a] + leaves[b]
+    order, head = [nnode - 1], 0
+    while head < len(order):
+        node = order[head]
+        head += 1
+        if left[node] >= 0:
+            order.append(int(left[node]))
+            order.append(int(right[node]))
+    return [leaves[node] for node in order]
+
+
+def _dist_matrices_to_groups(dist_matrices, cluster_funcs=None):
+    """
+    Groups from single / average / complete linkage on a distance matrix.
+    As in the reference (:491-521) a list of matrices is accepted, each matrix has
+    its diagonal zeroed IN PLACE, and only the LAST matrix contributes groups
+    (the accumulator is reset inside the loop, :502-514).
+    """
+    if isinstance(dist_matrices, np.ndarray):
+        dist_matrices = [dist_matrices]
+    p = dist_matrices[0].shape[0]
+    if cluster_funcs is None:
+        cluster_funcs = [hierarchy.single, hierarchy.average, hierarchy.complete]
+    all_groups = []
+    for idx, dist_matrix in enumerate(dist_matrices):
+        dist_matrix -= np.diag(np.diag(dist_matrix))     # in place, like the reference
+        if idx != len(dist_matrices) - 1:
+            continue                                      # overwritten below anyway
+        sym = (dist_matrix.T + dist_matrix) / 2
+        condensed = ssd.squareform(sym)
+        all_groups = []
+        for cluster_func in cluster_funcs:
+            link = cluster_func(condensed)
+            all_groups.extend(_tree_groups(link, p))
+            all_groups = _dedup_list_of_lists(all_groups)
+    return all_groups
+
+
+def _samples_dist_matrix(samples):
+    """corrcoef of the indicator columns, with one all-zero and one all-one row
+    appended so that no column is constant, plus one (:523-535).  Host code: it
+    feeds the (host) clustering; ``samples`` is a dense boolean matrix."""
+    p = samples.shape[1]
+    precorr = np.concatenate([samples, np.zeros((1, p)), np.ones((1, p))], axis=0)
+    return np.corrcoef(precorr.T) + 1
+
+
+def hierarchical_groups(
+    samples,
+    dist_matrix=None,
+    max_pep=0.25,
+    max_size=25,
+    filter_sequential=False,
+    min_purity=0,
+    X=None,
+    corr_matrix=None,
+    **kwargs
+):
+    """
+    Creates candidate groups by hierarchical clustering (create_groups.py:386-469).
+    The per-group count ``#rows with any signal in the group`` (:459) runs on the
+    device for all groups at once.
+    """
+    dev = _as_device(samples)
+    try:
+        p = dev.p
+        if p == 1:                                    # trivial case (:437-439)
+            pep = 1 - dev.column_counts()[0] / dev.N
+            return [CandidateGroup(group=set([0]), pep=pep)]
+        if dist_matrix is None:
+            dist_matrix = _samples_dist_matrix(_gathered_dense(dev))
+        groups = _dist_matrices_to_groups(dist_matrix, **kwargs)
+
+        kept = []
+        for group in groups:
+            gsize = len(group)
+            if gsize > max_size:
+                continue
+            if filter_sequential and np.max(group) - np.min(group) == gsize - 1:
+                continue
+            kept.append(group)
+        counts = dev.group_counts(kept)
+        cand_groups = []
+        for group, cnt in zip(kept, counts):
+            pep = 1 - cnt / dev.N
+            if pep < max_pep:
+                cand_groups.append(CandidateGroup(group=set(group), pep=pep))
+    finally:
+        if dev is not samples:
+            dev.close()
+    return filter_by_purity(cand_groups, min_purity=min_purity, X=X, corr_matrix=corr_matrix)
+
+
+def _gathered_dense(dev):
+    """Dense boolean matrix of a (column-compacted) device sample set, rows of all
+    ranks concatenated in rank order.  Only used to feed the host clustering."""
+    local = dev.to_dense()
+    d = dist._dist()
+    if d is None or d.get_world_size() == 1:
+        return local
+    parts = [None] * d.get_world_size()
+    d.all_gather_object(parts, local)
+    return np.concatenate(parts, axis=0)
+
+
+# ---------------------------------------------------------------------------
+# all candidate groups
+# ---------------------------------------------------------------------------
+def all_cand_groups(
+    samples,
+    X=None,
+    q=0,
+    max_pep=0.25,
+    max_size=25,
+    prenarrow=True,
+    prefilter_thresholds=[0, 0.01, 0.02, 0.03, 0.05, 0.1, 0.2],
+    min_purity=0.0,
+    corr_matrix=None,
+):
+    """
+    Creates many candidate groups by prefiltering locations at various thresholds
+    and then creating sequential and hierarchical candidate groups
+    (create_groups.py:56-149; same parameters, same result).
+    """
+    dev = _as_device(samples)
+    try:
+        marg_pips = dev.column_counts() / dev.N           # :105-106
+        all_groups = set()
+        all_cgs = []
+        for thresh in prefilter_thresholds:
+            rel_features = np.where(marg_pips > thresh)[0]
+            if len(rel_features) == 0:
+                continue
+            sub = dev if len(rel_features) == dev.p else dev.select(rel_features)
+            try:
+                cgs = sequential_groups(sub, q=q, max_pep=max_pep, max_size=max_size,
+                                        prenarrow=prenarrow)
+                dms = [_samples_dist_matrix(_gathered_dense(sub))]
+                if X is not None:
+                    dms.append(np.abs(1 - np.corrcoef(X[:, rel_features].T)))
+                cgs.extend(hierarchical_groups(sub, dist_matrix=dms, max_pep=max_pep,
+                                               max_size=max_size, filter_sequential=True))
+            finally:
+                if sub is not dev:
+                    sub.close()
+            # map the compacted indices back and drop duplicates across thresholds
+            fresh = []
+            for cg in cgs:
+                group = tuple(sorted(rel_features[list(cg.group)].tolist()))
+                if group not in all_groups:
+                    cg.group = set(group)
+                    all_cgs.append(cg)
+                    fresh.append(group)
+            all_groups = all_groups.union(fresh)
+    finally:
+        if dev is not samples:
+            dev.close()
+    return filter_by_purity(all_cgs, min_purity=min_purity, X=X, corr_matrix=corr_matrix)
+
+
+def _prefilter(cand_groups, max_pep):
+    """Returns the subset of cand_groups with a pep below max_pep."""
+    return [x for x in cand_groups if x.pep < max_pep]

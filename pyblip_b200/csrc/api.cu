@@ -1,0 +1,220 @@
+// api.cu -- context, error reporting and design-matrix handling of libblipgpu.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include "internal.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void blip_set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" int blipgpu_abi_version(void) { return BLIPGPU_ABI_VERSION; }
+extern "C" const char* blipgpu_last_error(void) { return g_err; }
+
+extern "C" int blipgpu_device_count(int* count)
+{
+    if (!count) { blip_set_error("count is NULL"); return BLIP_ERR_ARG; }
+    CUDA_TRY(cudaGetDeviceCount(count));
+    return BLIP_OK;
+}
+
+int blip_ctx_activate(blipgpu_ctx* ctx)
+{
+    if (!ctx) { blip_set_error("NULL context"); return BLIP_ERR_ARG; }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    return BLIP_OK;
+}
+
+extern "C" int blipgpu_ctx_create(int device, blipgpu_ctx** out)
+{
+    if (!out) { blip_set_error("out is NULL"); return BLIP_ERR_ARG; }
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) {
+        blip_set_error("device %d out of range (%d CUDA devices visible)", device, ndev);
+        return BLIP_ERR_ARG;
+    }
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        blip_set_error("libblipgpu is built for sm_100a (B200); device %d is sm_%d%d", device,
+                       prop.major, prop.minor);
+        return BLIP_ERR_UNSUPPORTED;
+    }
+    blipgpu_ctx* ctx = new (std::nothrow) blipgpu_ctx();
+    if (!ctx) { blip_set_error("host allocation failed"); return BLIP_ERR_NOMEM; }
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    ctx->sweep_ms = ctx->other_ms = 0.0;
+    ctx->sweep_launches = ctx->other_launches = 0;
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+    *out = ctx;
+    return BLIP_OK;
+}
+
+extern "C" int blipgpu_ctx_destroy(blipgpu_ctx* ctx)
+{
+    if (!ctx) return BLIP_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->stream2);
+    cudaStreamDestroy(ctx->stream);
+    cudaStreamDestroy(ctx->stream2);
+    delete ctx;
+    return BLIP_OK;
+}
+
+extern "C" int blipgpu_ctx_synchronize(blipgpu_ctx* ctx)
+{
+    BLIP_TRY(blip_ctx_activate(ctx));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream2));
+    return BLIP_OK;
+}
+
+extern "C" int blipgpu_ctx_timing(blipgpu_ctx* ctx, double* sweep_ms, int64_t* sweep_launches,
+                                  double* other_ms, int64_t* other_launches, int reset)
+{
+    if (!ctx) { blip_set_error("NULL context"); return BLIP_ERR_ARG; }
+    if (sweep_ms) *sweep_ms = ctx->sweep_ms;
+    if (sweep_launches) *sweep_launches = ctx->sweep_launches;
+    if (other_ms) *other_ms = ctx->other_ms;
+    if (other_launches) *other_launches = ctx->other_launches;
+    if (reset) { ctx->sweep_ms = ctx->other_ms = 0.0; ctx->sweep_launches = ctx->other_launches = 0; }
+    return BLIP_OK;
+}
+
+// ---------------------------------------------------------------------------
+// design upload: X (n x p row-major) -> XT (p x ldx), Xl2
+// ---------------------------------------------------------------------------
+// 32x32 tile transpose through shared memory; coalesced on both sides.
+__global__ void transpose_kernel(const double* __restrict__ X, double* __restrict__ XT, int64_t n,
+                                 int64_t p, int64_t ldx)
+{
+    __shared__ double tile[32][33];
+    const int64_t j0 = (int64_t)blockIdx.x * 32, i0 = (int64_t)blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int64_t i = i0 + r, j = j0 + threadIdx.x;
+        tile[r][threadIdx.x] = (i < n && j < p) ? X[i * p + j] : 0.0;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int64_t j = j0 + r, i = i0 + threadIdx.x;
+        if (j < p && i < ldx) XT[j * ldx + i] = tile[threadIdx.x][r];
+    }
+}
+
+// one warp per column: Xl2[j] = sum_i XT[j][i]^2
+__global__ void xl2_kernel(const double* __restrict__ XT, double* __restrict__ Xl2, int64_t n,
+                           int64_t p, int64_t ldx)
+{
+    const int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (j >= p) return;
+    const double* col = XT + j * ldx;
+    double s = 0.0;
+    for (int64_t i = threadIdx.x & 31; i < n; i += 32) s = fma(col[i], col[i], s);
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) Xl2[j] = s;
+}
+
+extern "C" int blipgpu_design_upload(blipgpu_ctx* ctx, const double* X, int64_t n, int64_t p,
+                                     blipgpu_design** out)
+{
+    BLIP_TRY(blip_ctx_activate(ctx));
+    if (!X || !out || n <= 0 || p <= 0) { blip_set_error("design_upload: bad arguments"); return BLIP_ERR_ARG; }
+    if (p >= (int64_t)1 << 31 || n >= (int64_t)1 << 31) {
+        blip_set_error("design_upload: n and p must be < 2^31"); return BLIP_ERR_ARG;
+    }
+    blipgpu_design* d = new (std::nothrow) blipgpu_design();
+    if (!d) { blip_set_error("host allocation failed"); return BLIP_ERR_NOMEM; }
+    d->ctx = ctx; d->kind = BLIPGPU_DESIGN_DENSE; d->n = n; d->p = p;
+    d->ldx = round_up(n, 4); d->G = nullptr; d->ldg = 0; d->XT = nullptr; d->Xl2 = nullptr;
+    double* Xrow = nullptr;
+    cudaError_t e;
+    if ((e = cudaMalloc(&Xrow, sizeof(double) * n * p)) != cudaSuccess ||
+        (e = cudaMalloc(&d->XT, sizeof(double) * p * d->ldx)) != cudaSuccess ||
+        (e = cudaMalloc(&d->Xl2, sizeof(double) * p)) != cudaSuccess) {
+        blip_set_error("design_upload: cudaMalloc failed: %s", cudaGetErrorString(e));
+        cudaFree(Xrow); cudaFree(d->XT); cudaFree(d->Xl2); delete d;
+        return BLIP_ERR_NOMEM;
+    }
+    CUDA_TRY(cudaMemcpyAsync(Xrow, X, sizeof(double) * n * p, cudaMemcpyHostToDevice, ctx->stream));
+    dim3 grid((unsigned)((p + 31) / 32), (unsigned)((d->ldx + 31) / 32));
+    transpose_kernel<<<grid, dim3(32, 8), 0, ctx->stream>>>(Xrow, d->XT, n, p, d->ldx);
+    xl2_kernel<<<(unsigned)((p + 7) / 8), 256, 0, ctx->stream>>>(d->XT, d->Xl2, n, p, d->ldx);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaFree(Xrow));
+    *out = d;
+    return BLIP_OK;
+}
+
+__global__ void changepoint_xl2_kernel(double* Xl2, int64_t T)
+{
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < T) Xl2[j] = (double)(T - j);   // column j has T-j ones
+}
+
+extern "C" int blipgpu_design_changepoint(blipgpu_ctx* ctx, int64_t T, blipgpu_design** out)
+{
+    BLIP_TRY(blip_ctx_activate(ctx));
+    if (!out || T <= 0 || T >= (int64_t)1 << 31) { blip_set_error("design_changepoint: bad T"); return BLIP_ERR_ARG; }
+    blipgpu_design* d = new (std::nothrow) blipgpu_design();
+    if (!d) { blip_set_error("host allocation failed"); return BLIP_ERR_NOMEM; }
+    d->ctx = ctx; d->kind = BLIPGPU_DESIGN_CHANGEPOINT; d->n = T; d->p = T; d->ldx = 0;
+    d->XT = nullptr; d->G = nullptr; d->ldg = 0;
+    CUDA_TRY(cudaMalloc(&d->Xl2, sizeof(double) * T));
+    changepoint_xl2_kernel<<<(unsigned)((T + 255) / 256), 256, 0, ctx->stream>>>(d->Xl2, T);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    *out = d;
+    return BLIP_OK;
+}
+
+int blip_gram_build(blipgpu_design* d);   // gram.cu
+
+extern "C" int blipgpu_design_build_gram(blipgpu_design* d)
+{
+    if (!d) { blip_set_error("NULL design"); return BLIP_ERR_ARG; }
+    BLIP_TRY(blip_ctx_activate(d->ctx));
+    if (d->kind == BLIPGPU_DESIGN_CHANGEPOINT) return BLIP_OK;  // closed form, nothing stored
+    if (d->G) return BLIP_OK;
+    return blip_gram_build(d);
+}
+
+extern "C" int blipgpu_design_get_gram(blipgpu_design* d, int64_t r0, int64_t r1, double* out)
+{
+    if (!d || !out || r0 < 0 || r1 > d->p || r0 > r1) { blip_set_error("get_gram: bad arguments"); return BLIP_ERR_ARG; }
+    BLIP_TRY(blip_ctx_activate(d->ctx));
+    if (!d->G) { blip_set_error("get_gram: Gram matrix has not been built"); return BLIP_ERR_ARG; }
+    CUDA_TRY(cudaMemcpy2D(out, sizeof(double) * d->p, d->G + r0 * d->ldg, sizeof(double) * d->ldg,
+                          sizeof(double) * d->p, (size_t)(r1 - r0), cudaMemcpyDeviceToHost));
+    return BLIP_OK;
+}
+
+extern "C" int blipgpu_design_get_xl2(blipgpu_design* d, double* out)
+{
+    if (!d || !out) { blip_set_error("get_xl2: bad arguments"); return BLIP_ERR_ARG; }
+    BLIP_TRY(blip_ctx_activate(d->ctx));
+    CUDA_TRY(cudaMemcpy(out, d->Xl2, sizeof(double) * d->p, cudaMemcpyDeviceToHost));
+    return BLIP_OK;
+}
+
+extern "C" int blipgpu_design_free(blipgpu_design* d)
+{
+    if (!d) return BLIP_OK;
+    cudaSetDevice(d->ctx->device);
+    cudaFree(d->XT); cudaFree(d->Xl2); cudaFree(d->G);
+    delete d;
+    return BLIP_OK;
+}

@@ -1,0 +1,205 @@
+// common.cuh -- shared device/host helpers for libblipgpu (sm_100a only).
+//
+// Random-stream contract (DESIGN.md "Stream contract"): every variate is a pure
+// function of (seed, chain, kind, index0, index1, attempt) through
+// Philox4x32-10, so results do not depend on launch geometry, chunking or the
+// number of GPUs.  The CPU oracle implements the same contract independently
+// (oracle/gibbs_oracle.c); the device code below is written from the contract,
+// not from the oracle.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#define BLIP_OK 0
+#define BLIP_ERR_CUDA 1
+#define BLIP_ERR_ARG 2
+#define BLIP_ERR_NOMEM 3
+#define BLIP_ERR_NUMERIC 4   // maps to RuntimeError/ValueError on the Python side
+#define BLIP_ERR_UNSUPPORTED 5
+
+void blip_set_error(const char* fmt, ...);
+
+#define CUDA_TRY(expr)                                                         \
+    do {                                                                       \
+        cudaError_t _e = (expr);                                               \
+        if (_e != cudaSuccess) {                                               \
+            blip_set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__, \
+                           cudaGetErrorString(_e));                            \
+            return BLIP_ERR_CUDA;                                              \
+        }                                                                      \
+    } while (0)
+
+#define BLIP_TRY(expr)                                                         \
+    do {                                                                       \
+        int _rc = (expr);                                                      \
+        if (_rc != BLIP_OK) return _rc;                                        \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// Philox4x32-10
+// ---------------------------------------------------------------------------
+enum : uint32_t {
+    KIND_SPIKE_U = 0,   // c0 = position in permutation, c1 = sweep
+    KIND_SLAB_Z = 1,    // c0 = position in permutation, c1 = sweep
+    KIND_PERM = 2,      // c0 = Fisher-Yates step >> 2,  c1 = sweep
+    KIND_HYPER = 3,     // c0 = slot, c1 = sweep, low 24 bits of c3 = attempt
+    KIND_TRUNCNORM = 4, // c0 = observation, c1 = redraw event, low 24 = attempt
+    KIND_NPRIOR = 5,    // neuronized prior sub-streams (see nprior.cu)
+    KIND_BLOCK = 6      // block sampler sub-streams (see gibbs_block.cu)
+};
+enum : uint32_t { SLOT_INVGAMMA = 0, SLOT_TAU_GAMMA = 1, SLOT_BETA_A = 10, SLOT_BETA_B = 11 };
+
+struct RngKey { uint32_t k0, k1, chain; };
+
+__host__ __device__ __forceinline__ uint4 philox4x32_10(uint32_t k0, uint32_t k1, uint32_t c0,
+                                                        uint32_t c1, uint32_t c2, uint32_t c3)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
+__host__ __device__ __forceinline__ double u52(uint32_t a, uint32_t b)
+{   // uniform strictly inside (0,1) with 52 random bits
+    double v = (double)(a >> 6) * 67108864.0 + (double)(b >> 6);
+    return (v + 0.5) * (1.0 / 4503599627370496.0);
+}
+
+__device__ __forceinline__ double box_muller(uint4 w)
+{
+    double u1 = u52(w.x, w.y);
+    double u2 = u52(w.z, w.w);
+    return sqrt(-2.0 * log(u1)) * cos(6.283185307179586476925286766559 * u2);
+}
+
+__device__ __forceinline__ uint4 rng_words(const RngKey& key, uint32_t kind, uint32_t c0,
+                                           uint32_t c1, uint32_t attempt)
+{
+    return philox4x32_10(key.k0, key.k1, c0, c1, key.chain, (kind << 24) | (attempt & 0xFFFFFFu));
+}
+__device__ __forceinline__ double rng_uniform(const RngKey& key, uint32_t kind, uint32_t c0,
+                                              uint32_t c1, uint32_t attempt)
+{
+    uint4 w = rng_words(key, kind, c0, c1, attempt);
+    return u52(w.x, w.y);
+}
+__device__ __forceinline__ double rng_normal(const RngKey& key, uint32_t kind, uint32_t c0,
+                                             uint32_t c1, uint32_t attempt)
+{
+    return box_muller(rng_words(key, kind, c0, c1, attempt));
+}
+
+// Marsaglia-Tsang Gamma(shape,1) on hyper sub-stream `slot` of sweep `sweep`.
+__device__ inline double rng_gamma(const RngKey& key, uint32_t slot, uint32_t sweep, double shape,
+                                   uint32_t kind = KIND_HYPER)
+{
+    double boost = 1.0;
+    if (shape < 1.0) {
+        double ub = rng_uniform(key, kind, slot, sweep, 0xFFFFFFu);
+        boost = pow(ub, 1.0 / shape);
+        shape += 1.0;
+    }
+    const double d = shape - 1.0 / 3.0;
+    const double c = 1.0 / sqrt(9.0 * d);
+    for (uint32_t t = 0; t < 100000u; ++t) {
+        double x = rng_normal(key, kind, slot, sweep, 2 * t);
+        double v = 1.0 + c * x;
+        if (v <= 0.0) continue;
+        v = v * v * v;
+        double u = rng_uniform(key, kind, slot, sweep, 2 * t + 1);
+        double x2 = x * x;
+        if (u < 1.0 - 0.0331 * x2 * x2) return boost * d * v;
+        if (log(u) < 0.5 * x2 + d * (1.0 - v + log(v))) return boost * d * v;
+    }
+    return boost * d;
+}
+
+__device__ inline double rng_beta(const RngKey& key, uint32_t proposal, uint32_t sweep, double a,
+                                  double b, uint32_t kind = KIND_HYPER)
+{
+    double ga = rng_gamma(key, SLOT_BETA_A + 2 * proposal, sweep, a, kind);
+    double gb = rng_gamma(key, SLOT_BETA_B + 2 * proposal, sweep, b, kind);
+    return ga / (ga + gb);
+}
+
+// Z ~ N(0,1) | Z >= a.  Exponential-proposal rejection for a >= 0.15, normal
+// rejection otherwise: the algorithm of the reference's truncated-normal
+// primitive (/root/reference/pyblip/cython_utils/_truncnorm.pyx:42-86), attempts
+// drawn from the keyed sub-stream (kind, c0, c1).
+__device__ inline double truncnorm_std(const RngKey& key, uint32_t kind, uint32_t c0, uint32_t c1,
+                                       double a)
+{
+    // attempts are capped so that a NaN argument (upstream bug) cannot hang the GPU
+    const uint32_t kMaxAttempts = 1u << 14;
+    uint32_t attempt = 0;
+    if (a >= 0.150) {
+        while (attempt < kMaxAttempts) {
+            uint4 w = rng_words(key, kind, c0, c1, attempt++);
+            double y = u52(w.x, w.y);
+            double u2 = u52(w.z, w.w);
+            y = -1 * log(y) / a;
+            double rho = exp(-0.5 * y * y);
+            if (u2 <= rho) return y + a;
+        }
+    } else {
+        while (attempt < kMaxAttempts) {
+            double z = box_muller(rng_words(key, kind, c0, c1, attempt++));
+            if (a >= 0) z = fabs(z);
+            if (z >= a) return z;
+        }
+    }
+    return nan("");
+}
+
+// sample_truncnorm(mean, var, b, lower_interval)  (_truncnorm.pyx:88-107)
+__device__ inline double truncnorm(const RngKey& key, uint32_t kind, uint32_t c0, uint32_t c1,
+                                   double mean, double var, double b, int lower_interval)
+{
+    double scale = sqrt(var);
+    double a = (b - mean) / scale;
+    double z;
+    if (lower_interval == 0) z = truncnorm_std(key, kind, c0, c1, a);
+    else z = -1 * truncnorm_std(key, kind, c0, c1, -1 * a);
+    return mean + scale * z;
+}
+
+// ---------------------------------------------------------------------------
+// warp / block reductions
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ int warp_sum_int(int v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Sum over the whole block; result returned to every thread.  `scratch` must
+// hold >= 33 doubles of shared memory.  Contains two __syncthreads().
+__device__ __forceinline__ double block_sum(double v, double* scratch)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        double t = (lane < nwarp) ? scratch[lane] : 0.0;
+        t = warp_sum(t);
+        if (lane == 0) scratch[32] = t;
+    }
+    __syncthreads();
+    return scratch[32];
+}

@@ -1,0 +1,437 @@
+// counting.cu -- candidate-group posterior-inclusion counting on bit-packed samples.
+//
+// Replaces the array math of /root/reference/pyblip/create_groups.py:
+//   :105-106  marg_pips = mean(samples != 0, axis=0)            -> count_columns
+//   :321-332  cum_incs / cum_diffs == 0 / mean over rows          -> count_sequential
+//   :459      1 - mean(any(samples[:, group], axis=1))            -> count_groups
+//   :117      samples[:, rel_features]                            -> select_columns
+// Everything is integer counting; the PEP is formed on the host as one correctly
+// rounded divide, so results are bit-identical to the reference's float64 means.
+//
+// Layout: bits[w][row] (word-column major).  A warp owns one 32-column word w and
+// walks rows with lane = row, so every load is a coalesced 128-byte line; per
+// column totals come from a 32x32 in-warp bit transpose followed by popc.
+#include <algorithm>
+#include <new>
+#include <vector>
+#include "internal.cuh"
+
+namespace {
+
+constexpr int CT_BLOCK = 256;
+constexpr int CT_NWARP = CT_BLOCK / 32;
+
+// In-warp 32x32 bit-matrix transpose: on entry lane r holds row r (bit c = column c);
+// on exit lane c holds column c (bit r = row r).
+__device__ __forceinline__ uint32_t warp_transpose32(uint32_t x)
+{
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        // swap the off-diagonal s x s blocks between lane and lane^s
+        const uint32_t mask = (s == 16) ? 0x0000FFFFu : (s == 8) ? 0x00FF00FFu : (s == 4) ? 0x0F0F0F0Fu
+                            : (s == 2) ? 0x33333333u : 0x55555555u;
+        const uint32_t y = __shfl_xor_sync(0xffffffffu, x, s);
+        if (lane & s) x = (x & ~mask) | ((y >> s) & mask);
+        else          x = (x & mask) | ((y << s) & ~mask);
+    }
+    return x;
+}
+
+// ---- dense -> bits -------------------------------------------------------
+template <typename T>
+__global__ void pack_dense_kernel(const T* __restrict__ dense, int64_t nrows, int64_t p, int words,
+                                  int64_t row0, int64_t N_pad, uint32_t* __restrict__ bits)
+{
+    const int64_t gw = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (gw >= nrows * words) return;
+    const int64_t r = gw / words;
+    const int w = (int)(gw % words);
+    const int64_t col = 32LL * w + (threadIdx.x & 31);
+    bool nz = false;
+    if (col < p) nz = dense[r * p + col] != (T)0;
+    const unsigned m = __ballot_sync(0xffffffffu, nz);
+    if ((threadIdx.x & 31) == 0) bits[(int64_t)w * N_pad + row0 + r] = m;
+}
+
+__global__ void clear_first_column_kernel(uint32_t* bits, int64_t N)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < N) bits[r] &= ~1u;
+}
+
+// ---- samples[:, cols] ----------------------------------------------------
+__global__ void select_columns_kernel(const uint32_t* __restrict__ src, int64_t N, int64_t N_pad,
+                                      const int32_t* __restrict__ cols, int ncols, int out_words,
+                                      uint32_t* __restrict__ dst)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int w = blockIdx.y;
+    if (r >= N) return;
+    uint32_t out = 0u;
+    int last_w = -1;
+    uint32_t last = 0u;
+    const int nb = min(32, ncols - 32 * w);
+    for (int b = 0; b < nb; ++b) {
+        const int cidx = cols[32 * w + b];
+        const int sw = cidx >> 5;
+        if (sw != last_w) { last = src[(int64_t)sw * N_pad + r]; last_w = sw; }
+        out |= ((last >> (cidx & 31)) & 1u) << b;
+    }
+    dst[(int64_t)w * N_pad + r] = out;
+}
+
+__global__ void unpack_kernel(const uint32_t* __restrict__ bits, int64_t N, int64_t N_pad, int64_t p,
+                              int64_t row0, int64_t nrows, uint8_t* __restrict__ out)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nrows * p) return;
+    const int64_t r = idx / p, j = idx % p;
+    out[idx] = (bits[(j >> 5) * N_pad + row0 + r] >> (j & 31)) & 1u;
+}
+
+// ---- column counts -------------------------------------------------------
+// grid (words, chunks); each warp walks 32-row tiles of its chunk.
+__global__ void __launch_bounds__(CT_BLOCK) count_columns_kernel(
+    const uint32_t* __restrict__ bits, int64_t N, int64_t N_pad, int64_t p, int64_t rows_per_block,
+    unsigned long long* __restrict__ counts)
+{
+    __shared__ int s_cnt[CT_NWARP][32];
+    const int w = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t r_begin = (int64_t)blockIdx.y * rows_per_block;
+    const int64_t r_end = min(N, r_begin + rows_per_block);
+    const uint32_t* col = bits + (int64_t)w * N_pad;
+    int cnt = 0;
+    for (int64_t r0 = r_begin + 32 * warp; r0 < r_end; r0 += 32 * CT_NWARP) {
+        const int64_t r = r0 + lane;
+        uint32_t x = (r < r_end) ? col[r] : 0u;
+        if (__any_sync(0xffffffffu, x != 0u)) cnt += __popc(warp_transpose32(x));
+    }
+    s_cnt[warp][lane] = cnt;
+    __syncthreads();
+    if (warp == 0) {
+        int t = 0;
+#pragma unroll
+        for (int i = 0; i < CT_NWARP; ++i) t += s_cnt[i][lane];
+        const int64_t j = 32LL * w + lane;
+        if (j < p && t) atomicAdd(counts + j, (unsigned long long)t);
+    }
+}
+
+// ---- sequential (contiguous-window) zero counts --------------------------
+// zero_counts[m][j] = #rows with bits j..j+m all zero, m < max_size, j + m < p.
+template <int MAXM>
+__global__ void __launch_bounds__(CT_BLOCK) count_sequential_kernel(
+    const uint32_t* __restrict__ bits, int64_t N, int64_t N_pad, int64_t p, int words, int max_size,
+    int64_t rows_per_block, unsigned long long* __restrict__ zero_counts)
+{
+    __shared__ int s_cnt[CT_NWARP][32];
+    const int w = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t r_begin = (int64_t)blockIdx.y * rows_per_block;
+    const int64_t r_end = min(N, r_begin + rows_per_block);
+    const uint32_t* c0 = bits + (int64_t)w * N_pad;
+    const uint32_t* c1 = (w + 1 < words) ? bits + (int64_t)(w + 1) * N_pad : nullptr;
+    const uint32_t* c2 = (MAXM > 32 && w + 2 < words) ? bits + (int64_t)(w + 2) * N_pad : nullptr;
+
+    int cnt[MAXM];      // lane b: rows (of the slow tiles) where window (32w+b, m) is all zero
+#pragma unroll
+    for (int m = 0; m < MAXM; ++m) cnt[m] = 0;
+    int zero_rows = 0;  // rows of tiles in which every window of this word is trivially zero
+
+    for (int64_t r0 = r_begin + 32 * warp; r0 < r_end; r0 += 32 * CT_NWARP) {
+        const int64_t r = r0 + lane;
+        const bool live = r < r_end;
+        const uint32_t lo = live ? c0[r] : 0xffffffffu;   // dead rows count for nothing
+        const uint32_t mid = (live && c1) ? c1[r] : 0u;
+        const uint32_t hi = (live && c2) ? c2[r] : 0u;
+        if (!__any_sync(0xffffffffu, (lo | mid | hi) != 0u)) { zero_rows += 32; continue; }
+        uint32_t acc = lo;                                  // OR of bits j..j+m
+#pragma unroll
+        for (int m = 0; m < MAXM; ++m) {
+            if (m < max_size) {
+                if (m > 0) {
+                    uint32_t sh;
+                    if (m < 32) sh = __funnelshift_r(lo, mid, m);
+                    else if (m == 32) sh = mid;
+                    else sh = __funnelshift_r(mid, hi, m - 32);
+                    acc |= sh;
+                }
+                cnt[m] += __popc(warp_transpose32(~acc));
+            }
+        }
+    }
+    // reduce over the warps of the block, then one atomic per (m, column)
+    const int64_t j = 32LL * w + lane;
+#pragma unroll
+    for (int m = 0; m < MAXM; ++m) {
+        if (m < max_size) {                 // uniform
+            __syncthreads();
+            s_cnt[warp][lane] = cnt[m] + zero_rows;
+            __syncthreads();
+            if (warp == 0) {
+                int t = 0;
+#pragma unroll
+                for (int i = 0; i < CT_NWARP; ++i) t += s_cnt[i][lane];
+                if (j + m < p && t) atomicAdd(zero_counts + (int64_t)m * p + j, (unsigned long long)t);
+            }
+        }
+    }
+}
+
+// ---- arbitrary groups: any(samples[:, group]) ---------------------------
+// grid (groups, chunks); lane = row.
+__global__ void __launch_bounds__(CT_BLOCK) count_groups_kernel(
+    const uint32_t* __restrict__ bits, int64_t N, int64_t N_pad, const int64_t* __restrict__ offsets,
+    const int32_t* __restrict__ members, int64_t rows_per_block, unsigned long long* __restrict__ any_counts)
+{
+    __shared__ int s_cnt[CT_NWARP];
+    const int g = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t m0 = offsets[g], m1 = offsets[g + 1];
+    const int64_t r_begin = (int64_t)blockIdx.y * rows_per_block;
+    const int64_t r_end = min(N, r_begin + rows_per_block);
+    int cnt = 0;
+    for (int64_t r = r_begin + threadIdx.x; r < r_end; r += CT_BLOCK) {
+        uint32_t any = 0u;
+        for (int64_t k = m0; k < m1; ++k) {
+            const int cidx = members[k];
+            any |= (bits[(int64_t)(cidx >> 5) * N_pad + r] >> (cidx & 31)) & 1u;
+        }
+        cnt += (int)any;
+    }
+    cnt = warp_sum_int(cnt);
+    if (lane == 0) s_cnt[warp] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int i = 0; i < CT_NWARP; ++i) t += s_cnt[i];
+        if (t) atomicAdd(any_counts + g, (unsigned long long)t);
+    }
+}
+
+int alloc_bits(blipgpu_ctx* ctx, int64_t N, int64_t p, blipgpu_bits** out)
+{
+    blipgpu_bits* b = new (std::nothrow) blipgpu_bits();
+    if (!b) { blip_set_error("host allocation failed"); return BLIP_ERR_NOMEM; }
+    b->ctx = ctx; b->N = N; b->N_pad = round_up(std::max<int64_t>(N, 1), 32); b->p = p;
+    b->words = (p + 31) / 32; b->owns = true; b->bits = nullptr;
+    const size_t bytes = sizeof(uint32_t) * std::max<int64_t>(b->words, 1) * b->N_pad;
+    cudaError_t e = cudaMalloc(&b->bits, bytes);
+    if (e != cudaSuccess) { delete b; blip_set_error("bits allocation (%zu bytes) failed: %s", bytes, cudaGetErrorString(e)); return BLIP_ERR_NOMEM; }
+    e = cudaMemsetAsync(b->bits, 0, bytes, ctx->stream);
+    if (e != cudaSuccess) { cudaFree(b->bits); delete b; blip_set_error("memset failed: %s", cudaGetErrorString(e)); return BLIP_ERR_CUDA; }
+    *out = b;
+    return BLIP_OK;
+}
+
+int64_t pick_rows_per_block(int64_t N, int64_t columns_of_blocks, int sm_count)
+{
+    // enough blocks to fill the machine a few times, but >= 2048 rows each so that the
+    // per-block atomics stay negligible
+    const int64_t target_blocks = 8LL * sm_count;
+    int64_t chunks = std::max<int64_t>(1, target_blocks / std::max<int64_t>(1, columns_of_blocks));
+    int64_t rpb = round_up((N + chunks - 1) / chunks, 32 * CT_NWARP);
+    rpb = std::max<int64_t>(rpb, 2048);
+    return rpb;
+}
+
+// run `launch(dev_counts)` into either the caller's device buffer or a temporary
+template <class F>
+int with_output(blipgpu_ctx* ctx, int64_t count, int64_t* out, int out_is_device, F launch)
+{
+    unsigned long long* dev = nullptr;
+    bool temp = !out_is_device;
+    if (temp) {
+        cudaError_t e = cudaMalloc(&dev, sizeof(unsigned long long) * std::max<int64_t>(count, 1));
+        if (e != cudaSuccess) { blip_set_error("count buffer allocation failed: %s", cudaGetErrorString(e)); return BLIP_ERR_NOMEM; }
+    } else dev = reinterpret_cast<unsigned long long*>(out);
+    int rc = BLIP_OK;
+    cudaError_t e = cudaMemsetAsync(dev, 0, sizeof(unsigned long long) * count, ctx->stream);
+    if (e == cudaSuccess) {
+        ScopedTimer timer(ctx, false);
+        launch(dev);
+        e = cudaGetLastError();
+        timer.stop(1);
+    }
+    if (e == cudaSuccess && temp) e = cudaMemcpyAsync(out, dev, sizeof(int64_t) * count, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { blip_set_error("counting kernel failed: %s", cudaGetErrorString(e)); rc = BLIP_ERR_CUDA; }
+    if (temp) cudaFree(dev);
+    return rc;
+}
+
+} // namespace
+
+extern "C" int blipgpu_bits_from_samples(blipgpu_samples* s, int32_t zero_first_column, blipgpu_bits** out)
+{
+    if (!s || !out) { blip_set_error("bits_from_samples: bad arguments"); return BLIP_ERR_ARG; }
+    BLIP_TRY(blip_ctx_activate(s->ctx));
+    blipgpu_bits* b = nullptr;
+    BLIP_TRY(alloc_bits(s->ctx, s->rows, s->p, &b));
+    cudaStream_t st = s->ctx->stream;
+    // same layout and the same row padding (rows_pad == N_pad): one device copy
+    cudaError_t e = cudaMemcpyAsync(b->bits, s->bits, sizeof(uint32_t) * s->words * s->rows_pad, cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess && zero_first_column)
+        clear_first_column_kernel<<<(unsigned)((s->rows + 255) / 256), 256, 0, st>>>(b->bits, s->rows);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { blipgpu_bits_free(b); blip_set_error("bits_from_samples: %s", cudaGetErrorString(e)); return BLIP_ERR_CUDA; }
+    *out = b;
+    return BLIP_OK;
+}
+
+extern "C" int blipgpu_bits_from_dense(blipgpu_ctx* ctx, const void* samples, int32_t dtype, int64_t N,
+                                       int64_t p, blipgpu_bits** out)
+{
+    BLIP_TRY(blip_ctx_activate(ctx));
+    if (!out || N < 0 || p <= 0 || (N > 0 && !samples) || p >= (int64_t)1 << 31) { blip_set_error("bits_from_dense: bad arguments"); return BLIP_ERR_ARG; }
+    if (dtype != BLIPGPU_DTYPE_F64 && dtype != BLIPGPU_DTYPE_U8) { blip_set_error("bits_from_dense: unknown dtype %d", dtype); return BLIP_ERR_ARG; }
+    blipgpu_bits* b = nullptr;
+    BLIP_TRY(alloc_bits(ctx, N, p, &b));
+    if (N == 0) { CUDA_TRY(cudaStreamSynchronize(ctx->stream)); *out = b; return BLIP_OK; }
+    const size_t esz = dtype == BLIPGPU_DTYPE_F64 ? 8 : 1;
+    const int64_t stage_rows = std::min<int64_t>(N, std::max<int64_t>(1, (int64_t)(256 << 20) / (int64_t)(esz * p)));
+    void* stage = nullptr;
+    cudaError_t e = cudaMalloc(&stage, esz * stage_rows * p);
+    if (e != cudaSuccess) { blipgpu_bits_free(b); blip_set_error("bits_from_dense: staging allocation failed: %s", cudaGetErrorString(e)); return BLIP_ERR_NOMEM; }
+    cudaStream_t st = ctx->stream;
+    for (int64_t r = 0; r < N && e == cudaSuccess; r += stage_rows) {
+        const int64_t nr = std::min<int64_t>(stage_rows, N - r);
+        e = cudaMemcpyAsync(stage, (const char*)samples + esz * r * p, esz * nr * p, cudaMemcpyHostToDevice, st);
+        const int64_t nwarps = nr * b->words;
+        const unsigned grid = (unsigned)((nwarps + 7) / 8);
+        if (dtype == BLIPGPU_DTYPE_F64)
+            pack_dense_kernel<double><<<grid, 256, 0, st>>>((const double*)stage, nr, p, (int)b->words, r, b->N_pad, b->bits);
+        else
+            pack_dense_kernel<uint8_t><<<grid, 256, 0, st>>>((const uint8_t*)stage, nr, p, (int)b->words, r, b->N_pad, b->bits);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    cudaFree(stage);
+    if (e != cudaSuccess) { blipgpu_bits_free(b); blip_set_error("bits_from_dense: %s", cudaGetErrorString(e)); return BLIP_ERR_CUDA; }
+    *out = b;
+    return BLIP_OK;
+}
+
+extern "C" int blipgpu_bits_shape(blipgpu_bits* b, int64_t* N, int64_t* p)
+{
+    if (!b) { blip_set_error("bits_shape: NULL handle"); return BLIP_ERR_ARG; }
+    if (N) *N = b->N;
+    if (p) *p = b->p;
+    return BLIP_OK;
+}
+
+extern "C" int blipgpu_bits_select_columns(blipgpu_bits* b, const int64_t* cols, int64_t ncols, blipgpu_bits** out)
+{
+    if (!b || !out || ncols <= 0 || !cols) { blip_set_error("select_columns: bad arguments"); return BLIP_ERR_ARG; }
+    BLIP_TRY(blip_ctx_activate(b->ctx));
+    std::vector<int32_t> c32((size_t)ncols);
+    for (int64_t i = 0; i < ncols; ++i) {
+        if (cols[i] < 0 || cols[i] >= b->p) { blip_set_error("select_columns: column %lld out of range", (long long)cols[i]); return BLIP_ERR_ARG; }
+        c32[(size_t)i] = (int32_t)cols[i];
+    }
+    blipgpu_bits* o = nullptr;
+    BLIP_TRY(alloc_bits(b->ctx, b->N, ncols, &o));
+    int32_t* d_cols = nullptr;
+    cudaStream_t st = b->ctx->stream;
+    cudaError_t e = cudaMalloc(&d_cols, sizeof(int32_t) * ncols);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_cols, c32.data(), sizeof(int32_t) * ncols, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && b->N > 0) {
+        dim3 grid((unsigned)((b->N + 255) / 256), (unsigned)o->words);
+        select_columns_kernel<<<grid, 256, 0, st>>>(b->bits, b->N, b->N_pad, d_cols, (int)ncols, (int)o->words, o->bits);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_cols);
+    if (e != cudaSuccess) { blipgpu_bits_free(o); blip_set_error("select_columns: %s", cudaGetErrorString(e)); return BLIP_ERR_CUDA; }
+    *out = o;
+    return BLIP_OK;
+}
+
+extern "C" int blipgpu_bits_to_dense(blipgpu_bits* b, uint8_t* out)
+{
+    if (!b || (!out && b->N > 0)) { blip_set_error("bits_to_dense: bad arguments"); return BLIP_ERR_ARG; }
+    BLIP_TRY(blip_ctx_activate(b->ctx));
+    if (b->N == 0) return BLIP_OK;
+    const int64_t stage_rows = std::min<int64_t>(b->N, std::max<int64_t>(1, (int64_t)(256 << 20) / b->p));
+    uint8_t* stage = nullptr;
+    CUDA_TRY(cudaMalloc(&stage, (size_t)stage_rows * b->p));
+    cudaStream_t st = b->ctx->stream;
+    cudaError_t e = cudaSuccess;
+    for (int64_t r = 0; r < b->N && e == cudaSuccess; r += stage_rows) {
+        const int64_t nr = std::min<int64_t>(stage_rows, b->N - r);
+        unpack_kernel<<<(unsigned)((nr * b->p + 255) / 256), 256, 0, st>>>(b->bits, b->N, b->N_pad, b->p, r, nr, stage);
+        e = cudaMemcpyAsync(out + r * b->p, stage, (size_t)nr * b->p, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    cudaFree(stage);
+    if (e != cudaSuccess) { blip_set_error("bits_to_dense: %s", cudaGetErrorString(e)); return BLIP_ERR_CUDA; }
+    return BLIP_OK;
+}
+
+extern "C" int blipgpu_count_columns(blipgpu_bits* b, int64_t* counts, int32_t out_is_device)
+{
+    if (!b || !counts) { blip_set_error("count_columns: bad arguments"); return BLIP_ERR_ARG; }
+    BLIP_TRY(blip_ctx_activate(b->ctx));
+    const int64_t rpb = pick_rows_per_block(b->N, b->words, b->ctx->sm_count);
+    const unsigned chunks = (unsigned)std::max<int64_t>(1, (b->N + rpb - 1) / rpb);
+    return with_output(b->ctx, b->p, counts, out_is_device, [&](unsigned long long* dev) {
+        if (b->N > 0)
+            count_columns_kernel<<<dim3((unsigned)b->words, chunks), CT_BLOCK, 0, b->ctx->stream>>>(b->bits, b->N, b->N_pad, b->p, rpb, dev);
+    });
+}
+
+extern "C" int blipgpu_count_sequential(blipgpu_bits* b, int32_t max_size, int64_t* zero_counts, int32_t out_is_device)
+{
+    if (!b || !zero_counts || max_size <= 0) { blip_set_error("count_sequential: bad arguments"); return BLIP_ERR_ARG; }
+    if (max_size > 64) { blip_set_error("count_sequential: max_size %d > 64 is not supported", max_size); return BLIP_ERR_UNSUPPORTED; }
+    BLIP_TRY(blip_ctx_activate(b->ctx));
+    const int64_t rpb = pick_rows_per_block(b->N, b->words, b->ctx->sm_count);
+    const unsigned chunks = (unsigned)std::max<int64_t>(1, (b->N + rpb - 1) / rpb);
+    return with_output(b->ctx, (int64_t)max_size * b->p, zero_counts, out_is_device, [&](unsigned long long* dev) {
+        if (b->N == 0) return;
+        dim3 grid((unsigned)b->words, chunks);
+        if (max_size <= 32)
+            count_sequential_kernel<32><<<grid, CT_BLOCK, 0, b->ctx->stream>>>(b->bits, b->N, b->N_pad, b->p, (int)b->words, max_size, rpb, dev);
+        else
+            count_sequential_kernel<64><<<grid, CT_BLOCK, 0, b->ctx->stream>>>(b->bits, b->N, b->N_pad, b->p, (int)b->words, max_size, rpb, dev);
+    });
+}
+
+extern "C" int blipgpu_count_groups(blipgpu_bits* b, const int64_t* offsets, const int64_t* members,
+                                    int64_t n_groups, int64_t* any_counts, int32_t out_is_device)
+{
+    if (!b || n_groups < 0 || (n_groups > 0 && (!offsets || !members || !any_counts))) { blip_set_error("count_groups: bad arguments"); return BLIP_ERR_ARG; }
+    BLIP_TRY(blip_ctx_activate(b->ctx));
+    if (n_groups == 0) return BLIP_OK;
+    const int64_t total = offsets[n_groups];
+    std::vector<int32_t> m32((size_t)std::max<int64_t>(total, 1));
+    for (int64_t i = 0; i < total; ++i) {
+        if (members[i] < 0 || members[i] >= b->p) { blip_set_error("count_groups: member %lld out of range", (long long)members[i]); return BLIP_ERR_ARG; }
+        m32[(size_t)i] = (int32_t)members[i];
+    }
+    int64_t* d_off = nullptr; int32_t* d_mem = nullptr;
+    cudaStream_t st = b->ctx->stream;
+    cudaError_t e = cudaMalloc(&d_off, sizeof(int64_t) * (n_groups + 1));
+    if (e == cudaSuccess) e = cudaMalloc(&d_mem, sizeof(int32_t) * std::max<int64_t>(total, 1));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_off, offsets, sizeof(int64_t) * (n_groups + 1), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && total > 0) e = cudaMemcpyAsync(d_mem, m32.data(), sizeof(int32_t) * total, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) { cudaFree(d_off); cudaFree(d_mem); blip_set_error("count_groups: %s", cudaGetErrorString(e)); return BLIP_ERR_CUDA; }
+    const int64_t rpb = pick_rows_per_block(b->N, n_groups, b->ctx->sm_count);
+    const unsigned chunks = (unsigned)std::max<int64_t>(1, (b->N + rpb - 1) / rpb);
+    int rc = with_output(b->ctx, n_groups, any_counts, out_is_device, [&](unsigned long long* dev) {
+        if (b->N == 0) return;
+        // grid.x is limited to 2^31-1 groups; grid.y to 65535 chunks
+        count_groups_kernel<<<dim3((unsigned)n_groups, chunks), CT_BLOCK, 0, st>>>(b->bits, b->N, b->N_pad, d_off, d_mem, rpb, dev);
+    });
+    cudaFree(d_off); cudaFree(d_mem);
+    return rc;
+}
+
+extern "C" int blipgpu_bits_free(blipgpu_bits* b)
+{
+    if (!b) return BLIP_OK;
+    cudaSetDevice(b->ctx->device);
+    if (b->owns) cudaFree(b->bits);
+    delete b;
+    return BLIP_OK;
+}

@@ -1,0 +1,420 @@
+// gibbs.cu -- host orchestration of the multi-chain spike-and-slab sampler.
+//
+// Replaces the reference's chain fan-out `apply_pool(_sample_spikeslab, ...)`
+// (/root/reference/pyblip/utilities.py:63-139, linear/linear.py:159-164,
+// probit/probit.py:89-94): all chains of this rank run as one grid, one CTA per
+// chain, in launches of `chunk_sweeps` sweeps.  Permutations for the next chunk
+// are generated on a second stream while the current chunk sweeps.
+#include <algorithm>
+#include <cstdio>
+#include <new>
+#include <vector>
+#include "gibbs_kernels.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------------------
+// permutations: one thread per (chain, sweep) runs Fisher-Yates from identity,
+// Philox words indexed by (step >> 2, sweep, chain).
+// ---------------------------------------------------------------------------
+__global__ void perm_fill_kernel(int32_t* perm, int chains, int S, int p, int sweep0, uint32_t k0,
+                                 uint32_t k1, uint32_t chain_offset)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)chains * S) return;
+    const int c = (int)(t / S), s = (int)(t % S);
+    int32_t* a = perm + t * p;
+    for (int j = 0; j < p; ++j) a[j] = j;
+    const uint32_t chain = chain_offset + (uint32_t)c, sweep = (uint32_t)(sweep0 + s);
+    uint4 w = make_uint4(0, 0, 0, 0);
+    int have = -1;
+    for (int k = p - 1; k >= 1; --k) {
+        if ((k >> 2) != have) {
+            have = k >> 2;
+            w = philox4x32_10(k0, k1, (uint32_t)have, sweep, chain, KIND_PERM << 24);
+        }
+        const int sel = k & 3;
+        const uint32_t x = sel == 0 ? w.x : sel == 1 ? w.y : sel == 2 ? w.z : w.w;
+        const int j = (int)(((uint64_t)x * (uint64_t)(k + 1)) >> 32);
+        int32_t tmp = a[k]; a[k] = a[j]; a[j] = tmp;
+    }
+}
+
+// q0[j] = X_j . y   (one warp per column)
+__global__ void xty_kernel(const double* __restrict__ XT, const double* __restrict__ y,
+                           double* __restrict__ q0, int64_t n, int64_t p, int64_t ldx)
+{
+    const int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (j >= p) return;
+    const double* col = XT + j * ldx;
+    double s = 0.0;
+    for (int64_t i = threadIdx.x & 31; i < n; i += 32) s = fma(col[i], y[i], s);
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) q0[j] = s;
+}
+
+// initial chain state: beta = 0 (memset), r = y or first probit latents (:117-124)
+__global__ void init_state_kernel(SweepParams P, const double* __restrict__ y, int probit, int gram)
+{
+    const int c = blockIdx.x, tid = threadIdx.x;
+    const RngKey key = { P.k0, P.k1, P.chain_offset + (uint32_t)c };
+    if (gram) {
+        for (int k = tid; k < P.p2; k += blockDim.x) P.q[(int64_t)c * P.p2 + k] = k < P.p ? P.q0[k] : 0.0;
+    } else {
+        for (int k = tid; k < P.n2; k += blockDim.x) {
+            double yv = 0.0, rv = 0.0;
+            if (k < P.n) {
+                if (probit) {
+                    yv = truncnorm(key, KIND_TRUNCNORM, (uint32_t)k, 0u, 0.0, P.cfg.sigma2, 0.0, P.zlab[k]);
+                    rv = yv;             // r = y - mu with mu = 0
+                } else {
+                    rv = y[k];
+                }
+            }
+            P.r[(int64_t)c * P.n2 + k] = rv;
+            if (probit) { P.mu[(int64_t)c * P.n2 + k] = 0.0; P.ylat[(int64_t)c * P.n2 + k] = yv; }
+        }
+    }
+    if (tid == 0) {
+        P.hstate[4 * c + 0] = P.cfg.sigma2; P.hstate[4 * c + 1] = P.cfg.tau2;
+        P.hstate[4 * c + 2] = P.cfg.p0;     P.hstate[4 * c + 3] = P.yy;
+        if (probit) { P.events[2 * c] = 1u; P.events[2 * c + 1] = 1u; }
+    }
+}
+
+struct DevBuf {
+    void* ptr = nullptr; size_t bytes = 0;
+    int alloc(size_t b) {
+        bytes = b;
+        if (b == 0) { ptr = nullptr; return BLIP_OK; }
+        cudaError_t e = cudaMalloc(&ptr, b);
+        if (e != cudaSuccess) {
+            ptr = nullptr;
+            blip_set_error("cudaMalloc(%zu bytes) failed: %s", b, cudaGetErrorString(e));
+            return BLIP_ERR_NOMEM;
+        }
+        return BLIP_OK;
+    }
+    ~DevBuf() { if (ptr) cudaFree(ptr); }
+    template <class T> T* as() { return reinterpret_cast<T*>(ptr); }
+};
+
+template <class T>
+int upload_chunk(T* dst, const T* src_host, int64_t chains, int64_t total_per_chain,
+                 int64_t off_per_chain, int64_t count_per_chain, cudaStream_t st)
+{   // host [chains][total] -> device [chains][count], starting at `off` inside every chain
+    CUDA_TRY(cudaMemcpy2DAsync(dst, sizeof(T) * count_per_chain, src_host + off_per_chain,
+                               sizeof(T) * total_per_chain, sizeof(T) * count_per_chain,
+                               (size_t)chains, cudaMemcpyHostToDevice, st));
+    return BLIP_OK;
+}
+
+} // namespace
+
+extern "C" int blipgpu_sample_spikeslab(blipgpu_ctx* ctx, blipgpu_design* design,
+                                        const blipgpu_spikeslab_config* cfg, const double* y,
+                                        const int64_t* z, int32_t probit, int64_t chains,
+                                        int64_t chain_offset, int64_t n_keep, int64_t burn,
+                                        uint64_t seed, const blipgpu_streams* streams,
+                                        const blipgpu_sample_options* opts, blipgpu_samples** out)
+{
+    BLIP_TRY(blip_ctx_activate(ctx));
+    if (!design || !cfg || !out || chains <= 0 || n_keep <= 0 || burn < 0) {
+        blip_set_error("sample_spikeslab: bad arguments"); return BLIP_ERR_ARG;
+    }
+    if (design->ctx != ctx) { blip_set_error("sample_spikeslab: design belongs to another context"); return BLIP_ERR_ARG; }
+    if (probit ? !z : !y) { blip_set_error("sample_spikeslab: %s is NULL", probit ? "z" : "y"); return BLIP_ERR_ARG; }
+    const int64_t n = design->n, p = design->p;
+    const int64_t n_total = n_keep + burn;
+    if (n_total >= (int64_t)1 << 31 || chains * n_keep >= (int64_t)1 << 40) {
+        blip_set_error("sample_spikeslab: too many sweeps"); return BLIP_ERR_ARG;
+    }
+    if (streams && (streams->u || streams->z) && !streams->perm) {
+        // allowed: injected u/z with keyed permutations
+    }
+    int mode = opts ? opts->mode : BLIPGPU_MODE_AUTO;
+    if (mode == BLIPGPU_MODE_AUTO) {
+        if (probit) mode = BLIPGPU_MODE_RESIDUAL;
+        else if (design->kind == BLIPGPU_DESIGN_CHANGEPOINT) mode = BLIPGPU_MODE_GRAM;
+        else {
+            size_t free_b = 0, total_b = 0;
+            CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+            const double gram_bytes = 8.0 * (double)p * (double)round_up(p, 4);
+            mode = (design->G || gram_bytes < 0.5 * (double)free_b) ? BLIPGPU_MODE_GRAM : BLIPGPU_MODE_RESIDUAL;
+        }
+    }
+    if (probit && mode == BLIPGPU_MODE_GRAM) {
+        blip_set_error("sample_spikeslab: probit needs residual mode (every change redraws all latents)");
+        return BLIP_ERR_ARG;
+    }
+    if (design->kind == BLIPGPU_DESIGN_CHANGEPOINT && mode != BLIPGPU_MODE_GRAM) {
+        blip_set_error("sample_spikeslab: the structured change-point design only supports gram mode");
+        return BLIP_ERR_ARG;
+    }
+    const bool gram = mode == BLIPGPU_MODE_GRAM;
+    if (gram && design->kind == BLIPGPU_DESIGN_DENSE) BLIP_TRY(blipgpu_design_build_gram(design));
+
+    const int64_t words = (p + 31) / 32, n2 = round_up(n, 2), p2 = round_up(p, 2);
+
+    // ---- shared memory budget -> kernel variant
+    size_t smem = 0;
+    bool qsmem = true;
+    if (gram) {
+        smem = sizeof(double) * p2 + sizeof(uint32_t) * words;
+        if (smem > ctx->smem_optin) { qsmem = false; smem = sizeof(uint32_t) * words; }
+    } else {
+        smem = sizeof(double) * ((probit ? 3 : 1) * n2 + GB_NWARP * 32 + 40) + sizeof(uint32_t) * words;
+    }
+    if (smem > ctx->smem_optin) {
+        blip_set_error("sample_spikeslab: problem too large for %s mode (needs %zu bytes of shared "
+                       "memory per chain, device allows %zu)", gram ? "gram" : "residual", smem, ctx->smem_optin);
+        return BLIP_ERR_UNSUPPORTED;
+    }
+
+    // ---- chunking
+    int S = opts && opts->chunk_sweeps > 0 ? opts->chunk_sweeps : 32;
+    {
+        const double perm_bytes_per_sweep = 4.0 * (double)chains * (double)p;
+        const int cap = (int)std::max(1.0, 1.0e9 / perm_bytes_per_sweep);
+        if (!(opts && opts->chunk_sweeps > 0)) S = std::min(S, cap);
+        S = (int)std::min<int64_t>(S, n_total);
+    }
+    const bool inj_perm = streams && streams->perm;
+    const bool inj_u = streams && streams->u, inj_z = streams && streams->z;
+    const bool inj_ig = streams && streams->invgamma, inj_p0 = streams && streams->p0_draw;
+    const bool inj_g = streams && streams->gamma_draw;
+    const int nprop = streams ? std::max(1, (int)streams->nprop) : 1;
+    if (inj_p0 && cfg->min_p0 != 0 && nprop < 100) {
+        blip_set_error("sample_spikeslab: min_p0 > 0 needs 100 injected Beta proposals per sweep");
+        return BLIP_ERR_ARG;
+    }
+
+    // ---- allocate
+    DevBuf d_beta, d_r, d_mu, d_ylat, d_q, d_h, d_mask, d_ev, d_q0, d_y, d_z, d_ovf;
+    DevBuf d_perm[2], d_u, d_zn, d_ig, d_p0, d_g;
+    DevBuf snap_beta, snap_r, snap_mu, snap_ylat, snap_q, snap_h, snap_mask, snap_ev;
+    BLIP_TRY(d_beta.alloc(sizeof(double) * chains * p));
+    BLIP_TRY(d_h.alloc(sizeof(double) * chains * 4));
+    BLIP_TRY(d_mask.alloc(sizeof(uint32_t) * chains * words));
+    BLIP_TRY(d_ovf.alloc(sizeof(int)));
+    BLIP_TRY(snap_beta.alloc(d_beta.bytes)); BLIP_TRY(snap_h.alloc(d_h.bytes)); BLIP_TRY(snap_mask.alloc(d_mask.bytes));
+    if (gram) {
+        BLIP_TRY(d_q.alloc(sizeof(double) * chains * p2)); BLIP_TRY(snap_q.alloc(d_q.bytes));
+        BLIP_TRY(d_q0.alloc(sizeof(double) * p));
+    } else {
+        BLIP_TRY(d_r.alloc(sizeof(double) * chains * n2)); BLIP_TRY(snap_r.alloc(d_r.bytes));
+        if (probit) {
+            BLIP_TRY(d_mu.alloc(d_r.bytes)); BLIP_TRY(d_ylat.alloc(d_r.bytes));
+            BLIP_TRY(snap_mu.alloc(d_r.bytes)); BLIP_TRY(snap_ylat.alloc(d_r.bytes));
+            BLIP_TRY(d_ev.alloc(sizeof(uint32_t) * chains * 2)); BLIP_TRY(snap_ev.alloc(d_ev.bytes));
+            BLIP_TRY(d_z.alloc(sizeof(int32_t) * n));
+        }
+    }
+    if (!probit) BLIP_TRY(d_y.alloc(sizeof(double) * n));
+    BLIP_TRY(d_perm[0].alloc(sizeof(int32_t) * chains * S * p));
+    if (!inj_perm && n_total > S) BLIP_TRY(d_perm[1].alloc(sizeof(int32_t) * chains * S * p));
+    if (inj_u) BLIP_TRY(d_u.alloc(sizeof(double) * chains * S * p));
+    if (inj_z) BLIP_TRY(d_zn.alloc(sizeof(double) * chains * S * p));
+    if (inj_ig) BLIP_TRY(d_ig.alloc(sizeof(double) * chains * S));
+    if (inj_p0) BLIP_TRY(d_p0.alloc(sizeof(double) * chains * S * nprop));
+    if (inj_g) BLIP_TRY(d_g.alloc(sizeof(double) * chains * S));
+
+    blipgpu_samples* smp = new (std::nothrow) blipgpu_samples();
+    if (!smp) { blip_set_error("host allocation failed"); return BLIP_ERR_NOMEM; }
+    smp->ctx = ctx; smp->rows = chains * n_keep; smp->rows_pad = round_up(smp->rows, 32);
+    smp->p = p; smp->n = n; smp->chains = chains; smp->n_keep = n_keep; smp->words = words;
+    smp->bits = nullptr; smp->row_off = nullptr; smp->row_nnz = nullptr; smp->values = nullptr;
+    smp->arena_used = nullptr; smp->hyper = nullptr; smp->latents = nullptr;
+    smp->n_events = 0; smp->mode = mode; smp->sweep_ms = 0.0; smp->sweep_launches = 0;
+    struct Guard { blipgpu_samples* s; ~Guard() { if (s) blipgpu_samples_free(s); } } guard{ smp };
+    const bool keep_lat = probit && (!opts || opts->keep_latents != 0);
+    {
+        cudaError_t e;
+        if ((e = cudaMalloc(&smp->bits, sizeof(uint32_t) * words * smp->rows_pad)) != cudaSuccess ||
+            (e = cudaMalloc(&smp->row_off, sizeof(int64_t) * smp->rows)) != cudaSuccess ||
+            (e = cudaMalloc(&smp->row_nnz, sizeof(int32_t) * smp->rows)) != cudaSuccess ||
+            (e = cudaMalloc(&smp->hyper, sizeof(double) * 3 * smp->rows)) != cudaSuccess ||
+            (e = cudaMalloc(&smp->arena_used, sizeof(unsigned long long))) != cudaSuccess ||
+            (keep_lat && (e = cudaMalloc(&smp->latents, sizeof(double) * smp->rows * n)) != cudaSuccess)) {
+            blip_set_error("sample_spikeslab: cannot allocate the sample store: %s", cudaGetErrorString(e));
+            return BLIP_ERR_NOMEM;
+        }
+    }
+    cudaStream_t st = ctx->stream, st2 = ctx->stream2;
+    CUDA_TRY(cudaMemsetAsync(smp->bits, 0, sizeof(uint32_t) * words * smp->rows_pad, st));
+    CUDA_TRY(cudaMemsetAsync(smp->arena_used, 0, sizeof(unsigned long long), st));
+    if (keep_lat) CUDA_TRY(cudaMemsetAsync(smp->latents, 0, sizeof(double) * smp->rows * n, st));
+    smp->arena_cap = std::max<int64_t>(chains * (int64_t)std::min<int64_t>(S, n_keep) * std::max<int64_t>(64, p / 16), 1 << 16);
+    CUDA_TRY(cudaMalloc(&smp->values, sizeof(double) * smp->arena_cap));
+
+    // ---- parameters
+    SweepParams P;
+    memset(&P, 0, sizeof(P));
+    P.XT = design->XT; P.ldx = design->ldx; P.Xl2 = design->Xl2; P.G = design->G; P.ldg = design->ldg;
+    P.n = (int)n; P.p = (int)p; P.words = (int)words; P.n2 = (int)n2; P.p2 = (int)p2;
+    P.cfg = *cfg;
+    P.beta = d_beta.as<double>(); P.r = d_r.as<double>(); P.mu = d_mu.as<double>();
+    P.ylat = d_ylat.as<double>(); P.q = d_q.as<double>(); P.hstate = d_h.as<double>();
+    P.mask = d_mask.as<uint32_t>(); P.events = d_ev.as<uint32_t>();
+    P.q0 = d_q0.as<double>(); P.zlab = d_z.as<int32_t>();
+    P.k0 = (uint32_t)seed; P.k1 = (uint32_t)(seed >> 32); P.chain_offset = (uint32_t)chain_offset;
+    P.nprop = nprop; P.burn = (int)burn; P.n_keep = (int)n_keep;
+    P.bits = smp->bits; P.rows = smp->rows; P.rows_pad = smp->rows_pad;
+    P.row_off = smp->row_off; P.row_nnz = smp->row_nnz; P.values = smp->values;
+    P.arena_cap = smp->arena_cap; P.arena_used = smp->arena_used; P.overflow = d_ovf.as<int>();
+    P.hyper_out = smp->hyper; P.latents = smp->latents;
+    P.gram_refresh = opts && opts->gram_refresh > 0 ? opts->gram_refresh : (opts && opts->gram_refresh < 0 ? 0 : 128);
+
+    // ---- data upload and initial state
+    double yy = 0.0;
+    if (!probit) {
+        for (int64_t i = 0; i < n; ++i) yy += y[i] * y[i];
+        CUDA_TRY(cudaMemcpyAsync(d_y.ptr, y, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    } else {
+        std::vector<int32_t> z32((size_t)n);
+        for (int64_t i = 0; i < n; ++i) z32[(size_t)i] = (int32_t)z[i];
+        CUDA_TRY(cudaMemcpyAsync(d_z.ptr, z32.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    P.yy = yy;
+    if (gram) {
+        if (design->kind == BLIPGPU_DESIGN_CHANGEPOINT) {
+            // X_j . y = sum_{i >= j} y_i  (suffix sums)
+            std::vector<double> q0h((size_t)p);
+            double acc = 0.0;
+            for (int64_t j = p - 1; j >= 0; --j) { acc += y[j]; q0h[(size_t)j] = acc; }
+            CUDA_TRY(cudaMemcpyAsync(d_q0.ptr, q0h.data(), sizeof(double) * p, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+        } else {
+            xty_kernel<<<(unsigned)((p + 7) / 8), 256, 0, st>>>(design->XT, d_y.as<double>(), d_q0.as<double>(), n, p, design->ldx);
+        }
+    }
+    CUDA_TRY(cudaMemsetAsync(d_beta.ptr, 0, d_beta.bytes, st));
+    CUDA_TRY(cudaMemsetAsync(d_mask.ptr, 0, d_mask.bytes, st));
+    init_state_kernel<<<(unsigned)chains, 256, 0, st>>>(P, d_y.as<double>(), probit, gram ? 1 : 0);
+    CUDA_TRY(cudaGetLastError());
+
+    // ---- kernel selection
+    void (*kern)(SweepParams) = nullptr;
+    if (!gram) kern = probit ? gibbs_residual_kernel<true> : gibbs_residual_kernel<false>;
+    else if (design->kind == BLIPGPU_DESIGN_CHANGEPOINT)
+        kern = qsmem ? gibbs_gram_kernel<BLIPGPU_DESIGN_CHANGEPOINT, true> : gibbs_gram_kernel<BLIPGPU_DESIGN_CHANGEPOINT, false>;
+    else
+        kern = qsmem ? gibbs_gram_kernel<BLIPGPU_DESIGN_DENSE, true> : gibbs_gram_kernel<BLIPGPU_DESIGN_DENSE, false>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+
+    cudaEvent_t ev_perm[2], ev_done[2];
+    for (int i = 0; i < 2; ++i) {
+        CUDA_TRY(cudaEventCreateWithFlags(&ev_perm[i], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&ev_done[i], cudaEventDisableTiming));
+    }
+    struct EvGuard { cudaEvent_t* a; cudaEvent_t* b; ~EvGuard() { for (int i = 0; i < 2; ++i) { cudaEventDestroy(a[i]); cudaEventDestroy(b[i]); } } } evg{ ev_perm, ev_done };
+
+    auto gen_perm = [&](int buf, int64_t sweep0, int Sc) -> int {
+        // wait until the sweep that last used this buffer has finished
+        CUDA_TRY(cudaStreamWaitEvent(st2, ev_done[buf], 0));
+        const int64_t nt = chains * Sc;
+        perm_fill_kernel<<<(unsigned)((nt + 63) / 64), 64, 0, st2>>>(d_perm[buf].as<int32_t>(), (int)chains, Sc, (int)p,
+                                                                   (int)sweep0, P.k0, P.k1, P.chain_offset);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaEventRecord(ev_perm[buf], st2));
+        return BLIP_OK;
+    };
+
+    const int64_t nchunks = (n_total + S - 1) / S;
+    if (!inj_perm) BLIP_TRY(gen_perm(0, 0, (int)std::min<int64_t>(S, n_total)));
+    int64_t max_chunk_use = 0;
+    unsigned long long used_before = 0;
+    for (int64_t ch = 0; ch < nchunks; ++ch) {
+        const int64_t sweep0 = ch * S;
+        const int Sc = (int)std::min<int64_t>(S, n_total - sweep0);
+        const int buf = inj_perm ? 0 : (int)(ch & 1);
+        if (inj_perm) BLIP_TRY(upload_chunk(d_perm[0].as<int32_t>(), streams->perm, chains, n_total * p, sweep0 * p, (int64_t)Sc * p, st));
+        else {
+            CUDA_TRY(cudaStreamWaitEvent(st, ev_perm[buf], 0));
+            if (ch + 1 < nchunks) BLIP_TRY(gen_perm(buf ^ 1, sweep0 + S, (int)std::min<int64_t>(S, n_total - sweep0 - S)));
+        }
+        if (inj_u) BLIP_TRY(upload_chunk(d_u.as<double>(), streams->u, chains, n_total * p, sweep0 * p, (int64_t)Sc * p, st));
+        if (inj_z) BLIP_TRY(upload_chunk(d_zn.as<double>(), streams->z, chains, n_total * p, sweep0 * p, (int64_t)Sc * p, st));
+        if (inj_ig) BLIP_TRY(upload_chunk(d_ig.as<double>(), streams->invgamma, chains, n_total, sweep0, (int64_t)Sc, st));
+        if (inj_p0) BLIP_TRY(upload_chunk(d_p0.as<double>(), streams->p0_draw, chains, n_total * nprop, sweep0 * nprop, (int64_t)Sc * nprop, st));
+        if (inj_g) BLIP_TRY(upload_chunk(d_g.as<double>(), streams->gamma_draw, chains, n_total, sweep0, (int64_t)Sc, st));
+
+        // grow the value arena ahead of need (kept sweeps in this chunk only)
+        const int64_t kept_in_chunk = std::max<int64_t>(0, std::min<int64_t>(sweep0 + Sc, n_total) - std::max<int64_t>(sweep0, burn));
+        int64_t need = std::max<int64_t>(2 * max_chunk_use, chains * kept_in_chunk * std::max<int64_t>(64, p / 16));
+        auto grow = [&](int64_t min_free) -> int {
+            if (smp->arena_cap - (int64_t)used_before >= min_free) return BLIP_OK;
+            const int64_t remaining_chunks = nchunks - ch;
+            int64_t newcap = (int64_t)used_before + std::max<int64_t>(min_free, (int64_t)(1.25 * remaining_chunks * std::max<int64_t>(max_chunk_use, 1)));
+            double* nv = nullptr;
+            cudaError_t e = cudaMalloc(&nv, sizeof(double) * newcap);
+            if (e != cudaSuccess) { blip_set_error("sample_spikeslab: cannot grow the value arena to %lld doubles: %s", (long long)newcap, cudaGetErrorString(e)); return BLIP_ERR_NOMEM; }
+            CUDA_TRY(cudaMemcpyAsync(nv, smp->values, sizeof(double) * used_before, cudaMemcpyDeviceToDevice, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            CUDA_TRY(cudaFree(smp->values));
+            smp->values = nv; smp->arena_cap = newcap;
+            return BLIP_OK;
+        };
+        BLIP_TRY(grow(need));
+
+        // snapshot the chain state so that an arena overflow can replay the chunk
+        auto copy_state = [&](bool save) -> int {
+            auto cp = [&](DevBuf& live, DevBuf& snap) -> int {
+                if (!live.ptr) return BLIP_OK;
+                CUDA_TRY(cudaMemcpyAsync(save ? snap.ptr : live.ptr, save ? live.ptr : snap.ptr, live.bytes, cudaMemcpyDeviceToDevice, st));
+                return BLIP_OK;
+            };
+            BLIP_TRY(cp(d_beta, snap_beta)); BLIP_TRY(cp(d_h, snap_h)); BLIP_TRY(cp(d_mask, snap_mask));
+            BLIP_TRY(cp(d_q, snap_q)); BLIP_TRY(cp(d_r, snap_r)); BLIP_TRY(cp(d_mu, snap_mu));
+            BLIP_TRY(cp(d_ylat, snap_ylat)); BLIP_TRY(cp(d_ev, snap_ev));
+            return BLIP_OK;
+        };
+        BLIP_TRY(copy_state(true));
+
+        for (int attempt = 0;; ++attempt) {
+            P.perm = d_perm[buf].as<int32_t>();
+            P.u = d_u.as<double>(); P.z = d_zn.as<double>(); P.invgamma = d_ig.as<double>();
+            P.p0_draw = d_p0.as<double>(); P.gamma_draw = d_g.as<double>();
+            P.sweep0 = (int)sweep0; P.S = Sc;
+            P.values = smp->values; P.arena_cap = smp->arena_cap;
+            CUDA_TRY(cudaMemsetAsync(d_ovf.ptr, 0, sizeof(int), st));
+            {
+                ScopedTimer timer(ctx, true);
+                kern<<<(unsigned)chains, GB_BLOCK, smem, st>>>(P);
+                CUDA_TRY(cudaGetLastError());
+                smp->sweep_ms += timer.stop(1);
+                smp->sweep_launches += 1;
+            }
+            int ovf = 0;
+            unsigned long long used = 0;
+            CUDA_TRY(cudaMemcpyAsync(&ovf, d_ovf.ptr, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(&used, smp->arena_used, sizeof(used), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            if (!ovf) {
+                max_chunk_use = std::max<int64_t>(max_chunk_use, (int64_t)(used - used_before));
+                used_before = used;
+                break;
+            }
+            if (attempt >= 8) { blip_set_error("sample_spikeslab: value arena overflow persists"); return BLIP_ERR_NOMEM; }
+            // replay: restore state, rewind the arena, enlarge it to what this chunk asked for
+            const int64_t wanted = (int64_t)(used - used_before);
+            CUDA_TRY(cudaMemcpyAsync(smp->arena_used, &used_before, sizeof(used_before), cudaMemcpyHostToDevice, st));
+            BLIP_TRY(copy_state(false));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            max_chunk_use = std::max<int64_t>(max_chunk_use, wanted);
+            BLIP_TRY(grow(wanted + wanted / 4 + 1024));
+        }
+        if (!inj_perm) CUDA_TRY(cudaEventRecord(ev_done[buf], st));
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaStreamSynchronize(st2));
+    if (probit) {
+        std::vector<uint32_t> ev((size_t)chains * 2);
+        CUDA_TRY(cudaMemcpy(ev.data(), d_ev.ptr, d_ev.bytes, cudaMemcpyDeviceToHost));
+        for (int64_t c = 0; c < chains; ++c) smp->n_events += ev[(size_t)(2 * c)];
+    }
+    guard.s = nullptr;
+    *out = smp;
+    return BLIP_OK;
+}

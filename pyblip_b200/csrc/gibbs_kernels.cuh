@@ -1,0 +1,561 @@
+// gibbs_kernels.cuh -- device side of the multi-chain single-site spike-and-slab
+// Gibbs sampler (linear + probit), sm_100a.
+//
+// Semantics follow /root/reference/pyblip/linear/_linear.pyx:126-229 (coordinate
+// sweep) and pyblip/cython_utils/_update_hparams.pyx:51-91 (hyper-parameters),
+// re-designed around EXACT SPECULATION: a null coordinate (beta_j == 0 before and
+// after its visit) leaves the chain state untouched, so a whole window of
+// upcoming coordinates is evaluated in parallel against the current state and
+// only the first coordinate whose value changes is applied; the window restarts
+// right after it.  The visiting order, the variates and every decision are
+// identical to a strictly sequential sweep.
+//
+// Two formulations:
+//   residual  state r = y - X beta in shared memory; a window is 32 columns of X
+//             streamed from HBM/L2 (one 8n-byte column per update); required for
+//             probit, where every change redraws all n latents.
+//   gram      state q = X^T r in shared memory; a window is one coordinate per
+//             thread at O(1) cost and a change reads one 8p-byte Gram column.
+#pragma once
+#include "internal.cuh"
+
+constexpr int GB_BLOCK = 256;
+constexpr int GB_NWARP = GB_BLOCK / 32;
+constexpr int GB_ROUND = 32;      // residual mode: columns speculated per window
+
+struct SweepParams {
+    // design
+    const double* XT; int64_t ldx; const double* Xl2; const double* G; int64_t ldg;
+    int n, p, words, n2, p2;
+    // data
+    const double* q0; double yy; const int32_t* zlab;
+    // model
+    blipgpu_spikeslab_config cfg;
+    // chain state (global, persists between launches)
+    double* beta;      // [chains][p]
+    double* r;         // [chains][n2]            residual mode
+    double* mu;        // [chains][n2]            probit
+    double* ylat;      // [chains][n2]            probit
+    double* q;         // [chains][p2]            gram mode
+    double* hstate;    // [chains][4]  sigma2, tau2, p0, rr
+    uint32_t* mask;    // [chains][words]  active-set bitmask
+    uint32_t* events;  // [chains][2]  probit: redraw events so far, latents-dirty flag
+    // random streams
+    uint32_t k0, k1; uint32_t chain_offset;
+    const int32_t* perm;       // [chains][S][p]   (generated or injected)
+    const double* u;           // [chains][S][p] or NULL
+    const double* z;           // [chains][S][p] or NULL
+    const double* invgamma;    // [chains][S] or NULL
+    const double* p0_draw;     // [chains][S][nprop] or NULL
+    const double* gamma_draw;  // [chains][S] or NULL
+    int nprop;
+    // sweep range of this launch
+    int sweep0, S, burn, n_keep;
+    // outputs
+    uint32_t* bits; int64_t rows, rows_pad;
+    int64_t* row_off; int32_t* row_nnz;
+    double* values; int64_t arena_cap; unsigned long long* arena_used; int* overflow;
+    double* hyper_out; double* latents;
+    int gram_refresh;
+};
+
+// ---------------------------------------------------------------------------
+// the scalar part of one coordinate update (_linear.pyx:146-158), fp64, with the
+// reference's association order.  Compiled with -fmad=false so nothing fuses.
+// ---------------------------------------------------------------------------
+struct Hyper { double sigma2, tau2, logodds; };
+
+__device__ __forceinline__ double kappa_of(double XjTr, double xl2, const Hyper& h)
+{
+    double logdet = log(1.0 + h.tau2 * xl2 / h.sigma2) / 2.0;          // :129
+    double log_ratio_num = h.tau2 / h.sigma2 * XjTr * XjTr;            // :146
+    double log_ratio_denom = 2 * (h.sigma2 + h.tau2 * xl2);            // :147
+    double ratio = exp(h.logodds - log_ratio_num / log_ratio_denom + logdet);
+    return ratio / (1.0 + ratio);                                      // :149
+}
+
+__device__ __forceinline__ double slab_draw(double XjTr, double xl2, const Hyper& h, double znorm)
+{
+    double post_var = 1.0 / (1.0 / h.tau2 + xl2 / h.sigma2);           // :130
+    double post_mean = post_var * XjTr / h.sigma2;                     // :155
+    return sqrt(post_var) * znorm + post_mean;                         // :158
+}
+
+// block-wide exclusive scan of one int per thread; returns the exclusive prefix,
+// *total gets the block sum.  s_warp: >= GB_NWARP+1 ints of shared memory.
+__device__ __forceinline__ int block_excl_scan(int v, int* s_warp, int* total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = lane < GB_NWARP ? s_warp[lane] : 0;
+        int wi = w;
+#pragma unroll
+        for (int o = 1; o < GB_NWARP; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += t;
+        }
+        if (lane < GB_NWARP) s_warp[lane] = wi - w;       // exclusive warp offsets
+        if (lane == GB_NWARP - 1) s_warp[GB_NWARP] = wi;  // total
+    }
+    __syncthreads();
+    int res = s_warp[warp] + incl - v;
+    *total = s_warp[GB_NWARP];
+    __syncthreads();
+    return res;
+}
+
+// ---------------------------------------------------------------------------
+// end-of-sweep: hyper-parameter draws (_update_hparams.pyx:51-91) and recording
+// ---------------------------------------------------------------------------
+struct SweepShared {
+    double sigma2, tau2, p0, rr, logodds;
+    long long off;
+    int scan[GB_NWARP + 2];
+};
+
+// Called by every thread of the block.  ssr = ||r||^2 (already reduced, same value
+// in every thread).  Updates sh->{sigma2,tau2,p0}; records the sweep if kept.
+__device__ inline void sweep_epilogue(const SweepParams& P, SweepShared* sh, const uint32_t* mask_s,
+                                      const double* beta_g, double* scratch, const RngKey& key,
+                                      int c, int s, double ssr, const double* y_s, bool latents_dirty)
+{
+    const int tid = threadIdx.x;
+    const int sweep = P.sweep0 + s;
+    // number of active coordinates and sum of squares (_update_hparams.pyx:52-54, 85-88)
+    int cnt = 0;
+    double ss = 0.0;
+    for (int w = tid; w < P.words; w += GB_BLOCK) {
+        uint32_t m = mask_s[w];
+        cnt += __popc(m);
+        while (m) {
+            int b = __ffs(m) - 1;
+            m &= m - 1;
+            double v = __ldcg(beta_g + 32 * w + b);
+            ss = fma(v, v, ss);
+        }
+    }
+    ss = block_sum(ss, scratch);
+    const int k = (int)(block_sum((double)cnt, scratch) + 0.5);
+
+    if (tid == 0) {
+        const blipgpu_spikeslab_config& cf = P.cfg;
+        const int64_t hs = (int64_t)c * P.S + s;
+        if (cf.update_p0 == 1) {
+            double a = cf.p0_a0 + P.p - k, b = cf.p0_b0 + k;
+            if (cf.min_p0 == 0) {
+                sh->p0 = P.p0_draw ? P.p0_draw[hs * P.nprop] : rng_beta(key, 0, sweep, a, b);
+            } else {
+                double p0 = cf.min_p0;
+                for (int jj = 0; jj < 100; ++jj) {
+                    double prop = P.p0_draw ? P.p0_draw[hs * P.nprop + jj]
+                                            : rng_beta(key, jj, sweep, a, b);
+                    if (prop > cf.min_p0) { p0 = prop; break; }
+                }
+                sh->p0 = p0;
+            }
+        }
+        if (cf.update_sigma2 == 1) {
+            double r2 = sqrt(ssr);             // dnrm2 ...
+            r2 = r2 * r2;                      // ... squared (:77-78)
+            double sigma_b = r2 / 2.0 + cf.sigma2_b0;
+            double ig = P.invgamma ? P.invgamma[hs]
+                                   : 1.0 / rng_gamma(key, SLOT_INVGAMMA, sweep, P.n / 2.0 + cf.sigma2_a0);
+            sh->sigma2 = sigma_b * ig;
+        }
+        if (cf.update_tau2) {
+            double g = P.gamma_draw ? P.gamma_draw[hs]
+                                    : rng_gamma(key, SLOT_TAU_GAMMA, sweep, cf.tau2_a0 + (double)k / 2.0);
+            sh->tau2 = (cf.tau2_b0 + ss / 2.0) / g;
+        }
+    }
+    __syncthreads();
+
+    if (sweep < P.burn) return;               // uniform across the block
+    const int64_t row = (int64_t)c * P.n_keep + (sweep - P.burn);
+    if (tid == 0) {
+        P.hyper_out[row] = sh->p0;
+        P.hyper_out[P.rows + row] = sh->tau2;
+        P.hyper_out[2 * P.rows + row] = sh->sigma2;
+        unsigned long long off = atomicAdd(P.arena_used, (unsigned long long)k);
+        long long o = (long long)off;
+        if (off + (unsigned long long)k > (unsigned long long)P.arena_cap) { *P.overflow = 1; o = -1; }
+        sh->off = o;
+        P.row_off[row] = o;
+        P.row_nnz[row] = k;
+    }
+    for (int w = tid; w < P.words; w += GB_BLOCK) P.bits[(int64_t)w * P.rows_pad + row] = mask_s[w];
+    __syncthreads();
+    const long long off = sh->off;
+    if (off >= 0 && k > 0) {
+        int base = 0;
+        for (int w0 = 0; w0 < P.words; w0 += GB_BLOCK) {     // uniform trip count
+            int w = w0 + tid;
+            uint32_t m = (w < P.words) ? mask_s[w] : 0u;
+            int total;
+            int pre = block_excl_scan(__popc(m), sh->scan, &total);
+            double* dst = P.values + off + base + pre;
+            while (m) {
+                int b = __ffs(m) - 1;
+                m &= m - 1;
+                *dst++ = __ldcg(beta_g + 32 * w + b);
+            }
+            base += total;
+        }
+    }
+    if (P.latents && latents_dirty && y_s) {
+        double* dst = P.latents + row * (int64_t)P.n;
+        for (int k2 = tid; k2 < P.n; k2 += GB_BLOCK) dst[k2] = y_s[k2];
+    }
+}
+
+// ===========================================================================
+// residual mode
+// ===========================================================================
+struct ResidualBcast { int tstar, jstar; double beta_old, dspec, beta_new; };
+
+template <bool PROBIT>
+__global__ void __launch_bounds__(GB_BLOCK, 2) gibbs_residual_kernel(SweepParams P)
+{
+    extern __shared__ __align__(16) double sm[];
+    __shared__ SweepShared sh;
+    __shared__ ResidualBcast bc;
+
+    const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = P.n, p = P.p, n2 = P.n2;
+    double* r_s = sm;
+    double* mu_s = PROBIT ? r_s + n2 : nullptr;
+    double* y_s = PROBIT ? r_s + 2 * n2 : nullptr;
+    double* part = r_s + (PROBIT ? 3 : 1) * n2;        // [GB_NWARP][32]
+    double* scratch = part + GB_NWARP * 32;            // [40]
+    uint32_t* mask_s = (uint32_t*)(scratch + 40);      // [words]
+
+    const RngKey key = { P.k0, P.k1, P.chain_offset + (uint32_t)c };
+    double* beta_g = P.beta + (int64_t)c * p;
+    double* r_g = P.r + (int64_t)c * n2;
+
+    for (int k = tid; k < n2; k += GB_BLOCK) {
+        r_s[k] = r_g[k];
+        if (PROBIT) { mu_s[k] = P.mu[(int64_t)c * n2 + k]; y_s[k] = P.ylat[(int64_t)c * n2 + k]; }
+    }
+    for (int w = tid; w < P.words; w += GB_BLOCK) mask_s[w] = P.mask[(int64_t)c * P.words + w];
+    if (tid == 0) {
+        sh.sigma2 = P.hstate[4 * c + 0]; sh.tau2 = P.hstate[4 * c + 1];
+        sh.p0 = P.hstate[4 * c + 2]; sh.rr = 0.0;
+    }
+    uint32_t event = PROBIT ? P.events[2 * c] : 0u;
+    bool dirty = PROBIT ? (P.events[2 * c + 1] != 0u) : false;
+    __syncthreads();
+
+    for (int s = 0; s < P.S; ++s) {
+        const int sweep = P.sweep0 + s;
+        const int64_t soff = ((int64_t)c * P.S + s) * p;
+        const int32_t* perm_s = P.perm + soff;
+        const double* u_s = P.u ? P.u + soff : nullptr;
+        const double* z_s = P.z ? P.z + soff : nullptr;
+        if (tid == 0) sh.logodds = log(sh.p0) - log(1 - sh.p0);   // :76, :222
+        __syncthreads();
+        const Hyper h = { sh.sigma2, sh.tau2, sh.logodds };
+
+        int pos0 = 0;
+        while (pos0 < p) {
+            const int T = min(GB_ROUND, p - pos0);
+            // ---- speculative dots of the next T columns against the current residual
+            const int jl = perm_s[min(pos0 + lane, p - 1)];
+            double acc[GB_ROUND];
+#pragma unroll
+            for (int cc = 0; cc < GB_ROUND; ++cc) acc[cc] = 0.0;
+            for (int kb = 0; kb < n2; kb += 2 * GB_BLOCK) {   // warp-uniform trip count (shuffles inside)
+                const int k = kb + 2 * tid;
+                const bool ok = k < n2;
+                const double2 rk = ok ? *reinterpret_cast<const double2*>(r_s + k) : make_double2(0.0, 0.0);
+                const double* xrow = P.XT + (ok ? k : 0);
+#pragma unroll
+                for (int cc = 0; cc < GB_ROUND; ++cc) {
+                    const int jc = __shfl_sync(0xffffffffu, jl, cc);
+                    const double2 x = __ldg(reinterpret_cast<const double2*>(xrow + (int64_t)jc * P.ldx));
+                    acc[cc] = fma(x.x, rk.x, acc[cc]);
+                    acc[cc] = fma(x.y, rk.y, acc[cc]);
+                }
+            }
+            // ---- transpose-reduce: lane l ends with the warp's partial dot of column l
+#pragma unroll
+            for (int o = 16, cnt = 16; o >= 1; o >>= 1, cnt >>= 1) {
+                const bool upper = (lane & o) != 0;
+#pragma unroll
+                for (int i = 0; i < cnt; ++i) {
+                    double send = upper ? acc[i] : acc[i + cnt];
+                    double keep = upper ? acc[i + cnt] : acc[i];
+                    acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                }
+            }
+            part[warp * 32 + lane] = acc[0];
+            __syncthreads();
+            if (warp == 0) {
+                double d = 0.0;
+#pragma unroll
+                for (int w = 0; w < GB_NWARP; ++w) d += part[w * 32 + lane];
+                bool change = false, act = false;
+                if (lane < T) {
+                    act = (mask_s[jl >> 5] >> (jl & 31)) & 1u;
+                    if (act) change = true;
+                    else {
+                        double u = u_s ? u_s[pos0 + lane] : rng_uniform(key, KIND_SPIKE_U, pos0 + lane, sweep, 0);
+                        double kappa = kappa_of(d, P.Xl2[jl], h);
+                        change = !(u <= kappa);      // NaN kappa -> slab, like the reference
+                    }
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, change);
+                const int tstar = m ? __ffs(m) - 1 : -1;
+                if (lane == (tstar < 0 ? 0 : tstar)) {
+                    bc.tstar = tstar; bc.jstar = jl;
+                    bc.beta_old = act ? __ldcg(beta_g + jl) : 0.0;
+                    bc.dspec = d;
+                }
+            }
+            __syncthreads();
+            const int tstar = bc.tstar;
+            if (tstar < 0) { pos0 += T; continue; }
+
+            // ---- apply the first changing coordinate exactly like the reference
+            const int j = bc.jstar;
+            const double beta_old = bc.beta_old;
+            const double* xcol = P.XT + (int64_t)j * P.ldx;
+            double d = bc.dspec;
+            if (beta_old != 0) {                      // :136-145 add back, fresh dot
+                double partial = 0.0;
+                for (int k = 2 * tid; k < n2; k += 2 * GB_BLOCK) {
+                    double2 x = __ldg(reinterpret_cast<const double2*>(xcol + k));
+                    double2 rk = *reinterpret_cast<double2*>(r_s + k);
+                    rk.x = fma(beta_old, x.x, rk.x); rk.y = fma(beta_old, x.y, rk.y);
+                    *reinterpret_cast<double2*>(r_s + k) = rk;
+                    partial = fma(x.x, rk.x, partial); partial = fma(x.y, rk.y, partial);
+                }
+                d = block_sum(partial, scratch);
+            }
+            if (tid == 0) {
+                const int pos = pos0 + tstar;
+                double u = u_s ? u_s[pos] : rng_uniform(key, KIND_SPIKE_U, pos, sweep, 0);
+                double xl2 = P.Xl2[j];
+                double kappa = kappa_of(d, xl2, h);
+                double bnew = 0.0;
+                if (!(u <= kappa)) {
+                    double zn = z_s ? z_s[pos] : rng_normal(key, KIND_SLAB_Z, pos, sweep, 0);
+                    bnew = slab_draw(d, xl2, h, zn);
+                }
+                bc.beta_new = bnew;
+                __stcg(beta_g + j, bnew);
+                if (bnew != 0) mask_s[j >> 5] |= (1u << (j & 31));
+                else mask_s[j >> 5] &= ~(1u << (j & 31));
+            }
+            __syncthreads();
+            const double bnew = bc.beta_new;
+            if (!PROBIT) {
+                if (bnew != 0) {                      // :160-170
+                    for (int k = 2 * tid; k < n2; k += 2 * GB_BLOCK) {
+                        double2 x = __ldg(reinterpret_cast<const double2*>(xcol + k));
+                        double2 rk = *reinterpret_cast<double2*>(r_s + k);
+                        rk.x = fma(-bnew, x.x, rk.x); rk.y = fma(-bnew, x.y, rk.y);
+                        *reinterpret_cast<double2*>(r_s + k) = rk;
+                    }
+                }
+            } else {
+                const double delta = bnew - beta_old; // :172-190
+                if (delta != 0) {
+                    for (int k = tid; k < n; k += GB_BLOCK) {
+                        double m = fma(delta, __ldg(xcol + k), mu_s[k]);
+                        mu_s[k] = m;
+                        double yv = truncnorm(key, KIND_TRUNCNORM, (uint32_t)k, event, m, P.cfg.sigma2,
+                                              0.0, P.zlab[k]);
+                        y_s[k] = yv;
+                        r_s[k] = yv - m;
+                    }
+                    event++;
+                    dirty = true;
+                }
+            }
+            __syncthreads();
+            pos0 += tstar + 1;
+        }
+
+        // ---- hyper-parameters + recording
+        double ssr = 0.0;
+        for (int k = tid; k < n; k += GB_BLOCK) ssr = fma(r_s[k], r_s[k], ssr);
+        ssr = block_sum(ssr, scratch);
+        sweep_epilogue(P, &sh, mask_s, beta_g, scratch, key, c, s, ssr, y_s, dirty);
+        dirty = false;
+        __syncthreads();
+    }
+
+    for (int k = tid; k < n2; k += GB_BLOCK) {
+        r_g[k] = r_s[k];
+        if (PROBIT) { P.mu[(int64_t)c * n2 + k] = mu_s[k]; P.ylat[(int64_t)c * n2 + k] = y_s[k]; }
+    }
+    for (int w = tid; w < P.words; w += GB_BLOCK) P.mask[(int64_t)c * P.words + w] = mask_s[w];
+    if (tid == 0) {
+        P.hstate[4 * c + 0] = sh.sigma2; P.hstate[4 * c + 1] = sh.tau2; P.hstate[4 * c + 2] = sh.p0;
+        if (PROBIT) { P.events[2 * c] = event; P.events[2 * c + 1] = dirty ? 1u : 0u; }
+    }
+}
+
+// ===========================================================================
+// gram mode (linear only)
+// ===========================================================================
+struct GramBcast { int jstar; double delta; };
+
+template <int DESIGN> __device__ __forceinline__ double2 gram_pair(const SweepParams& P, int jstar, int k)
+{
+    if (DESIGN == BLIPGPU_DESIGN_CHANGEPOINT) {
+        // X[i][j] = 1{i >= j}  =>  (X^T X)[a][b] = T - max(a, b)
+        return make_double2(k < P.p ? (double)(P.n - max(jstar, k)) : 0.0,
+                            k + 1 < P.p ? (double)(P.n - max(jstar, k + 1)) : 0.0);
+    } else {
+        return __ldg(reinterpret_cast<const double2*>(P.G + (int64_t)jstar * P.ldg + k));
+    }
+}
+
+template <int DESIGN, bool QSMEM>
+__global__ void __launch_bounds__(GB_BLOCK, 2) gibbs_gram_kernel(SweepParams P)
+{
+    extern __shared__ __align__(16) double sm[];
+    __shared__ SweepShared sh;
+    __shared__ GramBcast bc;
+    __shared__ unsigned flags[2][GB_NWARP];
+    __shared__ double scratch[40];
+
+    const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int p = P.p, p2 = P.p2;
+    double* q_g = P.q + (int64_t)c * p2;
+    double* q = QSMEM ? sm : q_g;
+    uint32_t* mask_s = (uint32_t*)(sm + (QSMEM ? p2 : 0));
+
+    const RngKey key = { P.k0, P.k1, P.chain_offset + (uint32_t)c };
+    double* beta_g = P.beta + (int64_t)c * p;
+
+    if (QSMEM) for (int k = tid; k < p2; k += GB_BLOCK) q[k] = q_g[k];
+    for (int w = tid; w < P.words; w += GB_BLOCK) mask_s[w] = P.mask[(int64_t)c * P.words + w];
+    if (tid == 0) {
+        sh.sigma2 = P.hstate[4 * c + 0]; sh.tau2 = P.hstate[4 * c + 1];
+        sh.p0 = P.hstate[4 * c + 2]; sh.rr = P.hstate[4 * c + 3];
+    }
+    __syncthreads();
+
+    int parity = 0;
+    for (int s = 0; s < P.S; ++s) {
+        const int sweep = P.sweep0 + s;
+        const int64_t soff = ((int64_t)c * P.S + s) * p;
+        const int32_t* perm_s = P.perm + soff;
+        const double* u_s = P.u ? P.u + soff : nullptr;
+        const double* z_s = P.z ? P.z + soff : nullptr;
+
+        // ---- periodic rebuild of q and ||r||^2 from q0 = X^T y (bounds rounding drift)
+        if (P.gram_refresh > 0 && sweep > 0 && sweep % P.gram_refresh == 0) {
+            for (int k = tid; k < p2; k += GB_BLOCK) q[k] = k < p ? P.q0[k] : 0.0;
+            __syncthreads();
+            for (int w = 0; w < P.words; ++w) {
+                uint32_t m = mask_s[w];
+                while (m) {
+                    int j = 32 * w + __ffs(m) - 1;
+                    m &= m - 1;
+                    const double bj = __ldcg(beta_g + j);
+                    for (int k = 2 * tid; k < p2; k += 2 * GB_BLOCK) {
+                        double2 g = gram_pair<DESIGN>(P, j, k);
+                        double2 qq = *reinterpret_cast<double2*>(q + k);
+                        qq.x = fma(-bj, g.x, qq.x); qq.y = fma(-bj, g.y, qq.y);
+                        *reinterpret_cast<double2*>(q + k) = qq;
+                    }
+                }
+            }
+            __syncthreads();
+            double acc = 0.0;                   // ||y - X b||^2 = y'y - sum_j b_j (q0_j + q_j)
+            for (int w = tid; w < P.words; w += GB_BLOCK) {
+                uint32_t m = mask_s[w];
+                while (m) {
+                    int j = 32 * w + __ffs(m) - 1;
+                    m &= m - 1;
+                    acc = fma(__ldcg(beta_g + j), P.q0[j] + q[j], acc);
+                }
+            }
+            acc = block_sum(acc, scratch);
+            if (tid == 0) sh.rr = P.yy - acc;
+        }
+        if (tid == 0) sh.logodds = log(sh.p0) - log(1 - sh.p0);
+        __syncthreads();
+        const Hyper h = { sh.sigma2, sh.tau2, sh.logodds };
+
+        int pos0 = 0;
+        while (pos0 < p) {
+            const int pos = pos0 + tid;
+            bool change = false, act = false, spike = true;
+            int j = 0;
+            double qj = 0.0, xl2 = 0.0, beta_old = 0.0, XjTr = 0.0;
+            if (pos < p) {
+                j = perm_s[pos];
+                qj = q[j];
+                xl2 = P.Xl2[j];
+                act = (mask_s[j >> 5] >> (j & 31)) & 1u;
+                if (act) beta_old = __ldcg(beta_g + j);
+                XjTr = act ? qj + beta_old * xl2 : qj;      // X_j . (r + beta_j X_j)
+                double u = u_s ? u_s[pos] : rng_uniform(key, KIND_SPIKE_U, pos, sweep, 0);
+                double kappa = kappa_of(XjTr, xl2, h);
+                spike = (u <= kappa);
+                change = act || !spike;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, change);
+            if (lane == 0) flags[parity][warp] = m;
+            __syncthreads();
+            int tstar = -1;
+#pragma unroll
+            for (int w = GB_NWARP - 1; w >= 0; --w) {
+                unsigned f = flags[parity][w];
+                if (f) tstar = 32 * w + __ffs(f) - 1;
+            }
+            parity ^= 1;
+            if (tstar < 0) { pos0 += GB_BLOCK; continue; }
+            if (tid == tstar) {
+                double bnew = 0.0;
+                if (!spike) {
+                    double zn = z_s ? z_s[pos] : rng_normal(key, KIND_SLAB_Z, pos, sweep, 0);
+                    bnew = slab_draw(XjTr, xl2, h, zn);
+                }
+                const double delta = bnew - beta_old;
+                bc.jstar = j; bc.delta = delta;
+                // ||r - delta X_j||^2 = ||r||^2 - 2 delta X_j.r + delta^2 ||X_j||^2
+                sh.rr = sh.rr - 2.0 * delta * qj + delta * delta * xl2;
+                __stcg(beta_g + j, bnew);
+                if (bnew != 0) mask_s[j >> 5] |= (1u << (j & 31));
+                else mask_s[j >> 5] &= ~(1u << (j & 31));
+            }
+            __syncthreads();
+            const double delta = bc.delta;
+            const int jstar = bc.jstar;
+            if (delta != 0) {                   // q -= delta * G[:, j*]
+                for (int k = 2 * tid; k < p2; k += 2 * GB_BLOCK) {
+                    double2 g = gram_pair<DESIGN>(P, jstar, k);
+                    double2 qq = *reinterpret_cast<double2*>(q + k);
+                    qq.x = fma(-delta, g.x, qq.x); qq.y = fma(-delta, g.y, qq.y);
+                    *reinterpret_cast<double2*>(q + k) = qq;
+                }
+            }
+            __syncthreads();
+            pos0 += tstar + 1;
+        }
+
+        sweep_epilogue(P, &sh, mask_s, beta_g, scratch, key, c, s, sh.rr, nullptr, false);
+        __syncthreads();
+    }
+
+    if (QSMEM) for (int k = tid; k < p2; k += GB_BLOCK) q_g[k] = q[k];
+    for (int w = tid; w < P.words; w += GB_BLOCK) P.mask[(int64_t)c * P.words + w] = mask_s[w];
+    if (tid == 0) {
+        P.hstate[4 * c + 0] = sh.sigma2; P.hstate[4 * c + 1] = sh.tau2;
+        P.hstate[4 * c + 2] = sh.p0; P.hstate[4 * c + 3] = sh.rr;
+    }
+}

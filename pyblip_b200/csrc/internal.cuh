@@ -1,0 +1,75 @@
+// internal.cuh -- opaque handle definitions behind include/blipgpu.h
+#pragma once
+#include "../../include/blipgpu.h"
+#include "common.cuh"
+
+struct blipgpu_ctx {
+    int device;
+    int sm_count;
+    size_t smem_optin;     // max dynamic shared memory per block (opt-in)
+    cudaStream_t stream;   // sweep / counting kernels
+    cudaStream_t stream2;  // permutation generation, copies
+    double sweep_ms, other_ms;
+    int64_t sweep_launches, other_launches;
+};
+
+struct blipgpu_design {
+    blipgpu_ctx* ctx;
+    int kind;              // BLIPGPU_DESIGN_*
+    int64_t n, p;
+    int64_t ldx;           // row pitch of XT in doubles (multiple of 4, zero padded)
+    double* XT;            // [p][ldx]  column j of X is row j here (HBM)
+    double* Xl2;           // [p]       squared column norms = diag of the Gram matrix
+    double* G;             // [p][ldg]  Gram matrix or NULL
+    int64_t ldg;
+};
+
+struct blipgpu_samples {
+    blipgpu_ctx* ctx;
+    int64_t rows, rows_pad, p, n, chains, n_keep, words;
+    uint32_t* bits;        // [words][rows_pad]  bit b of word w = (beta[row][32w+b] != 0)
+    int64_t* row_off;      // [rows] offset of the row's values in `values`
+    int32_t* row_nnz;      // [rows]
+    double* values;        // arena; a row's values are stored in increasing column order
+    int64_t arena_cap;
+    unsigned long long* arena_used;  // device counter
+    double* hyper;         // [3][rows]: p0, tau2, sigma2
+    double* latents;       // [rows][n] or NULL
+    int64_t n_events;
+    int mode;
+    double sweep_ms;
+    int64_t sweep_launches;
+};
+
+struct blipgpu_bits {
+    blipgpu_ctx* ctx;
+    int64_t N, N_pad, p, words;
+    uint32_t* bits;        // [words][N_pad]
+    bool owns;
+};
+
+// helpers implemented in api.cu
+int blip_ctx_activate(blipgpu_ctx* ctx);
+static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+// event-timed region on ctx->stream
+struct ScopedTimer {
+    blipgpu_ctx* ctx; cudaEvent_t e0, e1; bool sweep; bool ok;
+    ScopedTimer(blipgpu_ctx* c, bool is_sweep) : ctx(c), sweep(is_sweep), ok(false) {
+        if (cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess) {
+            ok = true; cudaEventRecord(e0, ctx->stream);
+        }
+    }
+    // returns elapsed ms (synchronises on the end event)
+    double stop(int64_t launches) {
+        if (!ok) return 0.0;
+        cudaEventRecord(e1, ctx->stream);
+        cudaEventSynchronize(e1);
+        float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+        cudaEventDestroy(e0); cudaEventDestroy(e1); ok = false;
+        if (sweep) { ctx->sweep_ms += ms; ctx->sweep_launches += launches; }
+        else { ctx->other_ms += ms; ctx->other_launches += launches; }
+        return ms;
+    }
+    ~ScopedTimer() { if (ok) { cudaEventDestroy(e0); cudaEventDestroy(e1); } }
+};

@@ -1,0 +1,93 @@
+"""Device PIP counting vs the reference's golden outputs and the NumPy oracle.
+Counts and PEPs must be bit-exact (integer work + one float64 divide)."""
+import json
+
+import numpy as np
+import pytest
+
+import blip_testutil as util
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", util.COUNTING_CASES)
+def test_primitive_counts_bit_exact(gpu, name):
+    from oracle import counting_oracle as co
+    from pyblip_b200 import _lib
+    samples = util.load_counting_case(name)["samples"]
+    bits = _lib.Bits.from_dense(samples)
+    assert np.array_equal(bits.to_dense(), samples != 0)
+    assert np.array_equal(bits.count_columns(), co.column_counts(samples))
+    for max_size in (1, 4, 25, 33, 64):
+        ms = min(max_size, samples.shape[1])
+        assert np.array_equal(bits.count_sequential(ms), co.sequential_zero_counts(samples, ms)), max_size
+    rng = np.random.default_rng(1)
+    p = samples.shape[1]
+    groups = [sorted(rng.choice(p, size=int(rng.integers(1, min(p, 25) + 1)), replace=False).tolist())
+              for _ in range(200)]
+    assert np.array_equal(bits.count_groups(groups), co.group_any_counts(samples, groups))
+    cols = np.sort(rng.choice(p, size=max(1, p // 3), replace=False))
+    sub = bits.select_columns(cols)
+    assert np.array_equal(sub.to_dense(), (samples != 0)[:, cols])
+    assert np.array_equal(sub.count_sequential(min(25, len(cols))),
+                          co.sequential_zero_counts(samples[:, cols], min(25, len(cols))))
+
+
+@pytest.mark.parametrize("name", util.COUNTING_CASES)
+def test_group_functions_match_reference_golden(gpu, name):
+    from pyblip_b200 import create_groups as cg
+    case = util.load_counting_case(name)
+    samples = case["samples"]
+    for key, fn in [("seq", cg.sequential_groups), ("hier", cg.hierarchical_groups),
+                    ("all", cg.all_cand_groups)]:
+        for k in [k for k in case if k.startswith(key + "_") and not k.endswith("_kwargs")]:
+            kwargs = case[k + "_kwargs"]
+            got = util.cg_list(fn(samples.copy(), **kwargs))
+            want = util.golden_groups(case[k])
+            assert sorted(got) == sorted(want), f"{name}/{k}: groups or PEPs differ"
+            if key == "seq" and not kwargs.get("prenarrow"):
+                assert got == want, f"{name}/{k}: order differs"
+
+
+def test_large_random_matrix_against_oracle(gpu):
+    """Sizes past the fixtures: ragged N (not a multiple of 32), p not a multiple of 32,
+    all-zero and all-one columns, > 2 row chunks."""
+    from oracle import counting_oracle as co
+    from pyblip_b200 import _lib, create_groups as cg
+    rng = np.random.default_rng(7)
+    N, p = 50021, 203
+    S = rng.random((N, p)) < 0.02
+    S[:, 17] = True
+    S[:, 40:44] = False
+    S[rng.random(N) < 0.8, 100] = True
+    bits = _lib.Bits.from_dense(S)
+    assert np.array_equal(bits.count_columns(), co.column_counts(S))
+    assert np.array_equal(bits.count_sequential(25), co.sequential_zero_counts(S, 25))
+    got = util.cg_list(cg.sequential_groups(S, max_pep=0.5))
+    want = co.sequential_groups(S, max_pep=0.5)
+    assert got == want
+
+
+def test_empty_and_degenerate_inputs(gpu):
+    from pyblip_b200 import create_groups as cg
+    assert cg.all_cand_groups(np.zeros((100, 40)), prenarrow=False, max_pep=0.5) == []
+    one = cg.hierarchical_groups(np.array([[1.0], [0.0], [1.0], [1.0]]))
+    assert len(one) == 1 and one[0].group == {0} and one[0].pep == 1 - 3 / 4
+    with pytest.raises(ValueError):
+        cg.sequential_groups()
+
+
+def test_sampler_handle_counting_equals_dense_path(gpu):
+    """Counting on the device-resident samples == counting on lm.betas."""
+    from pyblip_b200 import LinearSpikeSlab, create_groups as cg, changepoint
+    case = util.load_sampler_case("linear_c1")
+    lm = LinearSpikeSlab(case["X"], case["y"])
+    lm.sample(N=60, burn=10, chains=3, seed=3)
+    a = util.cg_list(cg.all_cand_groups(lm, max_pep=0.5))
+    b = util.cg_list(cg.all_cand_groups(lm.betas, max_pep=0.5))
+    assert sorted(a) == sorted(b) and len(a) > 0
+    c1 = util.cg_list(changepoint.changepoint_cand_groups(lm, max_pep=0.9))
+    dense = lm.betas != 0
+    dense[:, 0] = 0
+    c2 = util.cg_list(cg.sequential_groups(dense, max_pep=0.9))
+    assert c1 == c2
