@@ -40,6 +40,9 @@ typedef struct blipgpu_samples blipgpu_samples; /* posterior samples kept on dev
 typedef struct blipgpu_bits blipgpu_bits;       /* bit-packed indicator matrix      */
 
 int blipgpu_abi_version(void);
+/* sizeof() of the ABI structs as compiled, for binding self-checks:
+ * 0 spikeslab_config, 1 streams, 2 sample_options, 3 samples_info. */
+int blipgpu_sizeof(int which);
 const char* blipgpu_last_error(void);
 int blipgpu_device_count(int* count);
 
@@ -51,6 +54,14 @@ int blipgpu_ctx_synchronize(blipgpu_ctx* ctx);
  * sweep kernels / counting kernels since the last reset; used by bench.py. */
 int blipgpu_ctx_timing(blipgpu_ctx* ctx, double* sweep_ms, int64_t* sweep_launches,
                        double* other_ms, int64_t* other_launches, int reset);
+/* Work counters since the last reset: kernels launched by this library on the
+ * context, and bytes it copied host->device / device->host. */
+int blipgpu_ctx_counters(blipgpu_ctx* ctx, int64_t* kernel_launches, int64_t* h2d_bytes,
+                         int64_t* d2h_bytes, int reset);
+/* CUDA-event stopwatch on the context's stream (slot 0..7): bench.py brackets its
+ * timed regions with these because torch.cuda.Event only sees torch's stream. */
+int blipgpu_ctx_event_record(blipgpu_ctx* ctx, int slot);
+int blipgpu_ctx_event_elapsed_ms(blipgpu_ctx* ctx, int slot_begin, int slot_end, double* ms);
 
 /* ---- design matrix ----------------------------------------------------- */
 #define BLIPGPU_DESIGN_DENSE 0        /* X given, column-major copy kept in HBM   */
@@ -129,6 +140,10 @@ typedef struct blipgpu_samples_info {
     double sweep_ms;     /* device time in sweep kernels for this call           */
     int64_t sweep_launches;
     int64_t bytes_device;
+    double total_ms;     /* device time of the whole call (events on the stream) */
+    int64_t n_changes;   /* coordinate visits that changed a value (all sweeps)  */
+    int64_t n_windows;   /* speculation windows evaluated (all sweeps)           */
+    int64_t n_sweeps_total; /* chains * (n_keep + burn)                          */
 } blipgpu_samples_info;
 
 int blipgpu_samples_info_get(blipgpu_samples* s, blipgpu_samples_info* info);

@@ -21,8 +21,9 @@ ERR_NUMERIC, ERR_NOMEM, ERR_ARG, ERR_UNSUPPORTED = 4, 3, 2, 5
 
 # every symbol include/blipgpu.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
-    "blipgpu_abi_version", "blipgpu_last_error", "blipgpu_device_count",
+    "blipgpu_abi_version", "blipgpu_sizeof", "blipgpu_last_error", "blipgpu_device_count",
     "blipgpu_ctx_create", "blipgpu_ctx_destroy", "blipgpu_ctx_synchronize", "blipgpu_ctx_timing",
+    "blipgpu_ctx_counters", "blipgpu_ctx_event_record", "blipgpu_ctx_event_elapsed_ms",
     "blipgpu_design_upload", "blipgpu_design_changepoint", "blipgpu_design_build_gram",
     "blipgpu_design_get_gram", "blipgpu_design_get_xl2", "blipgpu_design_free",
     "blipgpu_sample_spikeslab",
@@ -69,6 +70,8 @@ class SamplesInfo(C.Structure):
         ("n_keep", C.c_int64), ("nnz", C.c_int64), ("n_events", C.c_int64),
         ("has_latents", C.c_int32), ("mode", C.c_int32),
         ("sweep_ms", C.c_double), ("sweep_launches", C.c_int64), ("bytes_device", C.c_int64),
+        ("total_ms", C.c_double), ("n_changes", C.c_int64), ("n_windows", C.c_int64),
+        ("n_sweeps_total", C.c_int64),
     ]
 
 
@@ -145,6 +148,21 @@ class Context:
 
     def synchronize(self):
         check(load().blipgpu_ctx_synchronize(self._h))
+
+    def counters(self, reset=False):
+        k, h, d = C.c_int64(), C.c_int64(), C.c_int64()
+        check(load().blipgpu_ctx_counters(self._h, C.byref(k), C.byref(h), C.byref(d),
+                                          C.c_int(int(reset))))
+        return dict(kernel_launches=k.value, h2d_bytes=h.value, d2h_bytes=d.value)
+
+    def event_record(self, slot):
+        check(load().blipgpu_ctx_event_record(self._h, C.c_int(slot)))
+
+    def event_elapsed_ms(self, slot_begin, slot_end):
+        ms = C.c_double()
+        check(load().blipgpu_ctx_event_elapsed_ms(self._h, C.c_int(slot_begin), C.c_int(slot_end),
+                                                  C.byref(ms)))
+        return ms.value
 
     def timing(self, reset=False):
         sm, ol = C.c_double(), C.c_double()

@@ -17,6 +17,16 @@ void blip_set_error(const char* fmt, ...)
 
 extern "C" int blipgpu_abi_version(void) { return BLIPGPU_ABI_VERSION; }
 extern "C" const char* blipgpu_last_error(void) { return g_err; }
+extern "C" int blipgpu_sizeof(int which)
+{
+    switch (which) {
+        case 0: return (int)sizeof(blipgpu_spikeslab_config);
+        case 1: return (int)sizeof(blipgpu_streams);
+        case 2: return (int)sizeof(blipgpu_sample_options);
+        case 3: return (int)sizeof(blipgpu_samples_info);
+        default: return -1;
+    }
+}
 
 extern "C" int blipgpu_device_count(int* count)
 {
@@ -56,6 +66,8 @@ extern "C" int blipgpu_ctx_create(int device, blipgpu_ctx** out)
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
     ctx->sweep_ms = ctx->other_ms = 0.0;
     ctx->sweep_launches = ctx->other_launches = 0;
+    ctx->kernel_launches = ctx->h2d_bytes = ctx->d2h_bytes = 0;
+    for (int i = 0; i < 8; ++i) CUDA_TRY(cudaEventCreate(&ctx->ev[i]));
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
     *out = ctx;
@@ -70,6 +82,7 @@ extern "C" int blipgpu_ctx_destroy(blipgpu_ctx* ctx)
     cudaStreamSynchronize(ctx->stream2);
     cudaStreamDestroy(ctx->stream);
     cudaStreamDestroy(ctx->stream2);
+    for (int i = 0; i < 8; ++i) cudaEventDestroy(ctx->ev[i]);
     delete ctx;
     return BLIP_OK;
 }
@@ -91,6 +104,38 @@ extern "C" int blipgpu_ctx_timing(blipgpu_ctx* ctx, double* sweep_ms, int64_t* s
     if (other_ms) *other_ms = ctx->other_ms;
     if (other_launches) *other_launches = ctx->other_launches;
     if (reset) { ctx->sweep_ms = ctx->other_ms = 0.0; ctx->sweep_launches = ctx->other_launches = 0; }
+    return BLIP_OK;
+}
+
+extern "C" int blipgpu_ctx_counters(blipgpu_ctx* ctx, int64_t* kernel_launches, int64_t* h2d_bytes,
+                                    int64_t* d2h_bytes, int reset)
+{
+    if (!ctx) { blip_set_error("NULL context"); return BLIP_ERR_ARG; }
+    if (kernel_launches) *kernel_launches = ctx->kernel_launches;
+    if (h2d_bytes) *h2d_bytes = ctx->h2d_bytes;
+    if (d2h_bytes) *d2h_bytes = ctx->d2h_bytes;
+    if (reset) ctx->kernel_launches = ctx->h2d_bytes = ctx->d2h_bytes = 0;
+    return BLIP_OK;
+}
+
+extern "C" int blipgpu_ctx_event_record(blipgpu_ctx* ctx, int slot)
+{
+    BLIP_TRY(blip_ctx_activate(ctx));
+    if (slot < 0 || slot >= 8) { blip_set_error("event slot out of range"); return BLIP_ERR_ARG; }
+    CUDA_TRY(cudaEventRecord(ctx->ev[slot], ctx->stream));
+    return BLIP_OK;
+}
+
+extern "C" int blipgpu_ctx_event_elapsed_ms(blipgpu_ctx* ctx, int slot_begin, int slot_end, double* ms)
+{
+    BLIP_TRY(blip_ctx_activate(ctx));
+    if (slot_begin < 0 || slot_begin >= 8 || slot_end < 0 || slot_end >= 8 || !ms) {
+        blip_set_error("event_elapsed: bad arguments"); return BLIP_ERR_ARG;
+    }
+    CUDA_TRY(cudaEventSynchronize(ctx->ev[slot_end]));
+    float f = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&f, ctx->ev[slot_begin], ctx->ev[slot_end]));
+    *ms = f;
     return BLIP_OK;
 }
 
@@ -154,6 +199,7 @@ extern "C" int blipgpu_design_upload(blipgpu_ctx* ctx, const double* X, int64_t 
     xl2_kernel<<<(unsigned)((p + 7) / 8), 256, 0, ctx->stream>>>(d->XT, d->Xl2, n, p, d->ldx);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    ctx->kernel_launches += 2; ctx->h2d_bytes += (int64_t)sizeof(double) * n * p;
     CUDA_TRY(cudaFree(Xrow));
     *out = d;
     return BLIP_OK;

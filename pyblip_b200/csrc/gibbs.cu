@@ -76,8 +76,9 @@ __global__ void init_state_kernel(SweepParams P, const double* __restrict__ y, i
         }
     }
     if (tid == 0) {
-        P.hstate[4 * c + 0] = P.cfg.sigma2; P.hstate[4 * c + 1] = P.cfg.tau2;
-        P.hstate[4 * c + 2] = P.cfg.p0;     P.hstate[4 * c + 3] = P.yy;
+        P.hstate[GB_HS * c + 0] = P.cfg.sigma2; P.hstate[GB_HS * c + 1] = P.cfg.tau2;
+        P.hstate[GB_HS * c + 2] = P.cfg.p0;     P.hstate[GB_HS * c + 3] = P.yy;
+        P.hstate[GB_HS * c + 4] = 0.0;          P.hstate[GB_HS * c + 5] = 0.0;
         if (probit) { P.events[2 * c] = 1u; P.events[2 * c + 1] = 1u; }
     }
 }
@@ -194,7 +195,7 @@ extern "C" int blipgpu_sample_spikeslab(blipgpu_ctx* ctx, blipgpu_design* design
     DevBuf d_perm[2], d_u, d_zn, d_ig, d_p0, d_g;
     DevBuf snap_beta, snap_r, snap_mu, snap_ylat, snap_q, snap_h, snap_mask, snap_ev;
     BLIP_TRY(d_beta.alloc(sizeof(double) * chains * p));
-    BLIP_TRY(d_h.alloc(sizeof(double) * chains * 4));
+    BLIP_TRY(d_h.alloc(sizeof(double) * chains * GB_HS));
     BLIP_TRY(d_mask.alloc(sizeof(uint32_t) * chains * words));
     BLIP_TRY(d_ovf.alloc(sizeof(int)));
     BLIP_TRY(snap_beta.alloc(d_beta.bytes)); BLIP_TRY(snap_h.alloc(d_h.bytes)); BLIP_TRY(snap_mask.alloc(d_mask.bytes));
@@ -226,6 +227,11 @@ extern "C" int blipgpu_sample_spikeslab(blipgpu_ctx* ctx, blipgpu_design* design
     smp->bits = nullptr; smp->row_off = nullptr; smp->row_nnz = nullptr; smp->values = nullptr;
     smp->arena_used = nullptr; smp->hyper = nullptr; smp->latents = nullptr;
     smp->n_events = 0; smp->mode = mode; smp->sweep_ms = 0.0; smp->sweep_launches = 0;
+    smp->total_ms = 0.0; smp->n_changes = 0; smp->n_windows = 0; smp->n_sweeps_total = chains * n_total;
+    cudaEvent_t ev_call0, ev_call1;
+    CUDA_TRY(cudaEventCreate(&ev_call0)); CUDA_TRY(cudaEventCreate(&ev_call1));
+    struct CallEv { cudaEvent_t a, b; ~CallEv() { cudaEventDestroy(a); cudaEventDestroy(b); } } callev{ ev_call0, ev_call1 };
+    CUDA_TRY(cudaEventRecord(ev_call0, ctx->stream));
     struct Guard { blipgpu_samples* s; ~Guard() { if (s) blipgpu_samples_free(s); } } guard{ smp };
     const bool keep_lat = probit && (!opts || opts->keep_latents != 0);
     {
@@ -407,8 +413,23 @@ extern "C" int blipgpu_sample_spikeslab(blipgpu_ctx* ctx, blipgpu_design* design
         }
         if (!inj_perm) CUDA_TRY(cudaEventRecord(ev_done[buf], st));
     }
-    CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaStreamSynchronize(st2));
+    CUDA_TRY(cudaEventRecord(ev_call1, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    {
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, ev_call0, ev_call1));
+        smp->total_ms = ms;
+        std::vector<double> hs((size_t)chains * GB_HS);
+        CUDA_TRY(cudaMemcpy(hs.data(), d_h.ptr, d_h.bytes, cudaMemcpyDeviceToHost));
+        for (int64_t c = 0; c < chains; ++c) {
+            smp->n_changes += (int64_t)hs[(size_t)(GB_HS * c + 4)];
+            smp->n_windows += (int64_t)hs[(size_t)(GB_HS * c + 5)];
+        }
+        // kernels: init + (x'y) + per chunk (permutation + sweep, sweeps counted by the timer)
+        ctx->kernel_launches += 1 + (gram && design->kind == BLIPGPU_DESIGN_DENSE ? 1 : 0) + (inj_perm ? 0 : nchunks);
+        ctx->h2d_bytes += (int64_t)(probit ? sizeof(int32_t) : sizeof(double)) * n;
+    }
     if (probit) {
         std::vector<uint32_t> ev((size_t)chains * 2);
         CUDA_TRY(cudaMemcpy(ev.data(), d_ev.ptr, d_ev.bytes, cudaMemcpyDeviceToHost));

@@ -22,6 +22,7 @@
 constexpr int GB_BLOCK = 256;
 constexpr int GB_NWARP = GB_BLOCK / 32;
 constexpr int GB_ROUND = 32;      // residual mode: columns speculated per window
+constexpr int GB_HS = 6;          // doubles of per-chain scalar state: sigma2 tau2 p0 rr n_changes n_windows
 
 struct SweepParams {
     // design
@@ -37,7 +38,7 @@ struct SweepParams {
     double* mu;        // [chains][n2]            probit
     double* ylat;      // [chains][n2]            probit
     double* q;         // [chains][p2]            gram mode
-    double* hstate;    // [chains][4]  sigma2, tau2, p0, rr
+    double* hstate;    // [chains][GB_HS]  sigma2, tau2, p0, rr, #changes, #windows
     uint32_t* mask;    // [chains][words]  active-set bitmask
     uint32_t* events;  // [chains][2]  probit: redraw events so far, latents-dirty flag
     // random streams
@@ -247,9 +248,10 @@ __global__ void __launch_bounds__(GB_BLOCK, 2) gibbs_residual_kernel(SweepParams
     }
     for (int w = tid; w < P.words; w += GB_BLOCK) mask_s[w] = P.mask[(int64_t)c * P.words + w];
     if (tid == 0) {
-        sh.sigma2 = P.hstate[4 * c + 0]; sh.tau2 = P.hstate[4 * c + 1];
-        sh.p0 = P.hstate[4 * c + 2]; sh.rr = 0.0;
+        sh.sigma2 = P.hstate[GB_HS * c + 0]; sh.tau2 = P.hstate[GB_HS * c + 1];
+        sh.p0 = P.hstate[GB_HS * c + 2]; sh.rr = 0.0;
     }
+    long long n_changes = 0, n_windows = 0;     // block-uniform work counters
     uint32_t event = PROBIT ? P.events[2 * c] : 0u;
     bool dirty = PROBIT ? (P.events[2 * c + 1] != 0u) : false;
     __syncthreads();
@@ -267,6 +269,7 @@ __global__ void __launch_bounds__(GB_BLOCK, 2) gibbs_residual_kernel(SweepParams
         int pos0 = 0;
         while (pos0 < p) {
             const int T = min(GB_ROUND, p - pos0);
+            ++n_windows;
             // ---- speculative dots of the next T columns against the current residual
             const int jl = perm_s[min(pos0 + lane, p - 1)];
             double acc[GB_ROUND];
@@ -325,6 +328,7 @@ __global__ void __launch_bounds__(GB_BLOCK, 2) gibbs_residual_kernel(SweepParams
             if (tstar < 0) { pos0 += T; continue; }
 
             // ---- apply the first changing coordinate exactly like the reference
+            ++n_changes;
             const int j = bc.jstar;
             const double beta_old = bc.beta_old;
             const double* xcol = P.XT + (int64_t)j * P.ldx;
@@ -400,7 +404,8 @@ __global__ void __launch_bounds__(GB_BLOCK, 2) gibbs_residual_kernel(SweepParams
     }
     for (int w = tid; w < P.words; w += GB_BLOCK) P.mask[(int64_t)c * P.words + w] = mask_s[w];
     if (tid == 0) {
-        P.hstate[4 * c + 0] = sh.sigma2; P.hstate[4 * c + 1] = sh.tau2; P.hstate[4 * c + 2] = sh.p0;
+        P.hstate[GB_HS * c + 0] = sh.sigma2; P.hstate[GB_HS * c + 1] = sh.tau2; P.hstate[GB_HS * c + 2] = sh.p0;
+        P.hstate[GB_HS * c + 4] += (double)n_changes; P.hstate[GB_HS * c + 5] += (double)n_windows;
         if (PROBIT) { P.events[2 * c] = event; P.events[2 * c + 1] = dirty ? 1u : 0u; }
     }
 }
@@ -442,12 +447,13 @@ __global__ void __launch_bounds__(GB_BLOCK, 2) gibbs_gram_kernel(SweepParams P)
     if (QSMEM) for (int k = tid; k < p2; k += GB_BLOCK) q[k] = q_g[k];
     for (int w = tid; w < P.words; w += GB_BLOCK) mask_s[w] = P.mask[(int64_t)c * P.words + w];
     if (tid == 0) {
-        sh.sigma2 = P.hstate[4 * c + 0]; sh.tau2 = P.hstate[4 * c + 1];
-        sh.p0 = P.hstate[4 * c + 2]; sh.rr = P.hstate[4 * c + 3];
+        sh.sigma2 = P.hstate[GB_HS * c + 0]; sh.tau2 = P.hstate[GB_HS * c + 1];
+        sh.p0 = P.hstate[GB_HS * c + 2]; sh.rr = P.hstate[GB_HS * c + 3];
     }
     __syncthreads();
 
     int parity = 0;
+    long long n_changes = 0, n_windows = 0;     // block-uniform work counters
     for (int s = 0; s < P.S; ++s) {
         const int sweep = P.sweep0 + s;
         const int64_t soff = ((int64_t)c * P.S + s) * p;
@@ -493,6 +499,7 @@ __global__ void __launch_bounds__(GB_BLOCK, 2) gibbs_gram_kernel(SweepParams P)
         int pos0 = 0;
         while (pos0 < p) {
             const int pos = pos0 + tid;
+            ++n_windows;
             bool change = false, act = false, spike = true;
             int j = 0;
             double qj = 0.0, xl2 = 0.0, beta_old = 0.0, XjTr = 0.0;
@@ -519,6 +526,7 @@ __global__ void __launch_bounds__(GB_BLOCK, 2) gibbs_gram_kernel(SweepParams P)
             }
             parity ^= 1;
             if (tstar < 0) { pos0 += GB_BLOCK; continue; }
+            ++n_changes;
             if (tid == tstar) {
                 double bnew = 0.0;
                 if (!spike) {
@@ -555,7 +563,8 @@ __global__ void __launch_bounds__(GB_BLOCK, 2) gibbs_gram_kernel(SweepParams P)
     if (QSMEM) for (int k = tid; k < p2; k += GB_BLOCK) q_g[k] = q[k];
     for (int w = tid; w < P.words; w += GB_BLOCK) P.mask[(int64_t)c * P.words + w] = mask_s[w];
     if (tid == 0) {
-        P.hstate[4 * c + 0] = sh.sigma2; P.hstate[4 * c + 1] = sh.tau2;
-        P.hstate[4 * c + 2] = sh.p0; P.hstate[4 * c + 3] = sh.rr;
+        P.hstate[GB_HS * c + 0] = sh.sigma2; P.hstate[GB_HS * c + 1] = sh.tau2;
+        P.hstate[GB_HS * c + 2] = sh.p0; P.hstate[GB_HS * c + 3] = sh.rr;
+        P.hstate[GB_HS * c + 4] += (double)n_changes; P.hstate[GB_HS * c + 5] += (double)n_windows;
     }
 }

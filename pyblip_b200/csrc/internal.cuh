@@ -11,6 +11,8 @@ struct blipgpu_ctx {
     cudaStream_t stream2;  // permutation generation, copies
     double sweep_ms, other_ms;
     int64_t sweep_launches, other_launches;
+    int64_t kernel_launches, h2d_bytes, d2h_bytes;
+    cudaEvent_t ev[8];
 };
 
 struct blipgpu_design {
@@ -37,8 +39,9 @@ struct blipgpu_samples {
     double* latents;       // [rows][n] or NULL
     int64_t n_events;
     int mode;
-    double sweep_ms;
+    double sweep_ms, total_ms;
     int64_t sweep_launches;
+    int64_t n_changes, n_windows, n_sweeps_total;
 };
 
 struct blipgpu_bits {
@@ -69,6 +72,7 @@ struct ScopedTimer {
         cudaEventDestroy(e0); cudaEventDestroy(e1); ok = false;
         if (sweep) { ctx->sweep_ms += ms; ctx->sweep_launches += launches; }
         else { ctx->other_ms += ms; ctx->other_launches += launches; }
+        ctx->kernel_launches += launches;
         return ms;
     }
     ~ScopedTimer() { if (ok) { cudaEventDestroy(e0); cudaEventDestroy(e1); } }

@@ -75,6 +75,8 @@ extern "C" int blipgpu_samples_info_get(blipgpu_samples* s, blipgpu_samples_info
     info->n_keep = s->n_keep; info->nnz = (int64_t)used; info->n_events = s->n_events;
     info->has_latents = s->latents ? 1 : 0; info->mode = s->mode;
     info->sweep_ms = s->sweep_ms; info->sweep_launches = s->sweep_launches;
+    info->total_ms = s->total_ms; info->n_changes = s->n_changes; info->n_windows = s->n_windows;
+    info->n_sweeps_total = s->n_sweeps_total;
     info->bytes_device = (int64_t)(sizeof(uint32_t) * s->words * s->rows_pad + sizeof(double) * s->arena_cap +
                                    sizeof(double) * 3 * s->rows + 12 * s->rows +
                                    (s->latents ? sizeof(double) * s->rows * s->n : 0));
@@ -86,6 +88,7 @@ extern "C" int blipgpu_samples_hyper(blipgpu_samples* s, double* p0s, double* ta
     if (!s) { blip_set_error("samples_hyper: NULL handle"); return BLIP_ERR_ARG; }
     BLIP_TRY(blip_ctx_activate(s->ctx));
     const size_t b = sizeof(double) * s->rows;
+    s->ctx->d2h_bytes += (int64_t)b * ((p0s != nullptr) + (tau2s != nullptr) + (sigma2s != nullptr));
     if (p0s) CUDA_TRY(cudaMemcpy(p0s, s->hyper, b, cudaMemcpyDeviceToHost));
     if (tau2s) CUDA_TRY(cudaMemcpy(tau2s, s->hyper + s->rows, b, cudaMemcpyDeviceToHost));
     if (sigma2s) CUDA_TRY(cudaMemcpy(sigma2s, s->hyper + 2 * s->rows, b, cudaMemcpyDeviceToHost));
@@ -107,6 +110,7 @@ extern "C" int blipgpu_samples_dense(blipgpu_samples* s, int64_t row0, int64_t r
     for (int64_t r = row0; r < row1 && rc == BLIP_OK; r += stage_rows) {
         const int64_t nr = std::min<int64_t>(stage_rows, row1 - r);
         cudaMemsetAsync(stage, 0, sizeof(double) * nr * s->p, st);
+        s->ctx->kernel_launches += 1; s->ctx->d2h_bytes += (int64_t)sizeof(double) * nr * s->p;
         dense_rows_kernel<<<(unsigned)nr, GB_BLOCK, 0, st>>>(s->bits, s->row_off, s->values, s->rows_pad,
                                                             (int)s->words, (int)s->p, r, stage);
         e = cudaMemcpyAsync(out + (r - row0) * s->p, stage, sizeof(double) * nr * s->p, cudaMemcpyDeviceToHost, st);
@@ -141,6 +145,9 @@ extern "C" int blipgpu_samples_csr(blipgpu_samples* s, int64_t* indptr, int32_t*
     e = cudaMemcpyAsync(d_indptr, indptr, sizeof(int64_t) * (s->rows + 1), cudaMemcpyHostToDevice, st);
     csr_rows_kernel<<<(unsigned)s->rows, GB_BLOCK, 0, st>>>(s->bits, s->row_off, s->values, d_indptr, s->rows_pad,
                                                            (int)s->words, d_idx, d_val);
+    s->ctx->kernel_launches += 1;
+    s->ctx->d2h_bytes += (int64_t)(sizeof(int32_t) + sizeof(double)) * total + (int64_t)sizeof(int32_t) * s->rows;
+    s->ctx->h2d_bytes += (int64_t)sizeof(int64_t) * (s->rows + 1);
     if (e == cudaSuccess) e = cudaMemcpyAsync(indices, d_idx, sizeof(int32_t) * total, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(values, d_val, sizeof(double) * total, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);

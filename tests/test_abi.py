@@ -1,0 +1,61 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol the header declares."""
+import ctypes
+import os
+import re
+
+from pyblip_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "blipgpu.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(blipgpu_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    syms = _header_symbols()
+    assert len(syms) >= 30
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/blipgpu.h but not exported"
+    assert sorted(_lib.SYMBOLS) == syms, "pyblip_b200/_lib.py SYMBOLS out of sync with the header"
+    assert lib.blipgpu_abi_version() == 1
+
+
+def test_struct_layouts_match_header_sizes():
+    lib = _lib.load()
+    for which, cls in enumerate([_lib.SpikeSlabConfig, _lib.Streams, _lib.SampleOptions,
+                                 _lib.SamplesInfo]):
+        assert ctypes.sizeof(cls) == lib.blipgpu_sizeof(which), cls.__name__
+    # 13 scalars of _sample_spikeslab: 10 doubles + 3 int32 (each padded to 8)
+    assert ctypes.sizeof(_lib.SpikeSlabConfig) == 104
+
+
+def test_no_cpu_fallback_without_gpu():
+    """Without a device the product path must fail loudly, not fall back."""
+    try:
+        n = _lib.device_count()
+    except _lib.BlipGpuError:
+        n = 0
+    if n > 0:
+        return   # GPU box: nothing to check here
+    import numpy as np
+    import pytest
+    from pyblip_b200 import LinearSpikeSlab, create_groups
+    lm = LinearSpikeSlab(np.random.randn(10, 4), np.random.randn(10))
+    with pytest.raises(Exception):
+        lm.sample(N=5, chains=1)
+    with pytest.raises(Exception):
+        create_groups.sequential_groups(np.eye(4))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "pyblip_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+                assert "gibbs_oracle" not in text.replace("oracle/gibbs_oracle.c", ""), f

@@ -1,0 +1,93 @@
+"""The CPU oracle against the reference's recorded outputs (tests/golden/*.npz).
+
+The fixtures were produced by oracle/pin_against_reference.py from the reference's own
+compiled Cython kernel running with its native random sources; replaying the recorded
+stream through the oracle must give identical indicators and <= 1e-11 relative agreement.
+"""
+import numpy as np
+import pytest
+
+import blip_testutil as util
+from oracle import gibbs_oracle as go
+
+
+@pytest.mark.parametrize("name", util.SAMPLER_CASES)
+def test_oracle_replays_reference(name):
+    case = util.load_sampler_case(name)
+    hp = go.hparams(**case["hp"])
+    for c, cd in enumerate(case["chains_data"]):
+        st = cd["streams"]
+        if case["probit"]:
+            out = go.sample_spikeslab(case["N"], case["X"], z=case["y"].astype(np.int64),
+                                      probit=True, hp=hp, seed=case["tn_seed"], chain=c, **st)
+        else:
+            out = go.sample_spikeslab(case["N"], case["X"], y=case["y"], hp=hp,
+                                      seed=case["tn_seed"], chain=c, **st)
+        ref = cd["ref"]
+        assert np.array_equal(out["betas"] != 0, ref["betas"] != 0)
+        for key in ("betas", "p0s", "tau2s", "sigma2s"):
+            assert util.rel_err(out[key], ref[key]) <= 1e-11, (name, c, key)
+        if case["probit"]:
+            assert util.rel_err(out["y_latent"], ref["y_latent"]) <= 1e-11
+
+
+def test_philox_known_answer():
+    """Random123 known-answer vectors for Philox4x32-10."""
+    assert go.philox(0, 0, 0, 0, 0, 0).tolist() == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    out = go.philox(0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff)
+    assert out.tolist() == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    out = go.philox(0xa4093822, 0x299f31d0, 0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344)
+    assert out.tolist() == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_keyed_permutation_is_a_permutation_and_depends_on_key():
+    a = go.permutation(5, 0, 0, 1000)
+    assert sorted(a.tolist()) == list(range(1000))
+    assert not np.array_equal(a, go.permutation(5, 1, 0, 1000))
+    assert not np.array_equal(a, go.permutation(5, 0, 1, 1000))
+    assert np.array_equal(a, go.permutation(5, 0, 0, 1000))
+
+
+def test_keyed_gamma_beta_laws():
+    import scipy.stats as st
+    lib = go.lib()
+    for shape in (0.4, 1.0, 2.5, 51.0, 502.0):
+        x = np.array([lib.orc_gamma(9, 1, 0, i, shape) for i in range(20000)])
+        assert st.kstest(x, st.gamma(shape).cdf).pvalue > 1e-3, shape
+    x = np.array([lib.orc_beta(9, 2, 0, i, 451.0, 51.0) for i in range(20000)])
+    assert st.kstest(x, st.beta(451.0, 51.0).cdf).pvalue > 1e-3
+
+
+def test_truncnorm_law_and_support():
+    import scipy.stats as st
+    lib = go.lib()
+    for mean, lower in [(0.0, 0), (1.3, 1), (-2.0, 0), (2.5, 1)]:
+        x = np.array([lib.orc_truncnorm(7, 3, e, 0, mean, 1.5, 0.0, lower) for e in range(20000)])
+        sd = np.sqrt(1.5)
+        if lower:
+            assert np.all(x < 0)
+            dist = st.truncnorm(-np.inf, (0 - mean) / sd, loc=mean, scale=sd)
+        else:
+            assert np.all(x > 0)
+            dist = st.truncnorm((0 - mean) / sd, np.inf, loc=mean, scale=sd)
+        assert st.kstest(x, dist.cdf).pvalue > 1e-3
+
+
+def test_oracle_conjugate_posterior():
+    """Reference test_mcmc.py:12-57 restated for the oracle: with hyper-updates off and
+    p0 ~ 0 the chain samples the conjugate Gaussian posterior."""
+    rng = np.random.default_rng(123)
+    n, p, M = 20, 3, 6000
+    X = rng.standard_normal((n, p))
+    X = X - X.mean(axis=0)
+    beta = rng.standard_normal(p)
+    y = X @ beta + rng.standard_normal(n)
+    hp = go.hparams(tau2=1, update_tau2=False, sigma2=1, update_sigma2=False, p0=1e-9,
+                    update_p0=False)
+    out = go.sample_spikeslab(2 * M, X, y=y, hp=hp, seed=3, chain=0)
+    S11I = np.linalg.inv(np.eye(n) + X @ X.T)
+    cond_mean = X.T @ S11I @ y
+    cond_var = np.eye(p) - X.T @ S11I @ X
+    b = out["betas"][M:]
+    np.testing.assert_allclose(b.mean(0), cond_mean, atol=0.03)
+    np.testing.assert_allclose(np.cov(b.T), cond_var, atol=0.03)
