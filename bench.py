@@ -10,8 +10,8 @@ spike-and-slab sampler (BASELINE.json metric) on N B200s.
 Workload (BASELINE.json configs[1]): LinearSpikeSlab, n=1000,
 p=10000, AR(1) rho=0.95 design, 50 signals, 512 chains sharded over the ranks, default
 hyper-priors.  One step = one full sampler pass of `--sweeps` recorded sweeps after
-`--burn` burn-in sweeps for every chain (a bounded slice of the N=5000 job; throughput
-is per-sweep stationary after the first few sweeps).  Rank 0 prints ONE JSON line.
+`--burn` burn-in sweeps for every chain -- by default the configuration's full job,
+N=5000 after 100 burn-in sweeps.  Rank 0 prints ONE JSON line.
 
   value     device-resident inputs: X and X'X already in HBM; timed region = the C-ABI
             sampler call (state init, permutations, sweeps, recording into HBM),
@@ -249,12 +249,14 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--sweeps", type=int, default=400, help="recorded sweeps per step")
+    ap.add_argument("--sweeps", type=int, default=5000, help="recorded sweeps per step (N)")
     ap.add_argument("--burn", type=int, default=100)
     ap.add_argument("--mode", default="gram", choices=["gram", "residual"])
     ap.add_argument("--ref-sweeps", type=int, default=200, dest="ref_sweeps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-clocks", action="store_true")
+    ap.add_argument("--debug", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -277,18 +279,24 @@ def main():
     S, B = args.sweeps, args.burn
 
     def step(seed):
+        t0 = time.perf_counter()
         smp = _lib.sample_spikeslab(design, cfg, y=y, chains=nloc, chain_offset=c0, n_keep=S,
                                     burn=B, seed=seed, mode=mode_id)
+        t1 = time.perf_counter()
         info = smp.info
         out = dict(total_ms=info.total_ms, sweep_ms=info.sweep_ms, launches=info.sweep_launches,
                    changes=info.n_changes, windows=info.n_windows, nnz=info.nnz)
         smp.close()
+        if args.debug and rank == 0:
+            print(f"[step] call {1e3 * (t1 - t0):.1f} ms  device {info.total_ms:.1f} ms  sweep kernels "
+                  f"{info.sweep_ms:.1f} ms  close {1e3 * (time.perf_counter() - t1):.1f} ms  "
+                  f"nnz/row {info.nnz / max(info.rows, 1):.1f}", file=sys.stderr, flush=True)
         return out
 
     for w in range(args.warmup):
         step(1000 + w)
     clocks = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not args.no_clocks:
         clocks.start()
     barrier(dist, ctx)
     ctx.counters(reset=True)

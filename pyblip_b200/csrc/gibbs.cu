@@ -17,14 +17,15 @@ namespace {
 // permutations: one thread per (chain, sweep) runs Fisher-Yates from identity,
 // Philox words indexed by (step >> 2, sweep, chain).
 // ---------------------------------------------------------------------------
-__global__ void perm_fill_kernel(int32_t* perm, int chains, int S, int p, int sweep0, uint32_t k0,
+template <typename T>
+__global__ void perm_fill_kernel(T* perm, int chains, int S, int p, int sweep0, uint32_t k0,
                                  uint32_t k1, uint32_t chain_offset)
 {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)chains * S) return;
     const int c = (int)(t / S), s = (int)(t % S);
-    int32_t* a = perm + t * p;
-    for (int j = 0; j < p; ++j) a[j] = j;
+    T* a = perm + t * p;
+    for (int j = 0; j < p; ++j) a[j] = (T)j;
     const uint32_t chain = chain_offset + (uint32_t)c, sweep = (uint32_t)(sweep0 + s);
     uint4 w = make_uint4(0, 0, 0, 0);
     int have = -1;
@@ -36,7 +37,7 @@ __global__ void perm_fill_kernel(int32_t* perm, int chains, int S, int p, int sw
         const int sel = k & 3;
         const uint32_t x = sel == 0 ? w.x : sel == 1 ? w.y : sel == 2 ? w.z : w.w;
         const int j = (int)(((uint64_t)x * (uint64_t)(k + 1)) >> 32);
-        int32_t tmp = a[k]; a[k] = a[j]; a[j] = tmp;
+        T tmp = a[k]; a[k] = a[j]; a[j] = tmp;
     }
 }
 
@@ -181,6 +182,18 @@ extern "C" int blipgpu_sample_spikeslab(blipgpu_ctx* ctx, blipgpu_design* design
         S = (int)std::min<int64_t>(S, n_total);
     }
     const bool inj_perm = streams && streams->perm;
+    // Permutations are generated for PS sweeps at a time (a multiple of the launch chunk S):
+    // Fisher-Yates is latency bound, so more (chain, sweep) pairs per launch amortise it.
+    // 16-bit entries when p allows; <= 1.5 GB per buffer, two buffers.
+    const bool perm16 = !inj_perm && p <= 65535;
+    const size_t perm_elt = perm16 ? sizeof(uint16_t) : sizeof(int32_t);
+    int64_t PS = S;
+    if (!inj_perm) {
+        const double per_sweep = (double)perm_elt * (double)chains * (double)p;
+        int64_t mult = std::max<int64_t>(1, (int64_t)(1.5e9 / per_sweep) / S);
+        mult = std::min<int64_t>(mult, std::max<int64_t>(1, 256 / S));
+        PS = std::min<int64_t>(S * mult, round_up(n_total, S));
+    }
     const bool inj_u = streams && streams->u, inj_z = streams && streams->z;
     const bool inj_ig = streams && streams->invgamma, inj_p0 = streams && streams->p0_draw;
     const bool inj_g = streams && streams->gamma_draw;
@@ -212,8 +225,8 @@ extern "C" int blipgpu_sample_spikeslab(blipgpu_ctx* ctx, blipgpu_design* design
         }
     }
     if (!probit) BLIP_TRY(d_y.alloc(sizeof(double) * n));
-    BLIP_TRY(d_perm[0].alloc(sizeof(int32_t) * chains * S * p));
-    if (!inj_perm && n_total > S) BLIP_TRY(d_perm[1].alloc(sizeof(int32_t) * chains * S * p));
+    BLIP_TRY(d_perm[0].alloc(perm_elt * chains * PS * p));
+    if (!inj_perm && n_total > S) BLIP_TRY(d_perm[1].alloc(perm_elt * chains * PS * p));
     if (inj_u) BLIP_TRY(d_u.alloc(sizeof(double) * chains * S * p));
     if (inj_z) BLIP_TRY(d_zn.alloc(sizeof(double) * chains * S * p));
     if (inj_ig) BLIP_TRY(d_ig.alloc(sizeof(double) * chains * S));
@@ -320,25 +333,45 @@ extern "C" int blipgpu_sample_spikeslab(blipgpu_ctx* ctx, blipgpu_design* design
         // wait until the sweep that last used this buffer has finished
         CUDA_TRY(cudaStreamWaitEvent(st2, ev_done[buf], 0));
         const int64_t nt = chains * Sc;
-        perm_fill_kernel<<<(unsigned)((nt + 63) / 64), 64, 0, st2>>>(d_perm[buf].as<int32_t>(), (int)chains, Sc, (int)p,
-                                                                   (int)sweep0, P.k0, P.k1, P.chain_offset);
+        if (perm16)
+            perm_fill_kernel<uint16_t><<<(unsigned)((nt + 63) / 64), 64, 0, st2>>>(d_perm[buf].as<uint16_t>(), (int)chains, Sc, (int)p,
+                                                                                 (int)sweep0, P.k0, P.k1, P.chain_offset);
+        else
+            perm_fill_kernel<int32_t><<<(unsigned)((nt + 63) / 64), 64, 0, st2>>>(d_perm[buf].as<int32_t>(), (int)chains, Sc, (int)p,
+                                                                                (int)sweep0, P.k0, P.k1, P.chain_offset);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(ev_perm[buf], st2));
         return BLIP_OK;
     };
 
     const int64_t nchunks = (n_total + S - 1) / S;
-    if (!inj_perm) BLIP_TRY(gen_perm(0, 0, (int)std::min<int64_t>(S, n_total)));
+    // permutation chunk boundaries: a short first chunk (nothing can hide its generation),
+    // then PS sweeps each
+    std::vector<int64_t> pstart;
+    if (!inj_perm) {
+        pstart.push_back(0);
+        int64_t at = std::min<int64_t>(S, n_total);
+        while (at < n_total) { pstart.push_back(at); at = std::min<int64_t>(at + PS, n_total); }
+        pstart.push_back(n_total);
+    }
+    const int64_t n_perm_chunks = inj_perm ? 0 : (int64_t)pstart.size() - 1;
+    if (!inj_perm) BLIP_TRY(gen_perm(0, 0, (int)(pstart[1] - pstart[0])));
+    int64_t pc = 0;
     int64_t max_chunk_use = 0;
     unsigned long long used_before = 0;
     for (int64_t ch = 0; ch < nchunks; ++ch) {
         const int64_t sweep0 = ch * S;
         const int Sc = (int)std::min<int64_t>(S, n_total - sweep0);
-        const int buf = inj_perm ? 0 : (int)(ch & 1);
+        if (!inj_perm) while (sweep0 >= pstart[(size_t)pc + 1]) ++pc;   // permutation chunk of this launch
+        const int buf = inj_perm ? 0 : (int)(pc & 1);
+        const int64_t pc_sweep0 = inj_perm ? sweep0 : pstart[(size_t)pc];
+        const int64_t pc_end = inj_perm ? sweep0 + Sc : pstart[(size_t)pc + 1];
+        const int PSc = (int)(pc_end - pc_sweep0);
         if (inj_perm) BLIP_TRY(upload_chunk(d_perm[0].as<int32_t>(), streams->perm, chains, n_total * p, sweep0 * p, (int64_t)Sc * p, st));
-        else {
+        else if (sweep0 == pc_sweep0) {                             // first launch of a permutation chunk
             CUDA_TRY(cudaStreamWaitEvent(st, ev_perm[buf], 0));
-            if (ch + 1 < nchunks) BLIP_TRY(gen_perm(buf ^ 1, sweep0 + S, (int)std::min<int64_t>(S, n_total - sweep0 - S)));
+            if (pc + 1 < n_perm_chunks)
+                BLIP_TRY(gen_perm(buf ^ 1, pstart[(size_t)pc + 1], (int)(pstart[(size_t)pc + 2] - pstart[(size_t)pc + 1])));
         }
         if (inj_u) BLIP_TRY(upload_chunk(d_u.as<double>(), streams->u, chains, n_total * p, sweep0 * p, (int64_t)Sc * p, st));
         if (inj_z) BLIP_TRY(upload_chunk(d_zn.as<double>(), streams->z, chains, n_total * p, sweep0 * p, (int64_t)Sc * p, st));
@@ -379,7 +412,8 @@ extern "C" int blipgpu_sample_spikeslab(blipgpu_ctx* ctx, blipgpu_design* design
         BLIP_TRY(copy_state(true));
 
         for (int attempt = 0;; ++attempt) {
-            P.perm = d_perm[buf].as<int32_t>();
+            P.perm = d_perm[buf].ptr; P.perm16 = perm16 ? 1 : 0;
+            P.perm_S = PSc; P.perm_s0 = inj_perm ? 0 : (int)(sweep0 - pc_sweep0);
             P.u = d_u.as<double>(); P.z = d_zn.as<double>(); P.invgamma = d_ig.as<double>();
             P.p0_draw = d_p0.as<double>(); P.gamma_draw = d_g.as<double>();
             P.sweep0 = (int)sweep0; P.S = Sc;
@@ -411,7 +445,8 @@ extern "C" int blipgpu_sample_spikeslab(blipgpu_ctx* ctx, blipgpu_design* design
             max_chunk_use = std::max<int64_t>(max_chunk_use, wanted);
             BLIP_TRY(grow(wanted + wanted / 4 + 1024));
         }
-        if (!inj_perm) CUDA_TRY(cudaEventRecord(ev_done[buf], st));
+        if (!inj_perm && sweep0 + Sc >= pc_end)
+            CUDA_TRY(cudaEventRecord(ev_done[buf], st));           // last launch that reads this buffer
     }
     CUDA_TRY(cudaStreamSynchronize(st2));
     CUDA_TRY(cudaEventRecord(ev_call1, st));
@@ -427,7 +462,7 @@ extern "C" int blipgpu_sample_spikeslab(blipgpu_ctx* ctx, blipgpu_design* design
             smp->n_windows += (int64_t)hs[(size_t)(GB_HS * c + 5)];
         }
         // kernels: init + (x'y) + per chunk (permutation + sweep, sweeps counted by the timer)
-        ctx->kernel_launches += 1 + (gram && design->kind == BLIPGPU_DESIGN_DENSE ? 1 : 0) + (inj_perm ? 0 : nchunks);
+        ctx->kernel_launches += 1 + (gram && design->kind == BLIPGPU_DESIGN_DENSE ? 1 : 0) + (inj_perm ? 0 : n_perm_chunks);
         ctx->h2d_bytes += (int64_t)(probit ? sizeof(int32_t) : sizeof(double)) * n;
     }
     if (probit) {

@@ -43,7 +43,8 @@ struct SweepParams {
     uint32_t* events;  // [chains][2]  probit: redraw events so far, latents-dirty flag
     // random streams
     uint32_t k0, k1; uint32_t chain_offset;
-    const int32_t* perm;       // [chains][S][p]   (generated or injected)
+    const void* perm;          // [chains][perm_S][p] uint16 or int32 (generated or injected);
+    int perm16, perm_S, perm_s0; //   this launch's sweep s is row perm_s0 + s of a chain
     const double* u;           // [chains][S][p] or NULL
     const double* z;           // [chains][S][p] or NULL
     const double* invgamma;    // [chains][S] or NULL
@@ -59,6 +60,18 @@ struct SweepParams {
     double* hyper_out; double* latents;
     int gram_refresh;
 };
+
+struct PermView {           // visiting order of one (chain, sweep)
+    const void* base; int64_t off; int is16;
+    __device__ __forceinline__ int operator[](int pos) const {
+        return is16 ? (int)reinterpret_cast<const uint16_t*>(base)[off + pos]
+                    : reinterpret_cast<const int32_t*>(base)[off + pos];
+    }
+};
+__device__ __forceinline__ PermView perm_view(const SweepParams& P, int c, int s)
+{
+    return PermView{ P.perm, ((int64_t)c * P.perm_S + P.perm_s0 + s) * P.p, P.perm16 };
+}
 
 // ---------------------------------------------------------------------------
 // the scalar part of one coordinate update (_linear.pyx:146-158), fp64, with the
@@ -259,7 +272,7 @@ __global__ void __launch_bounds__(GB_BLOCK, 2) gibbs_residual_kernel(SweepParams
     for (int s = 0; s < P.S; ++s) {
         const int sweep = P.sweep0 + s;
         const int64_t soff = ((int64_t)c * P.S + s) * p;
-        const int32_t* perm_s = P.perm + soff;
+        const PermView perm_s = perm_view(P, c, s);
         const double* u_s = P.u ? P.u + soff : nullptr;
         const double* z_s = P.z ? P.z + soff : nullptr;
         if (tid == 0) sh.logodds = log(sh.p0) - log(1 - sh.p0);   // :76, :222
@@ -414,6 +427,10 @@ __global__ void __launch_bounds__(GB_BLOCK, 2) gibbs_residual_kernel(SweepParams
 // gram mode (linear only)
 // ===========================================================================
 struct GramBcast { int jstar; double delta; };
+constexpr int GB_AXU = 10;         // 16-byte Gram loads in flight per thread in the axpy
+// 2 CTAs x 256 threads x 120 registers leave 4096 registers per SM free, so that the
+// permutation generator (32 registers/thread) can co-reside and overlap with the sweep.
+constexpr int GB_GRAM_REGS = 120;
 
 template <int DESIGN> __device__ __forceinline__ double2 gram_pair(const SweepParams& P, int jstar, int k)
 {
@@ -426,8 +443,43 @@ template <int DESIGN> __device__ __forceinline__ double2 gram_pair(const SweepPa
     }
 }
 
+// q -= delta * G[:, jstar], the whole block; GB_AXU independent 16-byte loads are
+// issued before the first use so that one CTA keeps ~32 KB of the column in flight.
+template <int DESIGN>
+__device__ __forceinline__ void gram_axpy(const SweepParams& P, double* q, int jstar, double delta)
+{
+    const int p2 = P.p2;
+    for (int k0 = 2 * threadIdx.x; k0 < p2; k0 += 2 * GB_BLOCK * GB_AXU) {
+        double2 g[GB_AXU];
+#pragma unroll
+        for (int u = 0; u < GB_AXU; ++u) {
+            const int k = k0 + u * 2 * GB_BLOCK;
+            g[u] = (k < p2) ? gram_pair<DESIGN>(P, jstar, k) : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int u = 0; u < GB_AXU; ++u) {
+            const int k = k0 + u * 2 * GB_BLOCK;
+            if (k < p2) {
+                double2 qq = *reinterpret_cast<double2*>(q + k);
+                qq.x = fma(-delta, g[u].x, qq.x); qq.y = fma(-delta, g[u].y, qq.y);
+                *reinterpret_cast<double2*>(q + k) = qq;
+            }
+        }
+    }
+}
+
+// Sliding speculation window: thread t owns the one position of [pos0, pos0+256)
+// that is congruent to t modulo 256, so a position keeps its thread (and the cached,
+// state-independent part of its decision) when the window restarts after a change.
+//
+// The decision  u <= kappa(XjTr)  is evaluated through the monotone re-arrangement
+//     E := logodds + logdet_j - c1_j * XjTr^2   >=   L := log(u / (1 - u))
+// with A_j = logodds + logdet_j, c1_j and L cached per position.  Outside a guard band
+// around E == L (and away from the saturation / overflow corners) this is provably the
+// same boolean as the reference's floating-point evaluation; inside the band the
+// reference formula itself (kappa_of) is evaluated, so every decision is exact.
 template <int DESIGN, bool QSMEM>
-__global__ void __launch_bounds__(GB_BLOCK, 2) gibbs_gram_kernel(SweepParams P)
+__global__ void __maxnreg__(GB_GRAM_REGS) gibbs_gram_kernel(SweepParams P)
 {
     extern __shared__ __align__(16) double sm[];
     __shared__ SweepShared sh;
@@ -457,7 +509,7 @@ __global__ void __launch_bounds__(GB_BLOCK, 2) gibbs_gram_kernel(SweepParams P)
     for (int s = 0; s < P.S; ++s) {
         const int sweep = P.sweep0 + s;
         const int64_t soff = ((int64_t)c * P.S + s) * p;
-        const int32_t* perm_s = P.perm + soff;
+        const PermView perm_s = perm_view(P, c, s);
         const double* u_s = P.u ? P.u + soff : nullptr;
         const double* z_s = P.z ? P.z + soff : nullptr;
 
@@ -470,13 +522,7 @@ __global__ void __launch_bounds__(GB_BLOCK, 2) gibbs_gram_kernel(SweepParams P)
                 while (m) {
                     int j = 32 * w + __ffs(m) - 1;
                     m &= m - 1;
-                    const double bj = __ldcg(beta_g + j);
-                    for (int k = 2 * tid; k < p2; k += 2 * GB_BLOCK) {
-                        double2 g = gram_pair<DESIGN>(P, j, k);
-                        double2 qq = *reinterpret_cast<double2*>(q + k);
-                        qq.x = fma(-bj, g.x, qq.x); qq.y = fma(-bj, g.y, qq.y);
-                        *reinterpret_cast<double2*>(q + k) = qq;
-                    }
+                    gram_axpy<DESIGN>(P, q, j, __ldcg(beta_g + j));
                 }
             }
             __syncthreads();
@@ -495,65 +541,146 @@ __global__ void __launch_bounds__(GB_BLOCK, 2) gibbs_gram_kernel(SweepParams P)
         if (tid == 0) sh.logodds = log(sh.p0) - log(1 - sh.p0);
         __syncthreads();
         const Hyper h = { sh.sigma2, sh.tau2, sh.logodds };
+        const double ts = h.tau2 / h.sigma2;
+
+        // per-position cache (state-independent within a sweep): filled when a position
+        // enters a thread's ownership, i.e. one window ahead of its first evaluation.
+        // f_A, f_c1, f_L only steer the guarded fast decision, so single precision is
+        // enough for them (the guard band below is 1e-4 relative); anything that reaches
+        // a coefficient or an exact decision (c_u, c_xl2, c_bold, c_zn) stays in fp64.
+        int c_pos = -1, c_j = 0, n_j = 0;
+        bool c_act = false, c_exact = true;
+        float f_A = 0.f, f_c1 = 0.f, f_L = 0.f;
+        double c_xl2 = 0.0, n_xl2 = 0.0, c_bold = 0.0, c_u = 0.0, c_zn = 0.0;
+        bool need_xl2 = false;
+        const float f_logodds = (float)h.logodds, f_tau2 = (float)h.tau2, f_sigma2 = (float)h.sigma2;
+        const float f_ts = (float)ts;
+        auto fill = [&](int pos) {        // needs n_j (and n_xl2) = perm / Xl2 of `pos` (prefetched)
+            c_pos = pos;
+            c_j = n_j;
+            c_xl2 = need_xl2 ? P.Xl2[n_j] : n_xl2;
+            need_xl2 = false;
+            if (pos + GB_BLOCK < p) {     // prefetch for the position this thread owns next;
+                n_j = perm_s[pos + GB_BLOCK];   // Xl2[n_j] is fetched one window later so that
+                need_xl2 = true;                // this dependent load never blocks the fill
+            }
+            c_act = (mask_s[c_j >> 5] >> (c_j & 31)) & 1u;
+            c_bold = c_act ? __ldcg(beta_g + c_j) : 0.0;
+            c_u = u_s ? u_s[pos] : rng_uniform(key, KIND_SPIKE_U, pos, sweep, 0);
+            c_exact = !(c_u > 1e-4 && c_u < 1.0 - 1e-4);
+            const float xl2f = (float)c_xl2;
+            f_A = f_logodds + 0.5f * logf(1.0f + f_tau2 * xl2f / f_sigma2);
+            f_c1 = f_ts / (2.0f * (f_sigma2 + f_tau2 * xl2f));
+            f_L = c_exact ? 0.f : logf((float)(c_u / (1.0 - c_u)));
+            // an active coordinate is redrawn for sure: take its normal off the critical path
+            if (c_act) c_zn = z_s ? z_s[pos] : rng_normal(key, KIND_SLAB_Z, pos, sweep, 0);
+        };
+        if (tid < p) { n_j = perm_s[tid]; n_xl2 = P.Xl2[n_j]; fill(tid); }
 
         int pos0 = 0;
         while (pos0 < p) {
-            const int pos = pos0 + tid;
             ++n_windows;
-            bool change = false, act = false, spike = true;
-            int j = 0;
-            double qj = 0.0, xl2 = 0.0, beta_old = 0.0, XjTr = 0.0;
+            const int off = (tid - pos0) & (GB_BLOCK - 1);
+            const int pos = pos0 + off;
+            bool change = false, spike = true;
+            double qj = 0.0, XjTr = 0.0;
+            if (need_xl2) { n_xl2 = P.Xl2[n_j]; need_xl2 = false; }
             if (pos < p) {
-                j = perm_s[pos];
-                qj = q[j];
-                xl2 = P.Xl2[j];
-                act = (mask_s[j >> 5] >> (j & 31)) & 1u;
-                if (act) beta_old = __ldcg(beta_g + j);
-                XjTr = act ? qj + beta_old * xl2 : qj;      // X_j . (r + beta_j X_j)
-                double u = u_s ? u_s[pos] : rng_uniform(key, KIND_SPIKE_U, pos, sweep, 0);
-                double kappa = kappa_of(XjTr, xl2, h);
-                spike = (u <= kappa);
-                change = act || !spike;
+                if (pos != c_pos) { n_j = perm_s[pos]; n_xl2 = P.Xl2[n_j]; fill(pos); }   // safety net
+                qj = q[c_j];
+                XjTr = c_act ? qj + c_bold * c_xl2 : qj;      // X_j . (r + beta_j X_j)
+                const double x2c = (double)f_c1 * (XjTr * XjTr);
+                const double E = (double)f_A - x2c;
+                const double margin = E - (double)f_L;
+                const double guard = 1e-4 * (1.0 + fabs((double)f_A) + x2c + fabs((double)f_L));
+                if (c_exact || !(fabs(margin) > guard) || !(fmax(E, (double)f_L) < 20.0)) {
+                    spike = (c_u <= kappa_of(XjTr, c_xl2, h));   // the reference's own formula
+                } else {
+                    spike = margin > 0.0;
+                }
+                change = c_act || !spike;
             }
             const unsigned m = __ballot_sync(0xffffffffu, change);
             if (lane == 0) flags[parity][warp] = m;
             __syncthreads();
-            int tstar = -1;
+            // first changed position in window order = first set bit at/after bit r, cyclically
+            const int r = pos0 & (GB_BLOCK - 1);
+            int first = -1;
+            {
+                const int w0 = r >> 5, b0 = r & 31;
 #pragma unroll
-            for (int w = GB_NWARP - 1; w >= 0; --w) {
-                unsigned f = flags[parity][w];
-                if (f) tstar = 32 * w + __ffs(f) - 1;
+                for (int i = GB_NWARP; i >= 0; --i) {       // scan backwards so the earliest wins
+                    const int w = (w0 + i) & (GB_NWARP - 1);
+                    unsigned f = flags[parity][w];
+                    if (i == 0) f &= (0xffffffffu << b0);
+                    else if (i == GB_NWARP) f &= ~(0xffffffffu << b0);   // b0 == 0 -> empty
+                    if (f) first = ((32 * w + __ffs(f) - 1) - r) & (GB_BLOCK - 1);
+                }
             }
             parity ^= 1;
-            if (tstar < 0) { pos0 += GB_BLOCK; continue; }
+            if (first < 0) {                                  // the whole window was null
+                pos0 += GB_BLOCK;
+                if (pos + GB_BLOCK < p) fill(pos + GB_BLOCK); else c_pos = -1;
+                continue;
+            }
             ++n_changes;
-            if (tid == tstar) {
+            // Everybody knows the changing coordinate without waiting for its owner, so the
+            // first GB_AXU 16-byte loads of its Gram column go out before the slab draw and
+            // before the leaving positions are re-filled: their latency hides behind that math.
+            const int jstar = perm_s[pos0 + first];
+            double2 g[GB_AXU];
+#pragma unroll
+            for (int u = 0; u < GB_AXU; ++u) {
+                const int k = 2 * tid + u * 2 * GB_BLOCK;
+                g[u] = (k < p2) ? gram_pair<DESIGN>(P, jstar, k) : make_double2(0.0, 0.0);
+            }
+            if (off == first) {
                 double bnew = 0.0;
                 if (!spike) {
-                    double zn = z_s ? z_s[pos] : rng_normal(key, KIND_SLAB_Z, pos, sweep, 0);
-                    bnew = slab_draw(XjTr, xl2, h, zn);
+                    const double zn = c_act ? c_zn
+                                            : (z_s ? z_s[pos] : rng_normal(key, KIND_SLAB_Z, pos, sweep, 0));
+                    bnew = slab_draw(XjTr, c_xl2, h, zn);
                 }
-                const double delta = bnew - beta_old;
-                bc.jstar = j; bc.delta = delta;
+                const double delta = bnew - c_bold;
+                bc.jstar = c_j; bc.delta = delta;
                 // ||r - delta X_j||^2 = ||r||^2 - 2 delta X_j.r + delta^2 ||X_j||^2
-                sh.rr = sh.rr - 2.0 * delta * qj + delta * delta * xl2;
-                __stcg(beta_g + j, bnew);
-                if (bnew != 0) mask_s[j >> 5] |= (1u << (j & 31));
-                else mask_s[j >> 5] &= ~(1u << (j & 31));
+                sh.rr = sh.rr - 2.0 * delta * qj + delta * delta * c_xl2;
+                __stcg(beta_g + c_j, bnew);
+                if (bnew != 0) mask_s[c_j >> 5] |= (1u << (c_j & 31));
+                else mask_s[c_j >> 5] &= ~(1u << (c_j & 31));
+            }
+            if (off <= first) {                               // my position leaves the window
+                if (pos + GB_BLOCK < p) fill(pos + GB_BLOCK); else c_pos = -1;
             }
             __syncthreads();
-            const double delta = bc.delta;
-            const int jstar = bc.jstar;
-            if (delta != 0) {                   // q -= delta * G[:, j*]
-                for (int k = 2 * tid; k < p2; k += 2 * GB_BLOCK) {
-                    double2 g = gram_pair<DESIGN>(P, jstar, k);
+            const double delta = bc.delta;                    // q -= delta * G[:, j*]
+#pragma unroll
+            for (int u = 0; u < GB_AXU; ++u) {
+                const int k = 2 * tid + u * 2 * GB_BLOCK;
+                if (k < p2) {
                     double2 qq = *reinterpret_cast<double2*>(q + k);
-                    qq.x = fma(-delta, g.x, qq.x); qq.y = fma(-delta, g.y, qq.y);
+                    qq.x = fma(-delta, g[u].x, qq.x); qq.y = fma(-delta, g[u].y, qq.y);
                     *reinterpret_cast<double2*>(q + k) = qq;
                 }
             }
+            for (int k0 = 2 * tid + GB_AXU * 2 * GB_BLOCK; k0 < p2; k0 += 2 * GB_BLOCK * GB_AXU) {
+#pragma unroll
+                for (int u = 0; u < GB_AXU; ++u) {
+                    const int k = k0 + u * 2 * GB_BLOCK;
+                    g[u] = (k < p2) ? gram_pair<DESIGN>(P, jstar, k) : make_double2(0.0, 0.0);
+                }
+#pragma unroll
+                for (int u = 0; u < GB_AXU; ++u) {
+                    const int k = k0 + u * 2 * GB_BLOCK;
+                    if (k < p2) {
+                        double2 qq = *reinterpret_cast<double2*>(q + k);
+                        qq.x = fma(-delta, g[u].x, qq.x); qq.y = fma(-delta, g[u].y, qq.y);
+                        *reinterpret_cast<double2*>(q + k) = qq;
+                    }
+                }
+            }
             __syncthreads();
-            pos0 += tstar + 1;
+            pos0 += first + 1;
         }
 
         sweep_epilogue(P, &sh, mask_s, beta_g, scratch, key, c, s, sh.rr, nullptr, false);
