@@ -268,5 +268,52 @@ def main():
           {k: (round(a, 3), round(b, 3)) for k, (a, b) in res.items()})
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--longrun" not in sys.argv:
     main()
+
+
+# ---------------------------------------------------------------------------
+# long-run posterior summaries of the reference (native RNG), for the
+# "PIPs within 4 Monte-Carlo standard errors" gate
+# ---------------------------------------------------------------------------
+def longrun_reference():
+    ref_loader.load()
+    from pyblip.linear import _linear as lin
+    out = {}
+    # linear: n=100, p=60, 64 chains x (500 burn + 2000)
+    rng = np.random.default_rng(4242)
+    X, y, beta = make_data(rng, 100, 60, 5, rho=0.9, coef_scale=1.0)
+    chains, burn, N = 64, 500, 2000
+    pips, means, p0m = [], [], []
+    for c in range(chains):
+        np.random.seed(900 + c)
+        r = lin._sample_spikeslab(N=N + burn, X=X, y=y.copy(), z=np.zeros(1, dtype=np.int64), probit=0,
+                                  tau2=1.0, update_tau2=1, tau2_a0=2.0, tau2_b0=1.0, sigma2=1.0,
+                                  update_sigma2=1, sigma2_a0=2.0, sigma2_b0=1.0, p0=0.9, update_p0=1,
+                                  min_p0=0.0, p0_a0=1.0, p0_b0=1.0)
+        b = r["betas"][burn:]
+        pips.append((b != 0).mean(0)); means.append(b.mean(0)); p0m.append(r["p0s"][burn:].mean())
+    out.update(lin_X=X, lin_y=y, lin_beta=beta, lin_pips=np.array(pips), lin_means=np.array(means),
+               lin_p0=np.array(p0m), lin_burn=np.int32(burn), lin_N=np.int32(N))
+    # probit: n=150, p=30, 24 chains x (300 burn + 1000), reference's own truncated normal
+    rng = np.random.default_rng(4343)
+    Xp, yp, betap = make_data(rng, 150, 30, 3, rho=0.5, probit=True, coef_scale=2.0)
+    chains, burn, N = 24, 300, 1000
+    pips, means = [], []
+    for c in range(chains):
+        np.random.seed(950 + c)
+        r = lin._sample_spikeslab(N=N + burn, X=Xp, y=np.zeros(150), z=yp.astype(np.int64), probit=1,
+                                  tau2=1.0, update_tau2=1, tau2_a0=2.0, tau2_b0=1.0, sigma2=1.0,
+                                  update_sigma2=1, sigma2_a0=2.0, sigma2_b0=1.0, p0=0.9, update_p0=1,
+                                  min_p0=0.0, p0_a0=1.0, p0_b0=1.0)
+        b = r["betas"][burn:]
+        pips.append((b != 0).mean(0)); means.append(b.mean(0))
+    out.update(pro_X=Xp, pro_y=yp, pro_beta=betap, pro_pips=np.array(pips), pro_means=np.array(means),
+               pro_burn=np.int32(burn), pro_N=np.int32(N))
+    np.savez_compressed(os.path.join(GOLDEN, "longrun_reference.npz"), **out)
+    print("[pin] longrun_reference: linear PIP range", out["lin_pips"].mean(0).min(), out["lin_pips"].mean(0).max(),
+          " probit PIP range", out["pro_pips"].mean(0).min(), out["pro_pips"].mean(0).max())
+
+
+if __name__ == "__main__" and "--longrun" in sys.argv:
+    longrun_reference()

