@@ -130,6 +130,44 @@ int blipgpu_sample_spikeslab(blipgpu_ctx* ctx, blipgpu_design* design,
                              const blipgpu_sample_options* opts,
                              blipgpu_samples** out);
 
+/* ---- neuronized-prior sampler ------------------------------------------ */
+/* Scalars of `_nprior_sample` (pyblip/nprior/_nprior.pyx:56-73). */
+typedef struct blipgpu_nprior_config {
+    double tauw2, p0_init, min_p0; int32_t update_p0;
+    double sigma_a0, sigma_b0;
+    int32_t sigma_prior_type, joint_sample_W, group_alpha_update, reserved;
+} blipgpu_nprior_config;
+
+/* Optional injected stream for the neuronized-prior sampler (HOST arrays, chain-major;
+ * NULL member = keyed Philox stream).  N = n_keep + burn. */
+typedef struct blipgpu_nprior_streams {
+    const int32_t* perm;       /* [chains][N][p] visiting order                             */
+    const double* u;           /* [chains][N][p] mixture uniform at position s              */
+    const double* wz;          /* [chains][N][p] normal of the w_j update at position s     */
+    const double* alpha_init;  /* [chains][p]    N(0,1) behind alphas[0] (:98)              */
+    const double* w_fresh;     /* [chains][N][p] N(0,1) behind the fresh ws rows (:100)     */
+    const double* sigma_init;  /* [chains]       N(0,1) behind sigma2s[0] (:117)            */
+    const double* joint_all;   /* [chains][N][p] randn(p) of _sample_w (:288)               */
+    const double* joint_act;   /* [chains][N][p] randn(num_active) of _sample_w, padded     */
+    const double* delta_z;     /* [chains][N]    group-move normal (:500)                   */
+    const double* invgamma;    /* [chains][N]                                               */
+    const double* p0_draw;     /* [chains][N]    Beta variates (:465-468)                   */
+} blipgpu_nprior_streams;
+
+typedef struct blipgpu_nprior blipgpu_nprior;   /* dense alphas / ws / betas on the device */
+
+/* Replaces `apply_pool(_nprior_sample, ...)` (pyblip/nprior/nprior.py:126-147): all chains of
+ * this rank in one call.  Needs a dense design; builds the Gram matrix if necessary. */
+int blipgpu_sample_nprior(blipgpu_ctx* ctx, blipgpu_design* design, const blipgpu_nprior_config* cfg,
+                          const double* y, int64_t chains, int64_t chain_offset, int64_t n_keep,
+                          int64_t burn, uint64_t seed, const blipgpu_nprior_streams* streams,
+                          blipgpu_nprior** out);
+/* which: 0 alphas, 1 ws, 2 betas ([rows][p]); 3 sigma2s, 4 alpha0s, 5 p0s ([rows]); host out */
+int blipgpu_nprior_get(blipgpu_nprior* r, int32_t which, double* out);
+int blipgpu_nprior_info(blipgpu_nprior* r, int64_t* rows, int64_t* p, double* sweep_ms);
+int blipgpu_nprior_bits(blipgpu_nprior* r, blipgpu_bits** out);   /* betas != 0, for counting */
+int blipgpu_nprior_free(blipgpu_nprior* r);
+
 /* ---- samples handle ---------------------------------------------------- */
 typedef struct blipgpu_samples_info {
     int64_t rows;        /* chains * n_keep, chain-major like linear.py:165-168   */

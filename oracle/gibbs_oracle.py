@@ -154,3 +154,55 @@ def sample_spikeslab(N, X, y=None, z=None, probit=False, hp=None, seed=0, chain=
     if probit:
         out["y_latent"] = ylat
     return out
+
+
+# ---------------------------------------------------------------------------
+# neuronized prior (oracle/nprior_oracle.c)
+# ---------------------------------------------------------------------------
+class NPriorStreams(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in
+                ("perm", "u", "wz", "alpha_init", "w_fresh", "sigma_init", "joint_all",
+                 "joint_act", "delta_z", "invgamma", "p0_draw")]
+
+
+def nprior_sample(N, X, y, tauw2, p0_init=None, min_p0=1e-10, update_p0=True, sigma_a0=5.0,
+                  sigma_b0=1.0, sigma_prior_type=0, joint_sample_W=True, group_alpha_update=True,
+                  seed=0, chain=0, streams=None):
+    """One chain of ``_nprior_sample`` (/root/reference/pyblip/nprior/_nprior.pyx:56).
+    `streams`: dict of injected arrays (see NPriorStreams); missing keys use the keyed stream."""
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    n, p = X.shape
+    if p0_init is None:
+        p0_init = 1 - min(0.01, 1 / p)
+    streams = streams or {}
+    keep = {}
+    shapes = dict(perm=(N, p), u=(N, p), wz=(N, p), alpha_init=(p,), w_fresh=(N, p),
+                  sigma_init=(1,), joint_all=(N, p), joint_act=(N, p), delta_z=(N,),
+                  invgamma=(N,), p0_draw=(N,))
+    st = NPriorStreams()
+    for k, shp in shapes.items():
+        a = streams.get(k)
+        if a is None:
+            setattr(st, k, None)
+            continue
+        a = np.ascontiguousarray(a, dtype=np.int32 if k == "perm" else np.float64)
+        assert a.shape == shp, (k, a.shape, shp)
+        keep[k] = a
+        setattr(st, k, a.ctypes.data)
+    alphas, ws, betas = np.zeros((N, p)), np.zeros((N, p)), np.zeros((N, p))
+    sigma2s, alpha0s, p0s = np.ones(N), np.zeros(N), np.zeros(N)
+    f = lib().orc_nprior_sample
+    f.restype = C.c_int
+    rc = f(C.c_int(N), C.c_int(n), C.c_int(p), C.c_void_p(X.ctypes.data), C.c_void_p(y.ctypes.data),
+           C.c_double(tauw2), C.c_double(p0_init), C.c_double(min_p0), C.c_int(int(update_p0)),
+           C.c_double(sigma_a0), C.c_double(sigma_b0), C.c_int(int(sigma_prior_type)),
+           C.c_int(int(joint_sample_W)), C.c_int(int(group_alpha_update)),
+           C.c_uint64(seed), C.c_uint32(chain), C.byref(st),
+           C.c_void_p(alphas.ctypes.data), C.c_void_p(ws.ctypes.data), C.c_void_p(betas.ctypes.data),
+           C.c_void_p(sigma2s.ctypes.data), C.c_void_p(alpha0s.ctypes.data), C.c_void_p(p0s.ctypes.data))
+    if rc == 2:
+        raise ValueError("Cholesky of the active-set precision failed")
+    if rc != 0:
+        raise MemoryError("oracle allocation failed")
+    return dict(alphas=alphas, ws=ws, betas=betas, sigma2s=sigma2s, alpha0s=alpha0s, p0s=p0s)

@@ -4,9 +4,10 @@ Same Python API as amspector100/pyblip for the multi-chain Gibbs samplers and th
 candidate-group PIP counting; everything numeric runs in libblipgpu.so
 (hand-written CUDA for sm_100a).  There is no CPU fallback.
 """
-from . import linear, probit, create_groups, changepoint
+from . import linear, probit, nprior, create_groups, changepoint
 from .linear import LinearSpikeSlab
 from .probit import ProbitSpikeSlab
+from .nprior import NPrior
 
 name = "pyblip_b200"
 __version__ = "0.1.0"

@@ -27,6 +27,8 @@ SYMBOLS = [
     "blipgpu_design_upload", "blipgpu_design_changepoint", "blipgpu_design_build_gram",
     "blipgpu_design_get_gram", "blipgpu_design_get_xl2", "blipgpu_design_free",
     "blipgpu_sample_spikeslab",
+    "blipgpu_sample_nprior", "blipgpu_nprior_get", "blipgpu_nprior_info", "blipgpu_nprior_bits",
+    "blipgpu_nprior_free",
     "blipgpu_samples_info_get", "blipgpu_samples_hyper", "blipgpu_samples_dense",
     "blipgpu_samples_csr", "blipgpu_samples_latents", "blipgpu_samples_free",
     "blipgpu_bits_from_samples", "blipgpu_bits_from_dense", "blipgpu_bits_shape",
@@ -455,3 +457,85 @@ class Bits:
             self.close()
         except Exception:
             pass
+
+
+# ---------------------------------------------------------------------------
+# neuronized prior
+# ---------------------------------------------------------------------------
+class NPriorConfig(C.Structure):
+    """``blipgpu_nprior_config``: scalars of ``_nprior_sample``
+    (/root/reference/pyblip/nprior/_nprior.pyx:56-73)."""
+    _fields_ = [
+        ("tauw2", C.c_double), ("p0_init", C.c_double), ("min_p0", C.c_double),
+        ("update_p0", C.c_int32), ("sigma_a0", C.c_double), ("sigma_b0", C.c_double),
+        ("sigma_prior_type", C.c_int32), ("joint_sample_W", C.c_int32),
+        ("group_alpha_update", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+NPRIOR_STREAM_KEYS = ("perm", "u", "wz", "alpha_init", "w_fresh", "sigma_init", "joint_all",
+                      "joint_act", "delta_z", "invgamma", "p0_draw")
+
+
+class NPriorStreams(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in NPRIOR_STREAM_KEYS]
+
+
+class NPriorSamples:
+    """Dense alphas / ws / betas of all chains on the device (``blipgpu_nprior``)."""
+    _WHICH = dict(alphas=0, ws=1, betas=2, sigma2s=3, alpha0s=4, p0s=5)
+
+    def __init__(self, ctx, handle):
+        self.ctx, self._h = ctx, handle
+        rows, p, ms = C.c_int64(), C.c_int64(), C.c_double()
+        check(load().blipgpu_nprior_info(self._h, C.byref(rows), C.byref(p), C.byref(ms)))
+        self.rows, self.p, self.sweep_ms = rows.value, p.value, ms.value
+
+    def get(self, name):
+        which = self._WHICH[name]
+        out = np.empty((self.rows, self.p) if which < 3 else (self.rows,))
+        check(load().blipgpu_nprior_get(self._h, C.c_int32(which), C.c_void_p(out.ctypes.data)))
+        return out
+
+    def bits(self, zero_first_column=False):
+        h = C.c_void_p()
+        check(load().blipgpu_nprior_bits(self._h, C.byref(h)))
+        return Bits(self.ctx, h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load().blipgpu_nprior_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def sample_nprior(design, cfg, y, chains=1, chain_offset=0, n_keep=1, burn=0, seed=0, streams=None):
+    """All chains of this rank in one call (``blipgpu_sample_nprior``)."""
+    n, p = design.n, design.p
+    N = n_keep + burn
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    if y.shape != (n,):
+        raise ValueError("y must have shape (n,)")
+    st_ptr, keep = None, []
+    if streams:
+        shapes = dict(perm=(chains, N, p), u=(chains, N, p), wz=(chains, N, p),
+                      alpha_init=(chains, p), w_fresh=(chains, N, p), sigma_init=(chains,),
+                      joint_all=(chains, N, p), joint_act=(chains, N, p), delta_z=(chains, N),
+                      invgamma=(chains, N), p0_draw=(chains, N))
+        st = NPriorStreams()
+        for k in NPRIOR_STREAM_KEYS:
+            a = _opt_array(streams.get(k), np.int32 if k == "perm" else np.float64, shapes[k])
+            keep.append(a)
+            setattr(st, k, None if a is None else a.ctypes.data)
+        st_ptr = C.byref(st)
+    h = C.c_void_p()
+    check(load().blipgpu_sample_nprior(design.ctx._h, design._h, C.byref(cfg), C.c_void_p(y.ctypes.data),
+                                       C.c_int64(chains), C.c_int64(chain_offset), C.c_int64(n_keep),
+                                       C.c_int64(burn), C.c_uint64(seed), st_ptr, C.byref(h)))
+    del keep
+    return NPriorSamples(design.ctx, h)

@@ -103,7 +103,7 @@ def _as_device(samples, zero_first_column=False):
     handle = getattr(samples, "samples_handle", None)
     if handle is not None:
         samples = handle
-    if isinstance(samples, _lib.Samples):
+    if isinstance(samples, (_lib.Samples, _lib.NPriorSamples)):
         return _DeviceSamples(samples.bits(zero_first_column=zero_first_column), True)
     arr = np.asarray(samples)
     if arr.ndim != 2:

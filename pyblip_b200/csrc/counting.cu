@@ -261,6 +261,8 @@ int with_output(blipgpu_ctx* ctx, int64_t count, int64_t* out, int out_is_device
 
 } // namespace
 
+int blip_bits_alloc(blipgpu_ctx* ctx, int64_t N, int64_t p, blipgpu_bits** out) { return alloc_bits(ctx, N, p, out); }
+
 extern "C" int blipgpu_bits_from_samples(blipgpu_samples* s, int32_t zero_first_column, blipgpu_bits** out)
 {
     if (!s || !out) { blip_set_error("bits_from_samples: bad arguments"); return BLIP_ERR_ARG; }

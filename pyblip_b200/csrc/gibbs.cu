@@ -113,6 +113,27 @@ int upload_chunk(T* dst, const T* src_host, int64_t chains, int64_t total_per_ch
 
 } // namespace
 
+// helpers shared with the other samplers (declared in internal.cuh)
+int blip_fill_perms(cudaStream_t st, void* buf, int perm16, int64_t chains, int S, int64_t p,
+                    int64_t sweep0, uint32_t k0, uint32_t k1, uint32_t chain_offset)
+{
+    const int64_t nt = chains * S;
+    if (nt <= 0) return BLIP_OK;
+    if (perm16)
+        perm_fill_kernel<uint16_t><<<(unsigned)((nt + 63) / 64), 64, 0, st>>>((uint16_t*)buf, (int)chains, S, (int)p, (int)sweep0, k0, k1, chain_offset);
+    else
+        perm_fill_kernel<int32_t><<<(unsigned)((nt + 63) / 64), 64, 0, st>>>((int32_t*)buf, (int)chains, S, (int)p, (int)sweep0, k0, k1, chain_offset);
+    CUDA_TRY(cudaGetLastError());
+    return BLIP_OK;
+}
+
+int blip_xty(cudaStream_t st, const blipgpu_design* d, const double* d_y, double* d_q0)
+{
+    xty_kernel<<<(unsigned)((d->p + 7) / 8), 256, 0, st>>>(d->XT, d_y, d_q0, d->n, d->p, d->ldx);
+    CUDA_TRY(cudaGetLastError());
+    return BLIP_OK;
+}
+
 extern "C" int blipgpu_sample_spikeslab(blipgpu_ctx* ctx, blipgpu_design* design,
                                         const blipgpu_spikeslab_config* cfg, const double* y,
                                         const int64_t* z, int32_t probit, int64_t chains,

@@ -53,6 +53,11 @@ struct blipgpu_bits {
 
 // helpers implemented in api.cu
 int blip_ctx_activate(blipgpu_ctx* ctx);
+// helpers implemented in gibbs.cu
+int blip_fill_perms(cudaStream_t st, void* buf, int perm16, int64_t chains, int S, int64_t p,
+                    int64_t sweep0, uint32_t k0, uint32_t k1, uint32_t chain_offset);
+int blip_xty(cudaStream_t st, const blipgpu_design* d, const double* d_y, double* d_q0);
+int blip_bits_alloc(blipgpu_ctx* ctx, int64_t N, int64_t p, blipgpu_bits** out);   // counting.cu
 static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
 // event-timed region on ctx->stream

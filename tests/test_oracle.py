@@ -91,3 +91,19 @@ def test_oracle_conjugate_posterior():
     b = out["betas"][M:]
     np.testing.assert_allclose(b.mean(0), cond_mean, atol=0.03)
     np.testing.assert_allclose(np.cov(b.T), cond_var, atol=0.03)
+
+
+@pytest.mark.parametrize("name", ["nprior_joint_group", "nprior_plain", "nprior_sigprior",
+                                  "nprior_fixedp0"])
+def test_nprior_oracle_replays_reference(name):
+    """oracle/nprior_oracle.c against the reference's recorded run (oracle/pin_nprior.py)."""
+    import os
+    d = np.load(os.path.join(util.GOLDEN, name + ".npz"))
+    kw = {k[3:]: float(d[k]) for k in d.files if k.startswith("kw_")}
+    for k in ("update_p0", "sigma_prior_type", "joint_sample_W", "group_alpha_update"):
+        kw[k] = int(kw[k])
+    st = {k[3:]: d[k] for k in d.files if k.startswith("st_")}
+    out = go.nprior_sample(int(d["N"]), d["X"], d["y"], seed=int(d["seed"]), chain=0, streams=st, **kw)
+    assert np.array_equal(out["betas"] != 0, d["ref_betas"] != 0)
+    for k in ("alphas", "ws", "betas", "sigma2s", "alpha0s", "p0s"):
+        assert util.rel_err(out[k], d["ref_" + k]) <= 1e-9, (name, k)
