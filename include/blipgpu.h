@@ -227,6 +227,27 @@ int blipgpu_count_groups(blipgpu_bits* b, const int64_t* offsets, const int64_t*
                          int64_t n_groups, int64_t* any_counts, int32_t out_is_device);
 int blipgpu_bits_free(blipgpu_bits* b);
 
+/* ---- continuous-space candidate regions -------------------------------- */
+typedef struct blipgpu_gridcounts blipgpu_gridcounts;
+/* Replaces the per-sample Python loops of `grid_peps` (pyblip/create_groups_cts.py:152-206).
+ * locs: HOST [N][n_src][d] float64 in [0,1], NaN rows = no signal.  For every grid size the
+ * cell containing each signal (and, if circle != 0 and d == 2, the axis-neighbour circles that
+ * also contain it, :47-66) is found, de-duplicated per sample and counted over samples.
+ * Optional extra centres (:165-184) with their per-grid radii.  Result: integer codes
+ *   bit 63 extra-centre flag | bits 56-62 grid index | low 56 bits: (cell coordinate + 1) packed
+ *   in 56/d bits per dimension (d <= 3), or the extra-centre index,
+ * with the number of samples containing each code; if want_pairs != 0 additionally one
+ * (code, multiplicity) pair per (sample, code) for `count_signals=True`. */
+int blipgpu_grid_count(blipgpu_ctx* ctx, const double* locs, int64_t N, int64_t n_src, int32_t d,
+                       const double* grid_sizes, int32_t G, int32_t circle,
+                       const double* extra_centers, int64_t n_extra, const double* extra_radii,
+                       const uint64_t* extra_codes /* [n_extra][G]: code counted for (centre, grid) */,
+                       int32_t want_pairs, blipgpu_gridcounts** out);
+int blipgpu_gridcounts_sizes(blipgpu_gridcounts* r, int64_t* n_keys, int64_t* n_pairs);
+int blipgpu_gridcounts_get(blipgpu_gridcounts* r, uint64_t* codes, uint32_t* counts,
+                           uint64_t* pair_codes, uint32_t* pair_mult);
+int blipgpu_gridcounts_free(blipgpu_gridcounts* r);
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,6 +35,7 @@ SYMBOLS = [
     "blipgpu_bits_select_columns", "blipgpu_bits_to_dense",
     "blipgpu_count_columns", "blipgpu_count_sequential", "blipgpu_count_groups",
     "blipgpu_bits_free",
+    "blipgpu_grid_count", "blipgpu_gridcounts_sizes", "blipgpu_gridcounts_get", "blipgpu_gridcounts_free",
 ]
 
 
@@ -539,3 +540,40 @@ def sample_nprior(design, cfg, y, chains=1, chain_offset=0, n_keep=1, burn=0, se
                                        C.c_int64(burn), C.c_uint64(seed), st_ptr, C.byref(h)))
     del keep
     return NPriorSamples(design.ctx, h)
+
+
+# ---------------------------------------------------------------------------
+# continuous-space region counting
+# ---------------------------------------------------------------------------
+def grid_count(locs, grid_sizes, circle, extra_centers=None, extra_radii=None, extra_codes=None,
+               want_pairs=False, ctx=None):
+    """``blipgpu_grid_count``: returns (codes u64, counts u32, pair_codes u64, pair_mult u32)."""
+    ctx = ctx or Context.get()
+    locs = np.ascontiguousarray(locs, dtype=np.float64)
+    N, n_src, d = locs.shape
+    grid = np.ascontiguousarray(grid_sizes, dtype=np.float64)
+    n_extra = 0
+    ecp = erp = ecc = None
+    if extra_centers is not None and len(extra_centers) > 0:
+        ec = np.ascontiguousarray(extra_centers, dtype=np.float64)
+        er = np.ascontiguousarray(extra_radii, dtype=np.float64)
+        eco = np.ascontiguousarray(extra_codes, dtype=np.uint64)
+        n_extra, ecp, erp, ecc = ec.shape[0], ec.ctypes.data, er.ctypes.data, eco.ctypes.data
+    h = C.c_void_p()
+    check(load().blipgpu_grid_count(ctx._h, C.c_void_p(locs.ctypes.data), C.c_int64(N), C.c_int64(n_src),
+                                    C.c_int32(d), C.c_void_p(grid.ctypes.data), C.c_int32(grid.shape[0]),
+                                    C.c_int32(int(bool(circle))), C.c_void_p(ecp), C.c_int64(n_extra),
+                                    C.c_void_p(erp), C.c_void_p(ecc), C.c_int32(int(bool(want_pairs))),
+                                    C.byref(h)))
+    try:
+        nk, npair = C.c_int64(), C.c_int64()
+        check(load().blipgpu_gridcounts_sizes(h, C.byref(nk), C.byref(npair)))
+        codes = np.empty(max(nk.value, 1), dtype=np.uint64)
+        counts = np.empty(max(nk.value, 1), dtype=np.uint32)
+        pcodes = np.empty(max(npair.value, 1), dtype=np.uint64)
+        pmult = np.empty(max(npair.value, 1), dtype=np.uint32)
+        check(load().blipgpu_gridcounts_get(h, C.c_void_p(codes.ctypes.data), C.c_void_p(counts.ctypes.data),
+                                            C.c_void_p(pcodes.ctypes.data), C.c_void_p(pmult.ctypes.data)))
+    finally:
+        load().blipgpu_gridcounts_free(h)
+    return codes[:nk.value], counts[:nk.value], pcodes[:npair.value], pmult[:npair.value]

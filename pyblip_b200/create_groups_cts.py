@@ -1,0 +1,160 @@
+"""Candidate regions when signals live in a continuous d-dimensional space.
+
+Drop-in for ``grid_peps`` / ``normalize_locs`` of
+/root/reference/pyblip/create_groups_cts.py:18-224.  The per-sample loops over grid
+sizes and points (:152-206) run on the B200 (``blipgpu_grid_count``): integer cell codes
+are de-duplicated per sample and counted over samples on the device; the host only turns
+each distinct code back into the reference's float key -- with the reference's own
+expression, so keys are bit-identical -- and each count k into the reference's running sum
+``1/N + ... + 1/N`` (k terms, :190-194), which is not always ``k/N``.
+"""
+import numpy as np
+
+from . import _lib, dist
+
+TOL = 1e-10
+
+
+def normalize_locs(locs):
+    """Shift/scale ``locs`` (N, num_disc, d) into [0, 1] per dimension (:18-45).
+    Returns (norm_locs, shifts, scales); NaNs stay NaN."""
+    min_val = np.nanmin(np.nanmin(locs, axis=0), axis=0)
+    max_val = np.nanmax(np.nanmax(locs, axis=0), axis=0)
+    shifts, scales = min_val, max_val - min_val
+    return (locs - shifts) / scales, shifts, scales
+
+
+def _merge_over_ranks(codes, counts):
+    d = dist._dist()
+    if d is None or d.get_world_size() == 1:
+        return codes, counts
+    parts = [None] * d.get_world_size()
+    d.all_gather_object(parts, (codes, counts))
+    allc = np.concatenate([p[0] for p in parts])
+    alln = np.concatenate([p[1] for p in parts]).astype(np.int64)
+    uniq, inv = np.unique(allc, return_inverse=True)
+    return uniq, np.bincount(inv, weights=alln, minlength=uniq.shape[0]).astype(np.int64)
+
+
+def grid_peps(
+    locs,
+    grid_sizes,
+    count_signals=False,
+    extra_centers=None,
+    max_pep=0.25,
+    log_interval=None,
+    time0=None,
+    shape='square'
+):
+    """
+    Same parameters and return value as the reference (:103-224): a dict mapping
+    ``(center_1, ..., center_d, radius)`` to its PEP (or, with ``count_signals``, to
+    ``{n_signals: prob, ..., 'pip': prob}``) for every region with ``pep <= max_pep``.
+    ``log_interval`` / ``time0`` are accepted and ignored.  Under ``torchrun`` each rank
+    passes ITS samples; counts are merged over ranks.
+    """
+    locs = np.asarray(locs, dtype=np.float64)
+    if np.nanmin(locs) < -TOL or np.nanmax(locs) > 1 + TOL:
+        raise ValueError(
+            "locs are not normalized: apply create_groups_cts.normalize_locs first."
+        )
+    if shape not in ('square', 'circle'):
+        raise ValueError(f"Unrecognized shape={shape}, must be one of 'square', 'circle'")
+    N_local, _, d = locs.shape
+    if shape == 'circle' and d != 2:
+        raise NotImplementedError(
+            f"Shape=circle only implemented for 2-d data, but detected {d} dimensions"
+        )
+    grid_all = np.asarray(list(grid_sizes), dtype=np.float64)
+    # a repeated grid size yields the same keys again: the reference's per-sample set() absorbs
+    # it, its Counter (count_signals) counts every repeat -- handled through `repeat` below
+    grid, repeat = np.unique(grid_all, return_counts=True)
+    world = dist.world()[1]
+    N = dist.allreduce_scalar(N_local) if world > 1 else N_local
+
+    # radii exactly as the reference writes them (:86-90 for cells, :175-177 for extra centres)
+    cell_radius = [np.sqrt(d) / (2 * g) if shape == 'circle' else 1 / (2 * g) for g in grid]
+    extra_radius = []
+    for g in grid:
+        r = 1 / (2 * g)
+        extra_radius.append(np.sqrt(d) * r if shape == 'circle' else r)
+    n_extra = 0 if extra_centers is None else extra_centers.shape[0]
+
+    bits = {1: 56, 2: 28, 3: 18}.get(d)
+    extra_codes = None
+    if n_extra:
+        # An extra centre whose key equals the key of the grid cell it lies in (same centre after
+        # rounding, same radius) is the SAME dict key in the reference, so both must count as one
+        # per sample: such a (centre, grid) pair is counted under the cell's code.
+        extra_codes = np.empty((n_extra, grid.shape[0]), dtype=np.uint64)
+        for g_idx, g in enumerate(grid):
+            cells = np.floor(extra_centers * g)
+            own = np.around(cells.astype(float) / g + 1 / (2 * g), 10)
+            same = np.all(own == extra_centers, axis=1) & (cell_radius[g_idx] == extra_radius[g_idx])
+            head = np.uint64(g_idx) << np.uint64(56)
+            cell_code = np.full(n_extra, head, dtype=np.uint64)
+            for k in range(d):
+                cell_code |= (cells[:, k].astype(np.int64) + 1).astype(np.uint64) << np.uint64(bits * k)
+            own_code = (np.uint64(1) << np.uint64(63)) | head | np.arange(n_extra, dtype=np.uint64)
+            extra_codes[:, g_idx] = np.where(same, cell_code, own_code)
+    codes, counts, pcodes, pmult = _lib.grid_count(
+        locs, grid, circle=(shape == 'circle'),
+        extra_centers=extra_centers if n_extra else None, extra_radii=extra_radius,
+        extra_codes=extra_codes, want_pairs=count_signals)
+    codes, counts = _merge_over_ranks(codes, counts.astype(np.int64))
+    if count_signals and np.any(repeat > 1):
+        pmult = pmult * repeat[((pcodes >> np.uint64(56)) & np.uint64(0x7f)).astype(np.int64)].astype(pmult.dtype)
+
+    # k repeated additions of 1/N (:190-194) -- cumulative sums, not k/N
+    running = np.cumsum(np.full(max(N, 1), 1 / N)) if N > 0 else np.zeros(1)
+
+    # decode codes -> the reference's float keys
+    is_extra = (codes >> np.uint64(63)).astype(bool)
+    gi = ((codes >> np.uint64(56)) & np.uint64(0x7f)).astype(np.int64)
+    keys = [None] * codes.shape[0]
+    for g_idx in range(grid.shape[0]):
+        sel = np.where((gi == g_idx) & ~is_extra)[0]
+        if sel.size == 0:
+            continue
+        g = grid[g_idx]
+        cells = np.empty((sel.size, d))
+        for k in range(d):
+            mask = np.uint64((1 << bits) - 1)
+            cells[:, k] = ((codes[sel] >> np.uint64(bits * k)) & mask).astype(np.int64) - 1
+        centers = np.around(cells / g + 1 / (2 * g), 10)            # :77-84, :101
+        radius = cell_radius[g_idx]
+        for row, idx in enumerate(sel):
+            keys[idx] = tuple(centers[row]) + (radius,)
+    for idx in np.where(is_extra)[0]:
+        nc = int(codes[idx] & np.uint64((1 << 56) - 1))
+        keys[idx] = tuple(extra_centers[nc]) + (extra_radius[int(gi[idx])],)
+
+    filtered = {}
+    if not count_signals:
+        for key, k in zip(keys, counts):
+            pep = 1 - running[k - 1]
+            if pep <= max_pep:
+                filtered[key] = pep
+        return filtered
+
+    # count_signals: distribution of the per-sample multiplicity of every key (:195-206)
+    if world > 1:
+        d_ = dist._dist()
+        parts = [None] * world
+        d_.all_gather_object(parts, (pcodes, pmult))
+        pcodes = np.concatenate([p[0] for p in parts])
+        pmult = np.concatenate([p[1] for p in parts])
+    index = {int(c): i for i, c in enumerate(codes)}
+    hist = {}
+    if pcodes.size:
+        pairs = np.stack([pcodes, pmult.astype(np.uint64)], axis=1)
+        uniq, cnt = np.unique(pairs, axis=0, return_counts=True)
+        for (c, m), n_s in zip(uniq, cnt):
+            hist.setdefault(int(c), {})[int(m)] = running[n_s - 1]
+    for key, c, k in zip(keys, codes, counts):
+        total = running[k - 1]
+        if 1 - total <= max_pep:
+            val = dict(hist.get(int(c), {}))
+            val['pip'] = total
+            filtered[key] = val
+    return filtered
