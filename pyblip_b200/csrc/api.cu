@@ -64,6 +64,8 @@ extern "C" int blipgpu_ctx_create(int device, blipgpu_ctx** out)
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    ctx->smem_per_sm = prop.sharedMemPerMultiprocessor;
+    ctx->smem_reserved = prop.reservedSharedMemPerBlock;
     ctx->sweep_ms = ctx->other_ms = 0.0;
     ctx->sweep_launches = ctx->other_launches = 0;
     ctx->kernel_launches = ctx->h2d_bytes = ctx->d2h_bytes = 0;

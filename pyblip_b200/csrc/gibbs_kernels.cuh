@@ -18,6 +18,7 @@
 //             thread at O(1) cost and a change reads one 8p-byte Gram column.
 #pragma once
 #include "internal.cuh"
+#include <cstdio>
 
 constexpr int GB_BLOCK = 256;
 constexpr int GB_NWARP = GB_BLOCK / 32;
@@ -426,11 +427,18 @@ __global__ void __launch_bounds__(GB_BLOCK, 2) gibbs_residual_kernel(SweepParams
 // ===========================================================================
 // gram mode (linear only)
 // ===========================================================================
-struct GramBcast { int jstar; double delta; };
-constexpr int GB_AXU = 10;         // 16-byte Gram loads in flight per thread in the axpy
-// 2 CTAs x 256 threads x 120 registers leave 4096 registers per SM free, so that the
-// permutation generator (32 registers/thread) can co-reside and overlap with the sweep.
-constexpr int GB_GRAM_REGS = 120;
+struct GramBcast { double delta; };
+#ifdef BLIP_PHASE_CLOCKS
+#define PH_DECL long long ph_t[12] = {0,0,0,0,0,0,0,0,0,0,0,0}; long long ph_last = clock64();
+#define PH(i) do { if (threadIdx.x == 0) { long long _n = clock64(); ph_t[i] += _n - ph_last; ph_last = _n; } } while (0)
+#else
+#define PH_DECL
+#define PH(i) do {} while (0)
+#endif
+constexpr int GB_AXU = 10;         // 16-byte Gram loads a thread keeps in flight
+constexpr int GB_PEND = 5;         // changes whose Gram columns are applied to q in one pass
+constexpr int GB_FLUSH_SLOTS = GB_AXU / GB_PEND;
+constexpr int GB_GRAM_REGS = 128;  // 2 CTAs x 256 threads x 128 registers = the whole register file
 
 template <int DESIGN> __device__ __forceinline__ double2 gram_pair(const SweepParams& P, int jstar, int k)
 {
@@ -442,9 +450,14 @@ template <int DESIGN> __device__ __forceinline__ double2 gram_pair(const SweepPa
         return __ldg(reinterpret_cast<const double2*>(P.G + (int64_t)jstar * P.ldg + k));
     }
 }
+template <int DESIGN> __device__ __forceinline__ double gram_entry(const SweepParams& P, int a, int b)
+{
+    if (DESIGN == BLIPGPU_DESIGN_CHANGEPOINT) return (double)(P.n - max(a, b));
+    else return __ldg(P.G + (int64_t)a * P.ldg + b);
+}
 
 // q -= delta * G[:, jstar], the whole block; GB_AXU independent 16-byte loads are
-// issued before the first use so that one CTA keeps ~32 KB of the column in flight.
+// issued before the first use so that one CTA keeps ~40 KB of the column in flight.
 template <int DESIGN>
 __device__ __forceinline__ void gram_axpy(const SweepParams& P, double* q, int jstar, double delta)
 {
@@ -468,6 +481,40 @@ __device__ __forceinline__ void gram_axpy(const SweepParams& P, double* q, int j
     }
 }
 
+// q -= sum_k pd[k] * G[:, pj[k]] for the npend pending changes, applied element-wise in
+// the order the changes happened (the same fma sequence as npend separate passes), but
+// with q read and written once.  Block-wide; the caller synchronises.
+template <int DESIGN>
+__device__ __forceinline__ void gram_flush(const SweepParams& P, double* q, const int* pj_s,
+                                           const double* pd_s, int npend)
+{
+    const int p2 = P.p2;
+    int pj[GB_PEND]; double pd[GB_PEND];
+#pragma unroll
+    for (int k = 0; k < GB_PEND; ++k) { pj[k] = k < npend ? pj_s[k] : 0; pd[k] = k < npend ? pd_s[k] : 0.0; }
+    for (int k0 = 2 * threadIdx.x; k0 < p2; k0 += 2 * GB_BLOCK * GB_FLUSH_SLOTS) {
+        double2 g[GB_FLUSH_SLOTS][GB_PEND];
+#pragma unroll
+        for (int u = 0; u < GB_FLUSH_SLOTS; ++u) {
+            const int kk = k0 + u * 2 * GB_BLOCK;
+#pragma unroll
+            for (int k = 0; k < GB_PEND; ++k)
+                g[u][k] = (kk < p2 && k < npend) ? gram_pair<DESIGN>(P, pj[k], kk) : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int u = 0; u < GB_FLUSH_SLOTS; ++u) {
+            const int kk = k0 + u * 2 * GB_BLOCK;
+            if (kk < p2) {
+                double2 qq = *reinterpret_cast<double2*>(q + kk);
+#pragma unroll
+                for (int k = 0; k < GB_PEND; ++k)
+                    if (k < npend) { qq.x = fma(-pd[k], g[u][k].x, qq.x); qq.y = fma(-pd[k], g[u][k].y, qq.y); }
+                *reinterpret_cast<double2*>(q + kk) = qq;
+            }
+        }
+    }
+}
+
 // Sliding speculation window: thread t owns the one position of [pos0, pos0+256)
 // that is congruent to t modulo 256, so a position keeps its thread (and the cached,
 // state-independent part of its decision) when the window restarts after a change.
@@ -478,6 +525,18 @@ __device__ __forceinline__ void gram_axpy(const SweepParams& P, double* q, int j
 // around E == L (and away from the saturation / overflow corners) this is provably the
 // same boolean as the reference's floating-point evaluation; inside the band the
 // reference formula itself (kappa_of) is evaluated, so every decision is exact.
+//
+// Deferred column updates.  A change at coordinate j* with increment delta turns q into
+// q - delta G[:, j*], but the next decisions only look at q in the positions of the
+// window.  Every thread therefore carries q of the position it owns in a register
+// (q_pos) and corrects it with ONE gathered Gram entry per change, while the change goes
+// on a pending list; after GB_PEND changes (and at the end of a sweep) the pending
+// columns are streamed and applied to q in shared memory in a single pass.  A position
+// that enters a thread's ownership reads q and replays the pending list.  The fma
+// sequence seen by every element of q is the same as with immediate updates, so the
+// results are bit-identical to them; what changes is that the latency chain of a change
+// is one gather instead of a whole column, and that q is read and written once per
+// GB_PEND changes instead of once per change.
 template <int DESIGN, bool QSMEM>
 __global__ void __maxnreg__(GB_GRAM_REGS) gibbs_gram_kernel(SweepParams P)
 {
@@ -485,6 +544,9 @@ __global__ void __maxnreg__(GB_GRAM_REGS) gibbs_gram_kernel(SweepParams P)
     __shared__ SweepShared sh;
     __shared__ GramBcast bc;
     __shared__ unsigned flags[2][GB_NWARP];
+    __shared__ int sj[GB_BLOCK];                // coordinate of the position each thread owns
+    __shared__ int pend_j[GB_PEND];
+    __shared__ double pend_d[GB_PEND];
     __shared__ double scratch[40];
 
     const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -506,12 +568,14 @@ __global__ void __maxnreg__(GB_GRAM_REGS) gibbs_gram_kernel(SweepParams P)
 
     int parity = 0;
     long long n_changes = 0, n_windows = 0;     // block-uniform work counters
+    PH_DECL
     for (int s = 0; s < P.S; ++s) {
         const int sweep = P.sweep0 + s;
         const int64_t soff = ((int64_t)c * P.S + s) * p;
         const PermView perm_s = perm_view(P, c, s);
         const double* u_s = P.u ? P.u + soff : nullptr;
         const double* z_s = P.z ? P.z + soff : nullptr;
+        PH(0);
 
         // ---- periodic rebuild of q and ||r||^2 from q0 = X^T y (bounds rounding drift)
         if (P.gram_refresh > 0 && sweep > 0 && sweep % P.gram_refresh == 0) {
@@ -543,39 +607,60 @@ __global__ void __maxnreg__(GB_GRAM_REGS) gibbs_gram_kernel(SweepParams P)
         const Hyper h = { sh.sigma2, sh.tau2, sh.logodds };
         const double ts = h.tau2 / h.sigma2;
 
-        // per-position cache (state-independent within a sweep): filled when a position
-        // enters a thread's ownership, i.e. one window ahead of its first evaluation.
-        // f_A, f_c1, f_L only steer the guarded fast decision, so single precision is
-        // enough for them (the guard band below is 1e-4 relative); anything that reaches
-        // a coefficient or an exact decision (c_u, c_xl2, c_bold, c_zn) stays in fp64.
-        int c_pos = -1, c_j = 0, n_j = 0;
+        // per-position cache: filled when a position enters a thread's ownership, i.e. one
+        // window ahead of its first evaluation.  f_A, f_c1, f_L only steer the guarded fast
+        // decision, so single precision (and the fast intrinsics) is enough for them: the
+        // guard band below is 1e-4 relative.  Anything that reaches a coefficient or an
+        // exact decision stays in fp64.
+        int c_pos = -1, c_j = 0, n_j = 0, nn_j = 0, npend = 0;
         bool c_act = false, c_exact = true;
         float f_A = 0.f, f_c1 = 0.f, f_L = 0.f;
-        double c_xl2 = 0.0, n_xl2 = 0.0, c_bold = 0.0, c_u = 0.0, c_zn = 0.0;
-        bool need_xl2 = false;
+        double c_xl2 = 0.0, n_xl2 = 0.0, c_bold = 0.0, c_u = 0.0, c_zn = 0.0, c_pv = 0.0;
+        double q_pos = 0.0;               // q[c_j] with every change so far applied
         const float f_logodds = (float)h.logodds, f_tau2 = (float)h.tau2, f_sigma2 = (float)h.sigma2;
         const float f_ts = (float)ts;
-        auto fill = [&](int pos) {        // needs n_j (and n_xl2) = perm / Xl2 of `pos` (prefetched)
+        // needs n_j (and n_xl2) = perm / Xl2 of `pos` (prefetched).  If jnow >= 0 a change at
+        // coordinate jnow is being decided: its Gram entry for the new position is fetched too.
+        auto fill = [&](int pos, int jnow) -> double {
             c_pos = pos;
             c_j = n_j;
-            c_xl2 = need_xl2 ? P.Xl2[n_j] : n_xl2;
-            need_xl2 = false;
-            if (pos + GB_BLOCK < p) {     // prefetch for the position this thread owns next;
-                n_j = perm_s[pos + GB_BLOCK];   // Xl2[n_j] is fetched one window later so that
-                need_xl2 = true;                // this dependent load never blocks the fill
-            }
+            sj[tid] = n_j;
+            const double gnow = jnow >= 0 ? gram_entry<DESIGN>(P, jnow, c_j) : 0.0;
+            double gp[GB_PEND];
+#pragma unroll
+            for (int k = 0; k < GB_PEND; ++k) gp[k] = k < npend ? gram_entry<DESIGN>(P, pend_j[k], c_j) : 0.0;
+            q_pos = q[c_j];
+            c_xl2 = n_xl2;
+            // two-deep prefetch of the visiting order (and one-deep of Xl2 behind it), so that
+            // neither dependent load is ever waited for: nn_j belongs to pos + 2*256
+            n_j = nn_j;
+            if (pos + GB_BLOCK < p) n_xl2 = P.Xl2[n_j];
+            if (pos + 2 * GB_BLOCK < p) nn_j = perm_s[pos + 2 * GB_BLOCK];
             c_act = (mask_s[c_j >> 5] >> (c_j & 31)) & 1u;
             c_bold = c_act ? __ldcg(beta_g + c_j) : 0.0;
             c_u = u_s ? u_s[pos] : rng_uniform(key, KIND_SPIKE_U, pos, sweep, 0);
             c_exact = !(c_u > 1e-4 && c_u < 1.0 - 1e-4);
             const float xl2f = (float)c_xl2;
-            f_A = f_logodds + 0.5f * logf(1.0f + f_tau2 * xl2f / f_sigma2);
-            f_c1 = f_ts / (2.0f * (f_sigma2 + f_tau2 * xl2f));
-            f_L = c_exact ? 0.f : logf((float)(c_u / (1.0 - c_u)));
-            // an active coordinate is redrawn for sure: take its normal off the critical path
-            if (c_act) c_zn = z_s ? z_s[pos] : rng_normal(key, KIND_SLAB_Z, pos, sweep, 0);
+            f_A = f_logodds + 0.5f * __logf(1.0f + __fdividef(f_tau2 * xl2f, f_sigma2));
+            f_c1 = __fdividef(f_ts, 2.0f * (f_sigma2 + f_tau2 * xl2f));
+            f_L = c_exact ? 0.f : __logf((float)c_u) - __logf((float)(1.0 - c_u));
+            // an active coordinate is redrawn for sure: take the state-independent part of
+            // its slab draw (_linear.pyx:130,158: sqrt(post_var) * z) off the critical path
+            if (c_act) {
+                const double zn = z_s ? z_s[pos] : rng_normal(key, KIND_SLAB_Z, pos, sweep, 0);
+                c_pv = 1.0 / (1.0 / h.tau2 + c_xl2 / h.sigma2);
+                c_zn = sqrt(c_pv) * zn;
+            }
+#pragma unroll
+            for (int k = 0; k < GB_PEND; ++k) if (k < npend) q_pos = fma(-pend_d[k], gp[k], q_pos);
+            return gnow;
         };
-        if (tid < p) { n_j = perm_s[tid]; n_xl2 = P.Xl2[n_j]; fill(tid); }
+        if (tid < p) {
+            n_j = perm_s[tid]; n_xl2 = P.Xl2[n_j];
+            if (tid + GB_BLOCK < p) nn_j = perm_s[tid + GB_BLOCK];
+            fill(tid, -1);
+        }
+        PH(1);
 
         int pos0 = 0;
         while (pos0 < p) {
@@ -583,12 +668,14 @@ __global__ void __maxnreg__(GB_GRAM_REGS) gibbs_gram_kernel(SweepParams P)
             const int off = (tid - pos0) & (GB_BLOCK - 1);
             const int pos = pos0 + off;
             bool change = false, spike = true;
-            double qj = 0.0, XjTr = 0.0;
-            if (need_xl2) { n_xl2 = P.Xl2[n_j]; need_xl2 = false; }
+            double XjTr = 0.0;
             if (pos < p) {
-                if (pos != c_pos) { n_j = perm_s[pos]; n_xl2 = P.Xl2[n_j]; fill(pos); }   // safety net
-                qj = q[c_j];
-                XjTr = c_act ? qj + c_bold * c_xl2 : qj;      // X_j . (r + beta_j X_j)
+                if (pos != c_pos) {                           // safety net; not reached by construction
+                    n_j = perm_s[pos]; n_xl2 = P.Xl2[n_j];
+                    if (pos + GB_BLOCK < p) nn_j = perm_s[pos + GB_BLOCK];
+                    fill(pos, -1);
+                }
+                XjTr = c_act ? q_pos + c_bold * c_xl2 : q_pos;      // X_j . (r + beta_j X_j)
                 const double x2c = (double)f_c1 * (XjTr * XjTr);
                 const double E = (double)f_A - x2c;
                 const double margin = E - (double)f_L;
@@ -602,90 +689,101 @@ __global__ void __maxnreg__(GB_GRAM_REGS) gibbs_gram_kernel(SweepParams P)
             }
             const unsigned m = __ballot_sync(0xffffffffu, change);
             if (lane == 0) flags[parity][warp] = m;
+            PH(2);
             __syncthreads();
-            // first changed position in window order = first set bit at/after bit r, cyclically
+            PH(3);
+            // first changed position in window order = first set bit at/after bit r, cyclically:
+            // lane i < 9 looks at the i-th word after the one that holds bit r
             const int r = pos0 & (GB_BLOCK - 1);
             int first = -1;
             {
                 const int w0 = r >> 5, b0 = r & 31;
-#pragma unroll
-                for (int i = GB_NWARP; i >= 0; --i) {       // scan backwards so the earliest wins
-                    const int w = (w0 + i) & (GB_NWARP - 1);
-                    unsigned f = flags[parity][w];
-                    if (i == 0) f &= (0xffffffffu << b0);
-                    else if (i == GB_NWARP) f &= ~(0xffffffffu << b0);   // b0 == 0 -> empty
-                    if (f) first = ((32 * w + __ffs(f) - 1) - r) & (GB_BLOCK - 1);
+                unsigned f = 0u;
+                if (lane <= GB_NWARP) {
+                    f = flags[parity][(w0 + lane) & (GB_NWARP - 1)];
+                    if (lane == 0) f &= (0xffffffffu << b0);
+                    else if (lane == GB_NWARP) f &= ~(0xffffffffu << b0);   // b0 == 0 -> empty
+                }
+                const unsigned nz = __ballot_sync(0xffffffffu, f != 0u);
+                if (nz) {
+                    const int i = __ffs(nz) - 1;
+                    const unsigned fi = __shfl_sync(0xffffffffu, f, i);
+                    first = ((32 * ((w0 + i) & (GB_NWARP - 1)) + __ffs(fi) - 1) - r) & (GB_BLOCK - 1);
                 }
             }
             parity ^= 1;
+            PH(4);
             if (first < 0) {                                  // the whole window was null
                 pos0 += GB_BLOCK;
-                if (pos + GB_BLOCK < p) fill(pos + GB_BLOCK); else c_pos = -1;
+                if (pos + GB_BLOCK < p) fill(pos + GB_BLOCK, -1); else c_pos = -1;
+                PH(5);
                 continue;
             }
             ++n_changes;
-            // Everybody knows the changing coordinate without waiting for its owner, so the
-            // first GB_AXU 16-byte loads of its Gram column go out before the slab draw and
-            // before the leaving positions are re-filled: their latency hides behind that math.
-            const int jstar = perm_s[pos0 + first];
-            double2 g[GB_AXU];
-#pragma unroll
-            for (int u = 0; u < GB_AXU; ++u) {
-                const int k = 2 * tid + u * 2 * GB_BLOCK;
-                g[u] = (k < p2) ? gram_pair<DESIGN>(P, jstar, k) : make_double2(0.0, 0.0);
-            }
-            if (off == first) {
+            // Everybody knows the changing coordinate without waiting for its owner: the Gram
+            // entry that corrects this thread's own q_pos is requested before the slab draw and
+            // before the leaving positions are re-filled, so its latency hides behind that math.
+            const int jstar = sj[(pos0 + first) & (GB_BLOCK - 1)];
+            double gj = 0.0;
+            PH(6);
+            if (off > first) {
+                if (c_pos >= 0) gj = gram_entry<DESIGN>(P, jstar, c_j);
+            } else if (off == first) {                        // the owner of the changing position
                 double bnew = 0.0;
                 if (!spike) {
-                    const double zn = c_act ? c_zn
-                                            : (z_s ? z_s[pos] : rng_normal(key, KIND_SLAB_Z, pos, sweep, 0));
-                    bnew = slab_draw(XjTr, c_xl2, h, zn);
+                    if (c_act) bnew = c_zn + c_pv * XjTr / h.sigma2;      // = slab_draw(...)
+                    else bnew = slab_draw(XjTr, c_xl2, h, z_s ? z_s[pos] : rng_normal(key, KIND_SLAB_Z, pos, sweep, 0));
                 }
                 const double delta = bnew - c_bold;
-                bc.jstar = c_j; bc.delta = delta;
+                bc.delta = delta;
+                pend_j[npend] = c_j; pend_d[npend] = delta;
                 // ||r - delta X_j||^2 = ||r||^2 - 2 delta X_j.r + delta^2 ||X_j||^2
-                sh.rr = sh.rr - 2.0 * delta * qj + delta * delta * c_xl2;
+                sh.rr = sh.rr - 2.0 * delta * q_pos + delta * delta * c_xl2;
                 __stcg(beta_g + c_j, bnew);
                 if (bnew != 0) mask_s[c_j >> 5] |= (1u << (c_j & 31));
                 else mask_s[c_j >> 5] &= ~(1u << (c_j & 31));
+                // a column that is not L2-resident is on its way by the time it is flushed
+                if (DESIGN == BLIPGPU_DESIGN_DENSE)
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(P.G + (int64_t)c_j * P.ldg),
+                                 "r"((unsigned)(p2 * sizeof(double))) : "memory");
             }
-            if (off <= first) {                               // my position leaves the window
-                if (pos + GB_BLOCK < p) fill(pos + GB_BLOCK); else c_pos = -1;
+            // positions up to and including the changed one leave the window: their threads take
+            // over the positions one window further (the owner after its draw, in the same
+            // divergent pass as the other lanes of its warp).  The current change is not on the
+            // pending list they replay yet; it reaches them through gj below like everybody else.
+            if (off <= first) {
+                if (pos + GB_BLOCK < p) gj = fill(pos + GB_BLOCK, jstar); else c_pos = -1;
             }
+            PH(7);
             __syncthreads();
-            const double delta = bc.delta;                    // q -= delta * G[:, j*]
-#pragma unroll
-            for (int u = 0; u < GB_AXU; ++u) {
-                const int k = 2 * tid + u * 2 * GB_BLOCK;
-                if (k < p2) {
-                    double2 qq = *reinterpret_cast<double2*>(q + k);
-                    qq.x = fma(-delta, g[u].x, qq.x); qq.y = fma(-delta, g[u].y, qq.y);
-                    *reinterpret_cast<double2*>(q + k) = qq;
-                }
+            PH(8);
+            q_pos = fma(-bc.delta, gj, q_pos);
+            ++npend;
+            PH(9);
+            if (npend == GB_PEND) {
+                gram_flush<DESIGN>(P, q, pend_j, pend_d, npend);
+                npend = 0;
+                __syncthreads();
             }
-            for (int k0 = 2 * tid + GB_AXU * 2 * GB_BLOCK; k0 < p2; k0 += 2 * GB_BLOCK * GB_AXU) {
-#pragma unroll
-                for (int u = 0; u < GB_AXU; ++u) {
-                    const int k = k0 + u * 2 * GB_BLOCK;
-                    g[u] = (k < p2) ? gram_pair<DESIGN>(P, jstar, k) : make_double2(0.0, 0.0);
-                }
-#pragma unroll
-                for (int u = 0; u < GB_AXU; ++u) {
-                    const int k = k0 + u * 2 * GB_BLOCK;
-                    if (k < p2) {
-                        double2 qq = *reinterpret_cast<double2*>(q + k);
-                        qq.x = fma(-delta, g[u].x, qq.x); qq.y = fma(-delta, g[u].y, qq.y);
-                        *reinterpret_cast<double2*>(q + k) = qq;
-                    }
-                }
-            }
-            __syncthreads();
+            PH(10);
             pos0 += first + 1;
+            PH(11);
         }
+        if (npend > 0) {                                      // block-uniform
+            __syncthreads();
+            gram_flush<DESIGN>(P, q, pend_j, pend_d, npend);
+        }
+        __syncthreads();
 
         sweep_epilogue(P, &sh, mask_s, beta_g, scratch, key, c, s, sh.rr, nullptr, false);
         __syncthreads();
     }
+#ifdef BLIP_PHASE_CLOCKS
+    if (tid == 0 && (c == 0 || c == 300)) {
+        printf("chain %d changes %lld windows %lld | epi+sweepstart %lld fill0 %lld | eval %lld sync1 %lld find %lld nullfill %lld | jstar %lld owner/fill/gather %lld sync2 %lld apply %lld flush %lld ownerfill %lld\n",
+               c, n_changes, n_windows, ph_t[0], ph_t[1], ph_t[2], ph_t[3], ph_t[4], ph_t[5], ph_t[6], ph_t[7], ph_t[8], ph_t[9], ph_t[10], ph_t[11]);
+    }
+#endif
 
     if (QSMEM) for (int k = tid; k < p2; k += GB_BLOCK) q_g[k] = q[k];
     for (int w = tid; w < P.words; w += GB_BLOCK) P.mask[(int64_t)c * P.words + w] = mask_s[w];

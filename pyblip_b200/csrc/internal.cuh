@@ -7,6 +7,8 @@ struct blipgpu_ctx {
     int device;
     int sm_count;
     size_t smem_optin;     // max dynamic shared memory per block (opt-in)
+    size_t smem_per_sm;    // shared memory of one SM
+    size_t smem_reserved;  // shared memory the system reserves per resident block
     cudaStream_t stream;   // sweep / counting kernels
     cudaStream_t stream2;  // permutation generation, copies
     double sweep_ms, other_ms;
