@@ -7,6 +7,7 @@
 // are generated on a second stream while the current chunk sweeps.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <new>
 #include <vector>
 #include "gibbs_kernels.cuh"
@@ -225,7 +226,7 @@ extern "C" int blipgpu_sample_spikeslab(blipgpu_ctx* ctx, blipgpu_design* design
     }
 
     // ---- allocate
-    DevBuf d_beta, d_r, d_mu, d_ylat, d_q, d_h, d_mask, d_ev, d_q0, d_y, d_z, d_ovf;
+    DevBuf d_beta, d_r, d_mu, d_ylat, d_q, d_h, d_mask, d_ev, d_q0, d_y, d_z, d_ovf, d_scrL, d_scrZ, d_queue;
     DevBuf d_perm[2], d_u, d_zn, d_ig, d_p0, d_g;
     DevBuf snap_beta, snap_r, snap_mu, snap_ylat, snap_q, snap_h, snap_mask, snap_ev;
     BLIP_TRY(d_beta.alloc(sizeof(double) * chains * p));
@@ -236,6 +237,8 @@ extern "C" int blipgpu_sample_spikeslab(blipgpu_ctx* ctx, blipgpu_design* design
     if (gram) {
         BLIP_TRY(d_q.alloc(sizeof(double) * chains * p2)); BLIP_TRY(snap_q.alloc(d_q.bytes));
         BLIP_TRY(d_q0.alloc(sizeof(double) * p));
+        BLIP_TRY(d_queue.alloc(sizeof(int) * (chains + 1)));
+        BLIP_TRY(d_scrL.alloc(sizeof(float) * chains * p)); BLIP_TRY(d_scrZ.alloc(sizeof(double2) * chains * p));
     } else {
         BLIP_TRY(d_r.alloc(sizeof(double) * chains * n2)); BLIP_TRY(snap_r.alloc(d_r.bytes));
         if (probit) {
@@ -297,6 +300,8 @@ extern "C" int blipgpu_sample_spikeslab(blipgpu_ctx* ctx, blipgpu_design* design
     P.ylat = d_ylat.as<double>(); P.q = d_q.as<double>(); P.hstate = d_h.as<double>();
     P.mask = d_mask.as<uint32_t>(); P.events = d_ev.as<uint32_t>();
     P.q0 = d_q0.as<double>(); P.zlab = d_z.as<int32_t>();
+    P.scrL = d_scrL.as<float>(); P.scrZ = d_scrZ.as<double2>();
+    P.queue = d_queue.as<int>(); P.progress = d_queue.as<int>() + 1; P.n_chains = (int)chains;
     P.k0 = (uint32_t)seed; P.k1 = (uint32_t)(seed >> 32); P.chain_offset = (uint32_t)chain_offset;
     P.nprop = nprop; P.burn = (int)burn; P.n_keep = (int)n_keep;
     P.bits = smp->bits; P.rows = smp->rows; P.rows_pad = smp->rows_pad;
@@ -342,6 +347,15 @@ extern "C" int blipgpu_sample_spikeslab(blipgpu_ctx* ctx, blipgpu_design* design
     else
         kern = qsmem ? gibbs_gram_kernel<BLIPGPU_DESIGN_DENSE, true> : gibbs_gram_kernel<BLIPGPU_DESIGN_DENSE, false>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // gram mode: persistent CTAs (as many as are resident at once) draw (chain, 8-sweep) items
+    // from a queue; with q in global memory (huge p) a chain stays on one CTA for the launch.
+    int resident = 0;
+    if (gram) {
+        int per_sm = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, GB_BLOCK, smem));
+        resident = std::max(1, per_sm) * ctx->sm_count;
+    }
+    const int sub_sweeps_opt = qsmem ? 8 : 0;
 
     cudaEvent_t ev_perm[2], ev_done[2];
     for (int i = 0; i < 2; ++i) {
@@ -366,6 +380,7 @@ extern "C" int blipgpu_sample_spikeslab(blipgpu_ctx* ctx, blipgpu_design* design
     };
 
     const int64_t nchunks = (n_total + S - 1) / S;
+    const bool launch_log = getenv("BLIPGPU_LAUNCH_LOG") != nullptr;
     // permutation chunk boundaries: a short first chunk (nothing can hide its generation),
     // then PS sweeps each
     std::vector<int64_t> pstart;
@@ -440,12 +455,23 @@ extern "C" int blipgpu_sample_spikeslab(blipgpu_ctx* ctx, blipgpu_design* design
             P.sweep0 = (int)sweep0; P.S = Sc;
             P.values = smp->values; P.arena_cap = smp->arena_cap;
             CUDA_TRY(cudaMemsetAsync(d_ovf.ptr, 0, sizeof(int), st));
+            unsigned grid = (unsigned)chains;
+            if (gram) {
+                // no more chains than resident CTAs: one CTA per chain, spread by the hardware
+                P.sub_sweeps = (sub_sweeps_opt > 0 && chains > resident) ? std::min(sub_sweeps_opt, Sc) : Sc;
+                const int64_t n_items = chains * ((Sc + P.sub_sweeps - 1) / P.sub_sweeps);
+                grid = (unsigned)std::min<int64_t>(n_items, resident);
+                CUDA_TRY(cudaMemsetAsync(d_queue.ptr, 0, d_queue.bytes, st));
+            }
             {
                 ScopedTimer timer(ctx, true);
-                kern<<<(unsigned)chains, GB_BLOCK, smem, st>>>(P);
+                kern<<<grid, GB_BLOCK, smem, st>>>(P);
                 CUDA_TRY(cudaGetLastError());
-                smp->sweep_ms += timer.stop(1);
+                const double ms = timer.stop(1);
+                smp->sweep_ms += ms;
                 smp->sweep_launches += 1;
+                if (launch_log) fprintf(stderr, "[blipgpu] launch sweeps %lld..%lld grid %u: %.3f ms\n",
+                                        (long long)sweep0, (long long)(sweep0 + Sc), grid, ms);
             }
             int ovf = 0;
             unsigned long long used = 0;

@@ -60,6 +60,11 @@ struct SweepParams {
     double* values; int64_t arena_cap; unsigned long long* arena_used; int* overflow;
     double* hyper_out; double* latents;
     int gram_refresh;
+    // gram mode work queue: items (chain, sub-chunk of sub_sweeps sweeps) handed out in order;
+    // progress[c] = sub-chunks of chain c completed in this launch
+    int* queue; int* progress; int n_chains, sub_sweeps;
+    float* scrL;               // gram mode: [chains][p]  logit of the spike uniform per position (NaN = exact path)
+    double2* scrZ;             // gram mode: [chains][p]  (sqrt(post_var) * z, post_var) at positions of active coordinates
 };
 
 struct PermView {           // visiting order of one (chain, sweep)
@@ -436,7 +441,10 @@ struct GramBcast { double delta; };
 #define PH(i) do {} while (0)
 #endif
 constexpr int GB_AXU = 10;         // 16-byte Gram loads a thread keeps in flight
-constexpr int GB_PEND = 5;         // changes whose Gram columns are applied to q in one pass
+#ifndef BLIP_GB_PEND
+#define BLIP_GB_PEND 2
+#endif
+constexpr int GB_PEND = BLIP_GB_PEND;   // changes whose Gram columns are applied to q in one pass
 constexpr int GB_FLUSH_SLOTS = GB_AXU / GB_PEND;
 constexpr int GB_GRAM_REGS = 128;  // 2 CTAs x 256 threads x 128 registers = the whole register file
 
@@ -515,6 +523,18 @@ __device__ __forceinline__ void gram_flush(const SweepParams& P, double* q, cons
     }
 }
 
+// The state-independent part of the slab draw of an active coordinate (visited at `pos`):
+// (sqrt(post_var) * z, post_var), _linear.pyx:130,158.
+__device__ __forceinline__ void slab_prepare(const SweepParams& P, double2* Zs, const PermView& perm_s,
+                                             const Hyper& h, const RngKey& key, const double* z_s,
+                                             int pos, int sweep)
+{
+    const int j = perm_s[pos];
+    const double zn = z_s ? z_s[pos] : rng_normal(key, KIND_SLAB_Z, pos, sweep, 0);
+    const double pv = 1.0 / (1.0 / h.tau2 + P.Xl2[j] / h.sigma2);
+    Zs[pos] = make_double2(sqrt(pv) * zn, pv);
+}
+
 // Sliding speculation window: thread t owns the one position of [pos0, pos0+256)
 // that is congruent to t modulo 256, so a position keeps its thread (and the cached,
 // state-independent part of its decision) when the window restarts after a change.
@@ -545,12 +565,41 @@ __global__ void __maxnreg__(GB_GRAM_REGS) gibbs_gram_kernel(SweepParams P)
     __shared__ GramBcast bc;
     __shared__ unsigned flags[2][GB_NWARP];
     __shared__ int sj[GB_BLOCK];                // coordinate of the position each thread owns
+    __shared__ int act_pos[GB_BLOCK];           // positions of the currently active coordinates
+    __shared__ int act_n;
     __shared__ int pend_j[GB_PEND];
     __shared__ double pend_d[GB_PEND];
     __shared__ double scratch[40];
 
-    const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ int s_item;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int p = P.p, p2 = P.p2;
+    // Persistent CTAs draw (chain, sub-chunk) items from a queue in launch order, so that the
+    // SMs stay evenly loaded whatever the number of chains (chains do not come in multiples of
+    // the resident CTA count, and one CTA per chain per launch would leave a ragged last wave).
+    // A chain's sub-chunks run in order: an item waits for progress[chain] to reach its index.
+    // Its predecessor was handed out earlier, i.e. to a CTA that is already running, so the
+    // wait always ends.  State crosses CTAs through L2 (ld.cg / fence + flag).
+    const int subs = (P.S + P.sub_sweeps - 1) / P.sub_sweeps;
+    const int n_items = P.n_chains * subs;
+    int parity = 0;
+    PH_DECL
+  for (;;) {
+    if (tid == 0) s_item = atomicAdd(P.queue, 1);
+    __syncthreads();
+    const int item = s_item;
+    __syncthreads();
+    if (item >= n_items) break;
+    const int c = item % P.n_chains, sub = item / P.n_chains;
+    const int s_begin = sub * P.sub_sweeps, s_end = min(P.S, s_begin + P.sub_sweeps);
+    if (sub > 0) {
+        if (tid == 0) {
+            volatile int* pr = P.progress + c;
+            while (*pr < sub) __nanosleep(200);
+            __threadfence();
+        }
+        __syncthreads();
+    }
     double* q_g = P.q + (int64_t)c * p2;
     double* q = QSMEM ? sm : q_g;
     uint32_t* mask_s = (uint32_t*)(sm + (QSMEM ? p2 : 0));
@@ -558,18 +607,16 @@ __global__ void __maxnreg__(GB_GRAM_REGS) gibbs_gram_kernel(SweepParams P)
     const RngKey key = { P.k0, P.k1, P.chain_offset + (uint32_t)c };
     double* beta_g = P.beta + (int64_t)c * p;
 
-    if (QSMEM) for (int k = tid; k < p2; k += GB_BLOCK) q[k] = q_g[k];
-    for (int w = tid; w < P.words; w += GB_BLOCK) mask_s[w] = P.mask[(int64_t)c * P.words + w];
+    if (QSMEM) for (int k = tid; k < p2; k += GB_BLOCK) q[k] = __ldcg(q_g + k);
+    for (int w = tid; w < P.words; w += GB_BLOCK) mask_s[w] = __ldcg(P.mask + (int64_t)c * P.words + w);
     if (tid == 0) {
-        sh.sigma2 = P.hstate[GB_HS * c + 0]; sh.tau2 = P.hstate[GB_HS * c + 1];
-        sh.p0 = P.hstate[GB_HS * c + 2]; sh.rr = P.hstate[GB_HS * c + 3];
+        sh.sigma2 = __ldcg(P.hstate + GB_HS * c + 0); sh.tau2 = __ldcg(P.hstate + GB_HS * c + 1);
+        sh.p0 = __ldcg(P.hstate + GB_HS * c + 2); sh.rr = __ldcg(P.hstate + GB_HS * c + 3);
     }
     __syncthreads();
 
-    int parity = 0;
     long long n_changes = 0, n_windows = 0;     // block-uniform work counters
-    PH_DECL
-    for (int s = 0; s < P.S; ++s) {
+    for (int s = s_begin; s < s_end; ++s) {
         const int sweep = P.sweep0 + s;
         const int64_t soff = ((int64_t)c * P.S + s) * p;
         const PermView perm_s = perm_view(P, c, s);
@@ -607,20 +654,57 @@ __global__ void __maxnreg__(GB_GRAM_REGS) gibbs_gram_kernel(SweepParams P)
         const Hyper h = { sh.sigma2, sh.tau2, sh.logodds };
         const double ts = h.tau2 / h.sigma2;
 
+        // ---- state-independent per-position quantities of this sweep, computed by the whole
+        // block without divergence and parked in (L2-resident) global scratch: the logit of the
+        // spike/slab uniform that steers the fast decision, and -- at the positions of the
+        // coordinates that are active now, which are exactly the ones that will be active when
+        // visited -- the state-independent part of the slab draw (_linear.pyx:130,158).
+        float* Ls = P.scrL + (int64_t)c * p;
+        double2* Zs = P.scrZ + (int64_t)c * p;
+        if (tid == 0) act_n = 0;
+        __syncthreads();
+        for (int base = tid; base < p; base += 4 * GB_BLOCK) {
+            int jj[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) jj[i] = base + i * GB_BLOCK < p ? perm_s[base + i * GB_BLOCK] : -1;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int pos = base + i * GB_BLOCK;
+                if (pos < p) {
+                    const double u = u_s ? u_s[pos] : rng_uniform(key, KIND_SPIKE_U, pos, sweep, 0);
+                    const bool ex = !(u > 1e-4 && u < 1.0 - 1e-4);
+                    Ls[pos] = ex ? __int_as_float(0x7fc00000) : __logf((float)u) - __logf((float)(1.0 - u));
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int j = jj[i];
+                if (j >= 0 && ((mask_s[j >> 5] >> (j & 31)) & 1u)) {
+                    const int slot = atomicAdd(&act_n, 1);
+                    if (slot < GB_BLOCK) act_pos[slot] = base + i * GB_BLOCK;
+                    else slab_prepare(P, Zs, perm_s, h, key, z_s, base + i * GB_BLOCK, sweep);   // list full (early burn-in)
+                }
+            }
+        }
+        __syncthreads();
+        if (tid < min(act_n, GB_BLOCK)) slab_prepare(P, Zs, perm_s, h, key, z_s, act_pos[tid], sweep);
+        __syncthreads();
+
         // per-position cache: filled when a position enters a thread's ownership, i.e. one
         // window ahead of its first evaluation.  f_A, f_c1, f_L only steer the guarded fast
         // decision, so single precision (and the fast intrinsics) is enough for them: the
         // guard band below is 1e-4 relative.  Anything that reaches a coefficient or an
         // exact decision stays in fp64.
         int c_pos = -1, c_j = 0, n_j = 0, nn_j = 0, npend = 0;
-        bool c_act = false, c_exact = true;
-        float f_A = 0.f, f_c1 = 0.f, f_L = 0.f;
-        double c_xl2 = 0.0, n_xl2 = 0.0, c_bold = 0.0, c_u = 0.0, c_zn = 0.0, c_pv = 0.0;
+        bool c_act = false, c_pref = false;
+        float f_A = 0.f, f_c1 = 0.f, f_L = 0.f, n_L = 0.f;
+        double c_xl2 = 0.0, n_xl2 = 0.0, c_bold = 0.0;
+        double2 c_zp = make_double2(0.0, 0.0);   // (sqrt(post_var) * z, post_var) of an active position
         double q_pos = 0.0;               // q[c_j] with every change so far applied
         const float f_logodds = (float)h.logodds, f_tau2 = (float)h.tau2, f_sigma2 = (float)h.sigma2;
         const float f_ts = (float)ts;
-        // needs n_j (and n_xl2) = perm / Xl2 of `pos` (prefetched).  If jnow >= 0 a change at
-        // coordinate jnow is being decided: its Gram entry for the new position is fetched too.
+        // needs n_j, n_xl2, n_L = perm / Xl2 / logit of `pos` (prefetched).  If jnow >= 0 a change
+        // at coordinate jnow is being decided: its Gram entry for the new position is fetched too.
         auto fill = [&](int pos, int jnow) -> double {
             c_pos = pos;
             c_j = n_j;
@@ -631,32 +715,34 @@ __global__ void __maxnreg__(GB_GRAM_REGS) gibbs_gram_kernel(SweepParams P)
             for (int k = 0; k < GB_PEND; ++k) gp[k] = k < npend ? gram_entry<DESIGN>(P, pend_j[k], c_j) : 0.0;
             q_pos = q[c_j];
             c_xl2 = n_xl2;
-            // two-deep prefetch of the visiting order (and one-deep of Xl2 behind it), so that
-            // neither dependent load is ever waited for: nn_j belongs to pos + 2*256
-            n_j = nn_j;
-            if (pos + GB_BLOCK < p) n_xl2 = P.Xl2[n_j];
-            if (pos + 2 * GB_BLOCK < p) nn_j = perm_s[pos + 2 * GB_BLOCK];
+            f_L = n_L;
             c_act = (mask_s[c_j >> 5] >> (c_j & 31)) & 1u;
-            c_bold = c_act ? __ldcg(beta_g + c_j) : 0.0;
-            c_u = u_s ? u_s[pos] : rng_uniform(key, KIND_SPIKE_U, pos, sweep, 0);
-            c_exact = !(c_u > 1e-4 && c_u < 1.0 - 1e-4);
+            if (c_act) { c_bold = __ldcg(beta_g + c_j); c_zp = __ldcg(Zs + pos); } else c_bold = 0.0;
+            // two-deep prefetch of the visiting order (and one-deep of what hangs off it), so that
+            // no dependent load is ever waited for: nn_j belongs to pos + 2*256
+            n_j = nn_j;
+            if (pos + GB_BLOCK < p) { n_xl2 = P.Xl2[n_j]; n_L = __ldcg(Ls + pos + GB_BLOCK); }
+            if (pos + 2 * GB_BLOCK < p) nn_j = perm_s[pos + 2 * GB_BLOCK];
             const float xl2f = (float)c_xl2;
             f_A = f_logodds + 0.5f * __logf(1.0f + __fdividef(f_tau2 * xl2f, f_sigma2));
             f_c1 = __fdividef(f_ts, 2.0f * (f_sigma2 + f_tau2 * xl2f));
-            f_L = c_exact ? 0.f : __logf((float)c_u) - __logf((float)(1.0 - c_u));
-            // an active coordinate is redrawn for sure: take the state-independent part of
-            // its slab draw (_linear.pyx:130,158: sqrt(post_var) * z) off the critical path
-            if (c_act) {
-                const double zn = z_s ? z_s[pos] : rng_normal(key, KIND_SLAB_Z, pos, sweep, 0);
-                c_pv = 1.0 / (1.0 / h.tau2 + c_xl2 / h.sigma2);
-                c_zn = sqrt(c_pv) * zn;
-            }
 #pragma unroll
             for (int k = 0; k < GB_PEND; ++k) if (k < npend) q_pos = fma(-pend_d[k], gp[k], q_pos);
+            // A position that would change if it were decided now very likely changes when its turn
+            // comes (an active one certainly does): start moving its Gram column into L2 a window
+            // ahead, so that neither the gathers nor the flush of that change wait for HBM.
+#ifdef BLIP_FILL_PREFETCH
+            c_pref = c_act || !(f_A - f_c1 * (float)(q_pos * q_pos) > f_L);
+#else
+            c_pref = false;
+#endif
+            if (DESIGN == BLIPGPU_DESIGN_DENSE && c_pref)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(P.G + (int64_t)c_j * P.ldg),
+                             "r"((unsigned)(p2 * sizeof(double))) : "memory");
             return gnow;
         };
         if (tid < p) {
-            n_j = perm_s[tid]; n_xl2 = P.Xl2[n_j];
+            n_j = perm_s[tid]; n_xl2 = P.Xl2[n_j]; n_L = __ldcg(Ls + tid);
             if (tid + GB_BLOCK < p) nn_j = perm_s[tid + GB_BLOCK];
             fill(tid, -1);
         }
@@ -671,7 +757,7 @@ __global__ void __maxnreg__(GB_GRAM_REGS) gibbs_gram_kernel(SweepParams P)
             double XjTr = 0.0;
             if (pos < p) {
                 if (pos != c_pos) {                           // safety net; not reached by construction
-                    n_j = perm_s[pos]; n_xl2 = P.Xl2[n_j];
+                    n_j = perm_s[pos]; n_xl2 = P.Xl2[n_j]; n_L = __ldcg(Ls + pos);
                     if (pos + GB_BLOCK < p) nn_j = perm_s[pos + GB_BLOCK];
                     fill(pos, -1);
                 }
@@ -680,7 +766,9 @@ __global__ void __maxnreg__(GB_GRAM_REGS) gibbs_gram_kernel(SweepParams P)
                 const double E = (double)f_A - x2c;
                 const double margin = E - (double)f_L;
                 const double guard = 1e-4 * (1.0 + fabs((double)f_A) + x2c + fabs((double)f_L));
-                if (c_exact || !(fabs(margin) > guard) || !(fmax(E, (double)f_L) < 20.0)) {
+                // (a NaN f_L -- uniform outside [1e-4, 1-1e-4] -- fails the first test)
+                if (!(fabs(margin) > guard) || !(fmax(E, (double)f_L) < 20.0)) {
+                    const double c_u = u_s ? u_s[pos] : rng_uniform(key, KIND_SPIKE_U, pos, sweep, 0);
                     spike = (c_u <= kappa_of(XjTr, c_xl2, h));   // the reference's own formula
                 } else {
                     spike = margin > 0.0;
@@ -731,7 +819,7 @@ __global__ void __maxnreg__(GB_GRAM_REGS) gibbs_gram_kernel(SweepParams P)
             } else if (off == first) {                        // the owner of the changing position
                 double bnew = 0.0;
                 if (!spike) {
-                    if (c_act) bnew = c_zn + c_pv * XjTr / h.sigma2;      // = slab_draw(...)
+                    if (c_act) bnew = c_zp.x + c_zp.y * XjTr / h.sigma2;  // = slab_draw(...)
                     else bnew = slab_draw(XjTr, c_xl2, h, z_s ? z_s[pos] : rng_normal(key, KIND_SLAB_Z, pos, sweep, 0));
                 }
                 const double delta = bnew - c_bold;
@@ -743,7 +831,7 @@ __global__ void __maxnreg__(GB_GRAM_REGS) gibbs_gram_kernel(SweepParams P)
                 if (bnew != 0) mask_s[c_j >> 5] |= (1u << (c_j & 31));
                 else mask_s[c_j >> 5] &= ~(1u << (c_j & 31));
                 // a column that is not L2-resident is on its way by the time it is flushed
-                if (DESIGN == BLIPGPU_DESIGN_DENSE)
+                if (DESIGN == BLIPGPU_DESIGN_DENSE && !c_pref)
                     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(P.G + (int64_t)c_j * P.ldg),
                                  "r"((unsigned)(p2 * sizeof(double))) : "memory");
             }
@@ -778,18 +866,22 @@ __global__ void __maxnreg__(GB_GRAM_REGS) gibbs_gram_kernel(SweepParams P)
         sweep_epilogue(P, &sh, mask_s, beta_g, scratch, key, c, s, sh.rr, nullptr, false);
         __syncthreads();
     }
-#ifdef BLIP_PHASE_CLOCKS
-    if (tid == 0 && (c == 0 || c == 300)) {
-        printf("chain %d changes %lld windows %lld | epi+sweepstart %lld fill0 %lld | eval %lld sync1 %lld find %lld nullfill %lld | jstar %lld owner/fill/gather %lld sync2 %lld apply %lld flush %lld ownerfill %lld\n",
-               c, n_changes, n_windows, ph_t[0], ph_t[1], ph_t[2], ph_t[3], ph_t[4], ph_t[5], ph_t[6], ph_t[7], ph_t[8], ph_t[9], ph_t[10], ph_t[11]);
-    }
-#endif
-
     if (QSMEM) for (int k = tid; k < p2; k += GB_BLOCK) q_g[k] = q[k];
     for (int w = tid; w < P.words; w += GB_BLOCK) P.mask[(int64_t)c * P.words + w] = mask_s[w];
     if (tid == 0) {
         P.hstate[GB_HS * c + 0] = sh.sigma2; P.hstate[GB_HS * c + 1] = sh.tau2;
         P.hstate[GB_HS * c + 2] = sh.p0; P.hstate[GB_HS * c + 3] = sh.rr;
-        P.hstate[GB_HS * c + 4] += (double)n_changes; P.hstate[GB_HS * c + 5] += (double)n_windows;
+        P.hstate[GB_HS * c + 4] = __ldcg(P.hstate + GB_HS * c + 4) + (double)n_changes;
+        P.hstate[GB_HS * c + 5] = __ldcg(P.hstate + GB_HS * c + 5) + (double)n_windows;
     }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) { volatile int* pr = P.progress + c; *pr = sub + 1; }
+  }
+#ifdef BLIP_PHASE_CLOCKS
+    if (tid == 0 && blockIdx.x == 0) {
+        printf("cta 0 | epi+sweepstart %lld fill0 %lld | eval %lld sync1 %lld find %lld nullfill %lld | jstar %lld owner/fill/gather %lld sync2 %lld apply %lld flush %lld ownerfill %lld\n",
+               ph_t[0], ph_t[1], ph_t[2], ph_t[3], ph_t[4], ph_t[5], ph_t[6], ph_t[7], ph_t[8], ph_t[9], ph_t[10], ph_t[11]);
+    }
+#endif
 }
