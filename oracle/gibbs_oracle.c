@@ -67,7 +67,7 @@ void orc_philox4x32_10(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1,
 enum {
     KIND_SPIKE_U = 0,  /* c0 = position in permutation, c1 = sweep        */
     KIND_SLAB_Z = 1,   /* c0 = position in permutation, c1 = sweep        */
-    KIND_PERM = 2,     /* c0 = Fisher-Yates step >> 2,  c1 = sweep        */
+    KIND_PERM = 2,     /* c0 = round-key block (0,1),   c1 = sweep        */
     KIND_HYPER = 3,    /* c0 = slot, c1 = sweep, low 24 bits = attempt    */
     KIND_TRUNCNORM = 4 /* c0 = observation, c1 = event, low 24 = attempt  */
 };
@@ -140,23 +140,43 @@ double orc_beta(uint64_t seed, uint32_t chain, uint32_t proposal, uint32_t sweep
     return ga / (ga + gb);
 }
 
-/* Fisher-Yates permutation of 0..p-1 for (chain, sweep), from identity. */
+/* Visiting order of (chain, sweep) under the keyed stream: a 6-round alternating
+ * Feistel permutation of Z_a x Z_b (a = ceil(sqrt(p)), b = ceil(p/a)) with cycle
+ * walking into [0, p); round keys are two Philox blocks (DESIGN.md "Stream
+ * contract", kind PERM).  The reference uses np.random.shuffle (_linear.pyx:132);
+ * parity runs inject the reference's permutations instead of using this one. */
+static uint32_t perm_round(uint32_t v, uint32_t key, uint32_t radix)
+{
+    v = (v + key) * 0x9E3779B1u;
+    v ^= v >> 15; v *= 0x85EBCA77u;
+    v ^= v >> 13; v *= 0xC2B2AE3Du;
+    v ^= v >> 16;
+    return (uint32_t)(((uint64_t)v * radix) >> 32);
+}
+
 void orc_permutation(uint64_t seed, uint32_t chain, uint32_t sweep, int p,
                      int32_t *perm)
 {
-    for (int j = 0; j < p; ++j) perm[j] = j;
-    uint32_t w[4];
-    int have = -1;
-    for (int k = p - 1; k >= 1; --k) {
-        if ((k >> 2) != have) {
-            have = k >> 2;
-            orc_philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32),
-                              (uint32_t)have, sweep, chain,
-                              ((uint32_t)KIND_PERM << 24), w);
-        }
-        uint32_t x = w[k & 3];
-        int j = (int)(((uint64_t)x * (uint64_t)(k + 1)) >> 32);
-        int32_t t = perm[k]; perm[k] = perm[j]; perm[j] = t;
+    uint32_t a = 1;
+    while ((uint64_t)a * a < (uint64_t)p) ++a;
+    const uint32_t b = ((uint32_t)p + a - 1) / a;
+    uint32_t x4[4], y4[4], rk[6];
+    orc_philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), 0u, sweep, chain,
+                      ((uint32_t)KIND_PERM << 24), x4);
+    orc_philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), 1u, sweep, chain,
+                      ((uint32_t)KIND_PERM << 24), y4);
+    rk[0] = x4[0]; rk[1] = x4[1]; rk[2] = x4[2]; rk[3] = x4[3]; rk[4] = y4[0]; rk[5] = y4[1];
+    for (int pos = 0; pos < p; ++pos) {
+        uint32_t x = (uint32_t)pos;
+        do {
+            uint32_t L = x / b, R = x - L * b;
+            for (int r = 0; r < 6; r += 2) {
+                L += perm_round(R, rk[r], a);     if (L >= a) L -= a;
+                R += perm_round(L, rk[r + 1], b); if (R >= b) R -= b;
+            }
+            x = L * b + R;
+        } while (x >= (uint32_t)p);
+        perm[pos] = (int32_t)x;
     }
 }
 

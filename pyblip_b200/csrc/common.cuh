@@ -42,7 +42,7 @@ void blip_set_error(const char* fmt, ...);
 enum : uint32_t {
     KIND_SPIKE_U = 0,   // c0 = position in permutation, c1 = sweep
     KIND_SLAB_Z = 1,    // c0 = position in permutation, c1 = sweep
-    KIND_PERM = 2,      // c0 = Fisher-Yates step >> 2,  c1 = sweep
+    KIND_PERM = 2,      // c0 = round-key block (0, 1),  c1 = sweep: keys of the visiting-order permutation
     KIND_HYPER = 3,     // c0 = slot, c1 = sweep, low 24 bits of c3 = attempt
     KIND_TRUNCNORM = 4, // c0 = observation, c1 = redraw event, low 24 = attempt
     KIND_NPRIOR = 5,    // neuronized prior sub-streams (see nprior.cu)
@@ -65,6 +65,54 @@ __host__ __device__ __forceinline__ uint4 philox4x32_10(uint32_t k0, uint32_t k1
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
     return make_uint4(c0, c1, c2, c3);
+}
+
+// Visiting order of a sweep: a keyed pseudo-random permutation of [0, p), evaluated point-wise
+// (any thread can compute the coordinate visited at any position, no sequential shuffle):
+// a 6-round alternating Feistel network on Z_a x Z_b (a = ceil(sqrt(p)), b = ceil(p / a), so
+// that a*b exceeds p by less than a) with cycle walking back into [0, p).  Round keys are
+// Philox words of (seed, chain, sweep); a round adds a keyed hash of one half to the other
+// half modulo its radix (multiply-shift range reduction, no division).  The reference
+// shuffles with NumPy's Fisher-Yates (pyblip/linear/_linear.pyx:132); any permutation law
+// gives a valid sampler, and parity runs inject the reference's own permutations.
+struct PermKey { uint32_t rk[6]; uint32_t a, b; };
+
+__host__ __device__ __forceinline__ PermKey perm_key(uint32_t k0, uint32_t k1, uint32_t chain,
+                                                     uint32_t sweep, uint32_t p)
+{
+    PermKey K;
+    uint32_t a = 1;
+    while ((uint64_t)a * a < (uint64_t)p) ++a;       // p <= 2^31: a <= 46341
+    K.a = a;
+    K.b = (p + a - 1) / a;
+    const uint4 x = philox4x32_10(k0, k1, 0u, sweep, chain, 2u << 24);
+    const uint4 y = philox4x32_10(k0, k1, 1u, sweep, chain, 2u << 24);
+    K.rk[0] = x.x; K.rk[1] = x.y; K.rk[2] = x.z; K.rk[3] = x.w; K.rk[4] = y.x; K.rk[5] = y.y;
+    return K;
+}
+
+__host__ __device__ __forceinline__ uint32_t perm_round(uint32_t v, uint32_t key, uint32_t radix)
+{
+    v = (v + key) * 0x9E3779B1u;
+    v ^= v >> 15; v *= 0x85EBCA77u;
+    v ^= v >> 13; v *= 0xC2B2AE3Du;
+    v ^= v >> 16;
+    return (uint32_t)(((uint64_t)v * radix) >> 32);   // uniform on [0, radix)
+}
+
+__host__ __device__ __forceinline__ uint32_t perm_at(const PermKey& K, uint32_t pos, uint32_t p)
+{
+    uint32_t x = pos;
+    do {
+        uint32_t L = x / K.b, R = x - L * K.b;        // L in [0,a), R in [0,b)
+#pragma unroll
+        for (int r = 0; r < 6; r += 2) {
+            L += perm_round(R, K.rk[r], K.a);     if (L >= K.a) L -= K.a;
+            R += perm_round(L, K.rk[r + 1], K.b); if (R >= K.b) R -= K.b;
+        }
+        x = L * K.b + R;
+    } while (x >= p);
+    return x;
 }
 
 __host__ __device__ __forceinline__ double u52(uint32_t a, uint32_t b)

@@ -15,31 +15,18 @@
 namespace {
 
 // ---------------------------------------------------------------------------
-// permutations: one thread per (chain, sweep) runs Fisher-Yates from identity,
-// Philox words indexed by (step >> 2, sweep, chain).
+// visiting orders: one block per (chain, sweep) evaluates the keyed permutation point-wise
+// (common.cuh: perm_at) -- embarrassingly parallel, coalesced stores.
 // ---------------------------------------------------------------------------
 template <typename T>
 __global__ void perm_fill_kernel(T* perm, int chains, int S, int p, int sweep0, uint32_t k0,
                                  uint32_t k1, uint32_t chain_offset)
 {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (int64_t)chains * S) return;
+    const int64_t t = blockIdx.x;                  // (chain, sweep) pair
     const int c = (int)(t / S), s = (int)(t % S);
+    const PermKey K = perm_key(k0, k1, chain_offset + (uint32_t)c, (uint32_t)(sweep0 + s), (uint32_t)p);
     T* a = perm + t * p;
-    for (int j = 0; j < p; ++j) a[j] = (T)j;
-    const uint32_t chain = chain_offset + (uint32_t)c, sweep = (uint32_t)(sweep0 + s);
-    uint4 w = make_uint4(0, 0, 0, 0);
-    int have = -1;
-    for (int k = p - 1; k >= 1; --k) {
-        if ((k >> 2) != have) {
-            have = k >> 2;
-            w = philox4x32_10(k0, k1, (uint32_t)have, sweep, chain, KIND_PERM << 24);
-        }
-        const int sel = k & 3;
-        const uint32_t x = sel == 0 ? w.x : sel == 1 ? w.y : sel == 2 ? w.z : w.w;
-        const int j = (int)(((uint64_t)x * (uint64_t)(k + 1)) >> 32);
-        T tmp = a[k]; a[k] = a[j]; a[j] = tmp;
-    }
+    for (int pos = threadIdx.x; pos < p; pos += blockDim.x) a[pos] = (T)perm_at(K, (uint32_t)pos, (uint32_t)p);
 }
 
 // q0[j] = X_j . y   (one warp per column)
@@ -121,9 +108,9 @@ int blip_fill_perms(cudaStream_t st, void* buf, int perm16, int64_t chains, int 
     const int64_t nt = chains * S;
     if (nt <= 0) return BLIP_OK;
     if (perm16)
-        perm_fill_kernel<uint16_t><<<(unsigned)((nt + 63) / 64), 64, 0, st>>>((uint16_t*)buf, (int)chains, S, (int)p, (int)sweep0, k0, k1, chain_offset);
+        perm_fill_kernel<uint16_t><<<(unsigned)nt, 256, 0, st>>>((uint16_t*)buf, (int)chains, S, (int)p, (int)sweep0, k0, k1, chain_offset);
     else
-        perm_fill_kernel<int32_t><<<(unsigned)((nt + 63) / 64), 64, 0, st>>>((int32_t*)buf, (int)chains, S, (int)p, (int)sweep0, k0, k1, chain_offset);
+        perm_fill_kernel<int32_t><<<(unsigned)nt, 256, 0, st>>>((int32_t*)buf, (int)chains, S, (int)p, (int)sweep0, k0, k1, chain_offset);
     CUDA_TRY(cudaGetLastError());
     return BLIP_OK;
 }
@@ -205,7 +192,6 @@ extern "C" int blipgpu_sample_spikeslab(blipgpu_ctx* ctx, blipgpu_design* design
     }
     const bool inj_perm = streams && streams->perm;
     // Permutations are generated for PS sweeps at a time (a multiple of the launch chunk S):
-    // Fisher-Yates is latency bound, so more (chain, sweep) pairs per launch amortise it.
     // 16-bit entries when p allows; <= 1.5 GB per buffer, two buffers.
     const bool perm16 = !inj_perm && p <= 65535;
     const size_t perm_elt = perm16 ? sizeof(uint16_t) : sizeof(int32_t);
@@ -226,7 +212,7 @@ extern "C" int blipgpu_sample_spikeslab(blipgpu_ctx* ctx, blipgpu_design* design
     }
 
     // ---- allocate
-    DevBuf d_beta, d_r, d_mu, d_ylat, d_q, d_h, d_mask, d_ev, d_q0, d_y, d_z, d_ovf, d_scrL, d_scrZ, d_queue;
+    DevBuf d_beta, d_r, d_mu, d_ylat, d_q, d_h, d_mask, d_ev, d_q0, d_y, d_z, d_ovf, d_scrL, d_scrZ, d_scrP, d_queue;
     DevBuf d_perm[2], d_u, d_zn, d_ig, d_p0, d_g;
     DevBuf snap_beta, snap_r, snap_mu, snap_ylat, snap_q, snap_h, snap_mask, snap_ev;
     BLIP_TRY(d_beta.alloc(sizeof(double) * chains * p));
@@ -249,8 +235,15 @@ extern "C" int blipgpu_sample_spikeslab(blipgpu_ctx* ctx, blipgpu_design* design
         }
     }
     if (!probit) BLIP_TRY(d_y.alloc(sizeof(double) * n));
-    BLIP_TRY(d_perm[0].alloc(perm_elt * chains * PS * p));
-    if (!inj_perm && n_total > S) BLIP_TRY(d_perm[1].alloc(perm_elt * chains * PS * p));
+    // gram mode evaluates the keyed visiting order inside the sweep kernel (chain-private scratch);
+    // the other kernels read permutation buffers filled ahead of them on the second stream
+    const bool perm_in_kernel = gram && !inj_perm;
+    const bool gen_perms = !inj_perm && !perm_in_kernel;
+    if (perm_in_kernel) BLIP_TRY(d_scrP.alloc(perm_elt * chains * p));
+    else {
+        BLIP_TRY(d_perm[0].alloc(perm_elt * chains * PS * p));
+        if (!inj_perm && n_total > S) BLIP_TRY(d_perm[1].alloc(perm_elt * chains * PS * p));
+    }
     if (inj_u) BLIP_TRY(d_u.alloc(sizeof(double) * chains * S * p));
     if (inj_z) BLIP_TRY(d_zn.alloc(sizeof(double) * chains * S * p));
     if (inj_ig) BLIP_TRY(d_ig.alloc(sizeof(double) * chains * S));
@@ -301,6 +294,7 @@ extern "C" int blipgpu_sample_spikeslab(blipgpu_ctx* ctx, blipgpu_design* design
     P.mask = d_mask.as<uint32_t>(); P.events = d_ev.as<uint32_t>();
     P.q0 = d_q0.as<double>(); P.zlab = d_z.as<int32_t>();
     P.scrL = d_scrL.as<float>(); P.scrZ = d_scrZ.as<double2>();
+    P.scrP = d_scrP.ptr;
     P.queue = d_queue.as<int>(); P.progress = d_queue.as<int>() + 1; P.n_chains = (int)chains;
     P.k0 = (uint32_t)seed; P.k1 = (uint32_t)(seed >> 32); P.chain_offset = (uint32_t)chain_offset;
     P.nprop = nprop; P.burn = (int)burn; P.n_keep = (int)n_keep;
@@ -369,10 +363,10 @@ extern "C" int blipgpu_sample_spikeslab(blipgpu_ctx* ctx, blipgpu_design* design
         CUDA_TRY(cudaStreamWaitEvent(st2, ev_done[buf], 0));
         const int64_t nt = chains * Sc;
         if (perm16)
-            perm_fill_kernel<uint16_t><<<(unsigned)((nt + 63) / 64), 64, 0, st2>>>(d_perm[buf].as<uint16_t>(), (int)chains, Sc, (int)p,
+            perm_fill_kernel<uint16_t><<<(unsigned)nt, 256, 0, st2>>>(d_perm[buf].as<uint16_t>(), (int)chains, Sc, (int)p,
                                                                                  (int)sweep0, P.k0, P.k1, P.chain_offset);
         else
-            perm_fill_kernel<int32_t><<<(unsigned)((nt + 63) / 64), 64, 0, st2>>>(d_perm[buf].as<int32_t>(), (int)chains, Sc, (int)p,
+            perm_fill_kernel<int32_t><<<(unsigned)nt, 256, 0, st2>>>(d_perm[buf].as<int32_t>(), (int)chains, Sc, (int)p,
                                                                                 (int)sweep0, P.k0, P.k1, P.chain_offset);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(ev_perm[buf], st2));
@@ -384,24 +378,24 @@ extern "C" int blipgpu_sample_spikeslab(blipgpu_ctx* ctx, blipgpu_design* design
     // permutation chunk boundaries: a short first chunk (nothing can hide its generation),
     // then PS sweeps each
     std::vector<int64_t> pstart;
-    if (!inj_perm) {
+    if (gen_perms) {
         pstart.push_back(0);
         int64_t at = std::min<int64_t>(S, n_total);
         while (at < n_total) { pstart.push_back(at); at = std::min<int64_t>(at + PS, n_total); }
         pstart.push_back(n_total);
     }
-    const int64_t n_perm_chunks = inj_perm ? 0 : (int64_t)pstart.size() - 1;
-    if (!inj_perm) BLIP_TRY(gen_perm(0, 0, (int)(pstart[1] - pstart[0])));
+    const int64_t n_perm_chunks = !gen_perms ? 0 : (int64_t)pstart.size() - 1;
+    if (gen_perms) BLIP_TRY(gen_perm(0, 0, (int)(pstart[1] - pstart[0])));
     int64_t pc = 0;
     int64_t max_chunk_use = 0;
     unsigned long long used_before = 0;
     for (int64_t ch = 0; ch < nchunks; ++ch) {
         const int64_t sweep0 = ch * S;
         const int Sc = (int)std::min<int64_t>(S, n_total - sweep0);
-        if (!inj_perm) while (sweep0 >= pstart[(size_t)pc + 1]) ++pc;   // permutation chunk of this launch
-        const int buf = inj_perm ? 0 : (int)(pc & 1);
-        const int64_t pc_sweep0 = inj_perm ? sweep0 : pstart[(size_t)pc];
-        const int64_t pc_end = inj_perm ? sweep0 + Sc : pstart[(size_t)pc + 1];
+        if (gen_perms) while (sweep0 >= pstart[(size_t)pc + 1]) ++pc;   // permutation chunk of this launch
+        const int buf = !gen_perms ? 0 : (int)(pc & 1);
+        const int64_t pc_sweep0 = !gen_perms ? sweep0 : pstart[(size_t)pc];
+        const int64_t pc_end = !gen_perms ? sweep0 + Sc : pstart[(size_t)pc + 1];
         const int PSc = (int)(pc_end - pc_sweep0);
         if (inj_perm) BLIP_TRY(upload_chunk(d_perm[0].as<int32_t>(), streams->perm, chains, n_total * p, sweep0 * p, (int64_t)Sc * p, st));
         else if (sweep0 == pc_sweep0) {                             // first launch of a permutation chunk
@@ -448,8 +442,8 @@ extern "C" int blipgpu_sample_spikeslab(blipgpu_ctx* ctx, blipgpu_design* design
         BLIP_TRY(copy_state(true));
 
         for (int attempt = 0;; ++attempt) {
-            P.perm = d_perm[buf].ptr; P.perm16 = perm16 ? 1 : 0;
-            P.perm_S = PSc; P.perm_s0 = inj_perm ? 0 : (int)(sweep0 - pc_sweep0);
+            P.perm = perm_in_kernel ? nullptr : d_perm[buf].ptr; P.perm16 = perm16 ? 1 : 0;
+            P.perm_S = PSc; P.perm_s0 = !gen_perms ? 0 : (int)(sweep0 - pc_sweep0);
             P.u = d_u.as<double>(); P.z = d_zn.as<double>(); P.invgamma = d_ig.as<double>();
             P.p0_draw = d_p0.as<double>(); P.gamma_draw = d_g.as<double>();
             P.sweep0 = (int)sweep0; P.S = Sc;
@@ -492,7 +486,7 @@ extern "C" int blipgpu_sample_spikeslab(blipgpu_ctx* ctx, blipgpu_design* design
             max_chunk_use = std::max<int64_t>(max_chunk_use, wanted);
             BLIP_TRY(grow(wanted + wanted / 4 + 1024));
         }
-        if (!inj_perm && sweep0 + Sc >= pc_end)
+        if (gen_perms && sweep0 + Sc >= pc_end)
             CUDA_TRY(cudaEventRecord(ev_done[buf], st));           // last launch that reads this buffer
     }
     CUDA_TRY(cudaStreamSynchronize(st2));
@@ -509,7 +503,7 @@ extern "C" int blipgpu_sample_spikeslab(blipgpu_ctx* ctx, blipgpu_design* design
             smp->n_windows += (int64_t)hs[(size_t)(GB_HS * c + 5)];
         }
         // kernels: init + (x'y) + per chunk (permutation + sweep, sweeps counted by the timer)
-        ctx->kernel_launches += 1 + (gram && design->kind == BLIPGPU_DESIGN_DENSE ? 1 : 0) + (inj_perm ? 0 : n_perm_chunks);
+        ctx->kernel_launches += 1 + (gram && design->kind == BLIPGPU_DESIGN_DENSE ? 1 : 0) + (gen_perms ? n_perm_chunks : 0);
         ctx->h2d_bytes += (int64_t)(probit ? sizeof(int32_t) : sizeof(double)) * n;
     }
     if (probit) {

@@ -63,15 +63,16 @@ struct SweepParams {
     // gram mode work queue: items (chain, sub-chunk of sub_sweeps sweeps) handed out in order;
     // progress[c] = sub-chunks of chain c completed in this launch
     int* queue; int* progress; int n_chains, sub_sweeps;
+    void* scrP;                // gram mode, keyed visiting order: [chains][p] uint16/int32, rewritten every sweep
     float* scrL;               // gram mode: [chains][p]  logit of the spike uniform per position (NaN = exact path)
     double2* scrZ;             // gram mode: [chains][p]  (sqrt(post_var) * z, post_var) at positions of active coordinates
 };
 
 struct PermView {           // visiting order of one (chain, sweep)
     const void* base; int64_t off; int is16;
-    __device__ __forceinline__ int operator[](int pos) const {
-        return is16 ? (int)reinterpret_cast<const uint16_t*>(base)[off + pos]
-                    : reinterpret_cast<const int32_t*>(base)[off + pos];
+    __device__ __forceinline__ int operator[](int pos) const {   // L2 loads: the gram kernel's
+        return is16 ? (int)__ldcg(reinterpret_cast<const uint16_t*>(base) + off + pos)   // scratch copy is
+                    : __ldcg(reinterpret_cast<const int32_t*>(base) + off + pos);         // rewritten every sweep
     }
 };
 __device__ __forceinline__ PermView perm_view(const SweepParams& P, int c, int s)
@@ -619,7 +620,8 @@ __global__ void __maxnreg__(GB_GRAM_REGS) gibbs_gram_kernel(SweepParams P)
     for (int s = s_begin; s < s_end; ++s) {
         const int sweep = P.sweep0 + s;
         const int64_t soff = ((int64_t)c * P.S + s) * p;
-        const PermView perm_s = perm_view(P, c, s);
+        // keyed visiting order: computed point-wise below into chain-private scratch; injected: read
+        const PermView perm_s = P.perm ? perm_view(P, c, s) : PermView{ P.scrP, (int64_t)c * p, P.perm16 };
         const double* u_s = P.u ? P.u + soff : nullptr;
         const double* z_s = P.z ? P.z + soff : nullptr;
         PH(0);
@@ -663,10 +665,21 @@ __global__ void __maxnreg__(GB_GRAM_REGS) gibbs_gram_kernel(SweepParams P)
         double2* Zs = P.scrZ + (int64_t)c * p;
         if (tid == 0) act_n = 0;
         __syncthreads();
+        const bool keyed_perm = P.perm == nullptr;
+        PermKey pk;
+        if (keyed_perm) pk = perm_key(P.k0, P.k1, key.chain, (uint32_t)sweep, (uint32_t)p);
         for (int base = tid; base < p; base += 4 * GB_BLOCK) {
             int jj[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) jj[i] = base + i * GB_BLOCK < p ? perm_s[base + i * GB_BLOCK] : -1;
+            for (int i = 0; i < 4; ++i) {
+                const int pos = base + i * GB_BLOCK;
+                if (pos >= p) jj[i] = -1;
+                else if (keyed_perm) {
+                    jj[i] = (int)perm_at(pk, (uint32_t)pos, (uint32_t)p);
+                    if (P.perm16) reinterpret_cast<uint16_t*>(P.scrP)[(int64_t)c * p + pos] = (uint16_t)jj[i];
+                    else reinterpret_cast<int32_t*>(P.scrP)[(int64_t)c * p + pos] = jj[i];
+                } else jj[i] = perm_s[pos];
+            }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int pos = base + i * GB_BLOCK;
