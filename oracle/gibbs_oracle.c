@@ -261,6 +261,53 @@ typedef struct {
     int32_t nprop;
 } orc_streams;
 
+/* _update_hparams (pyblip/cython_utils/_update_hparams.pyx:18-92) for sweep i:
+ * beta_i = row i of betas, r = current residual.  Shared by the single-site and
+ * the block sampler (oracle/multi_oracle.c). */
+void orc_update_hparams(int i, int n, int p, const double *beta_i, const double *r,
+                        const orc_hparams *hp, uint64_t seed, uint32_t chain,
+                        const orc_streams *st, double *p0s, double *tau2s, double *sigma2s)
+{
+    const int max_nprop = 100;
+    const double sigma_a = n / 2.0 + hp->sigma2_a0;  /* _linear.pyx:108 */
+    int num_active = 0;                              /* :52-54 */
+    for (int j = 0; j < p; ++j) if (beta_i[j] != 0) num_active++;
+    if (hp->update_p0 == 1) {                        /* :57-72 */
+        double a = hp->p0_a0 + p - num_active, b = hp->p0_b0 + num_active;
+        if (hp->min_p0 == 0) {
+            p0s[i] = (st && st->p0_draw) ? st->p0_draw[(size_t)i * st->nprop]
+                                         : orc_beta(seed, chain, 0, i, a, b);
+        } else {
+            p0s[i] = hp->min_p0;
+            for (int jj = 0; jj < max_nprop; ++jj) {
+                double prop = (st && st->p0_draw)
+                    ? st->p0_draw[(size_t)i * st->nprop + jj]
+                    : orc_beta(seed, chain, jj, i, a, b);
+                if (prop > hp->min_p0) { p0s[i] = prop; break; }
+            }
+        }
+    }
+    if (hp->update_sigma2 == 1) {                    /* :75-81 */
+        double ss = 0;
+        for (int it = 0; it < n; ++it) ss += r[it] * r[it];
+        double r2 = sqrt(ss);                        /* dnrm2 ... */
+        r2 = r2 * r2;                                /* ... squared, :77-78 */
+        double sigma_b = r2 / 2.0 + hp->sigma2_b0;
+        double ig = (st && st->invgamma) ? st->invgamma[i]
+            : 1.0 / orc_gamma(seed, chain, SLOT_INVGAMMA, i, sigma_a);
+        sigma2s[i] = sigma_b * ig;
+    }
+    if (hp->update_tau2) {                           /* :84-91 */
+        double sample_var = 0;
+        for (int j = 0; j < p; ++j)
+            if (beta_i[j] != 0) sample_var += beta_i[j] * beta_i[j];
+        double g = (st && st->gamma_draw) ? st->gamma_draw[i]
+            : orc_gamma(seed, chain, SLOT_TAU_GAMMA, i,
+                        hp->tau2_a0 + (double)num_active / 2.0);
+        tau2s[i] = (hp->tau2_b0 + sample_var / 2.0) / g;
+    }
+}
+
 int orc_sample_spikeslab(
     int N, int n, int p,
     const double *X,          /* [n][p] row-major, like the reference          */
@@ -275,7 +322,6 @@ int orc_sample_spikeslab(
     double *y_latent,         /* [N][n] or NULL */
     int64_t *n_events_out)    /* probit: number of latent redraw events */
 {
-    const int max_nprop = 100;
     double *XT = (double *)malloc(sizeof(double) * (size_t)n * p);
     double *Xl2 = (double *)calloc(p, sizeof(double));
     double *logdets = (double *)calloc(p, sizeof(double));
@@ -297,7 +343,6 @@ int orc_sample_spikeslab(
     if (!probit) memcpy(y, y_in, sizeof(double) * n);
 
     double logodds = log(hp->p0) - log(1 - hp->p0);  /* :76 */
-    double sigma_a = n / 2.0 + hp->sigma2_a0;        /* :108 */
     uint32_t event = 0;
 
     sigma2s[0] = hp->sigma2; tau2s[0] = hp->tau2; p0s[0] = hp->p0;  /* :112-114 */
@@ -365,43 +410,7 @@ int orc_sample_spikeslab(
             }
         }
 
-        /* ---- _update_hparams.pyx:51-91 ---- */
-        int num_active = 0;
-        for (int j = 0; j < p; ++j) if (beta_i[j] != 0) num_active++;
-        if (hp->update_p0 == 1) {
-            double a = hp->p0_a0 + p - num_active, b = hp->p0_b0 + num_active;
-            if (hp->min_p0 == 0) {
-                p0s[i] = (st && st->p0_draw) ? st->p0_draw[(size_t)i * st->nprop]
-                                             : orc_beta(seed, chain, 0, i, a, b);
-            } else {
-                p0s[i] = hp->min_p0;
-                for (int jj = 0; jj < max_nprop; ++jj) {
-                    double prop = (st && st->p0_draw)
-                        ? st->p0_draw[(size_t)i * st->nprop + jj]
-                        : orc_beta(seed, chain, jj, i, a, b);
-                    if (prop > hp->min_p0) { p0s[i] = prop; break; }
-                }
-            }
-        }
-        if (hp->update_sigma2 == 1) {
-            double ss = 0;
-            for (int it = 0; it < n; ++it) ss += r[it] * r[it];
-            double r2 = sqrt(ss);                    /* dnrm2 ... */
-            r2 = r2 * r2;                            /* ... squared, :77-78 */
-            double sigma_b = r2 / 2.0 + hp->sigma2_b0;
-            double ig = (st && st->invgamma) ? st->invgamma[i]
-                : 1.0 / orc_gamma(seed, chain, SLOT_INVGAMMA, i, sigma_a);
-            sigma2s[i] = sigma_b * ig;
-        }
-        if (hp->update_tau2) {
-            double sample_var = 0;
-            for (int j = 0; j < p; ++j)
-                if (beta_i[j] != 0) sample_var += beta_i[j] * beta_i[j];
-            double g = (st && st->gamma_draw) ? st->gamma_draw[i]
-                : orc_gamma(seed, chain, SLOT_TAU_GAMMA, i,
-                            hp->tau2_a0 + (double)num_active / 2.0);
-            tau2s[i] = (hp->tau2_b0 + sample_var / 2.0) / g;
-        }
+        orc_update_hparams(i, n, p, beta_i, r, hp, seed, chain, st, p0s, tau2s, sigma2s);
         logodds = log(p0s[i]) - log(1 - p0s[i]);     /* :222 */
         if (i != N - 1) {                            /* :225-229 */
             memcpy(betas + (size_t)(i + 1) * p, beta_i, sizeof(double) * p);

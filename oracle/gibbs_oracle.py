@@ -206,3 +206,89 @@ def nprior_sample(N, X, y, tauw2, p0_init=None, min_p0=1e-10, update_p0=True, si
     if rc != 0:
         raise MemoryError("oracle allocation failed")
     return dict(alphas=alphas, ws=ws, betas=betas, sigma2s=sigma2s, alpha0s=alpha0s, p0s=p0s)
+
+
+# ---------------------------------------------------------------------------
+# block sampler, bsize > 1 (oracle/multi_oracle.c)
+# ---------------------------------------------------------------------------
+class MultiStreams(C.Structure):
+    _fields_ = [("blocks", C.c_void_p), ("u", C.c_void_p), ("z", C.c_void_p),
+                ("invgamma", C.c_void_p), ("p0_draw", C.c_void_p), ("gamma_draw", C.c_void_p),
+                ("nprop", C.c_int32)]
+
+
+def multi_nblock(p, bsize):
+    """`round((p + bsize - 1) / bsize)` with C integer division (_linear_multi.pyx:298)."""
+    f = lib().orc_multi_nblock
+    f.restype = C.c_int
+    return int(f(C.c_int(p), C.c_int(bsize)))
+
+
+def multi_models(bsize, max_signals_per_block=0):
+    """Bit masks of the non-empty models in the reference's enumeration order (:405-409)."""
+    f = lib().orc_multi_models
+    f.restype = C.c_int
+    ms = max_signals_per_block or bsize
+    n = f(C.c_int(bsize), C.c_int(ms), None, C.c_int(0))
+    out = np.zeros(n, dtype=np.uint32)
+    f(C.c_int(bsize), C.c_int(ms), C.c_void_p(out.ctypes.data), C.c_int(n))
+    return out
+
+
+def sample_spikeslab_multi(N, bsize, X, y=None, z=None, probit=False, hp=None,
+                           max_signals_per_block=0, seed=0, chain=0, blocks=None, u=None, zn=None,
+                           invgamma=None, p0_draw=None, gamma_draw=None):
+    """One chain of ``_sample_spikeslab_multi`` (_linear_multi.pyx:271).  Streams left as None
+    use the keyed Philox stream."""
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    n, p = X.shape
+    hp = hp or hparams()
+    nblock = multi_nblock(p, bsize)
+    y = np.zeros(n) if y is None else np.ascontiguousarray(y, dtype=np.float64)
+    zl = np.zeros(n, dtype=np.int64) if z is None else np.ascontiguousarray(z, dtype=np.int64)
+    keep = []
+
+    def prep(a, dt, shape):
+        if a is None:
+            return None
+        a = np.ascontiguousarray(a, dtype=dt)
+        assert a.shape == shape, (a.shape, shape)
+        keep.append(a)
+        return a
+
+    blocks = prep(blocks, np.int32, (nblock, bsize))
+    u = prep(u, np.float64, (N, nblock))
+    zn = prep(zn, np.float64, (N, nblock, bsize))
+    invgamma = prep(invgamma, np.float64, (N,))
+    gamma_draw = prep(gamma_draw, np.float64, (N,))
+    nprop = 1
+    if p0_draw is not None:
+        p0_draw = np.ascontiguousarray(p0_draw, dtype=np.float64)
+        if p0_draw.ndim == 1:
+            p0_draw = p0_draw.reshape(N, 1)
+        nprop = p0_draw.shape[1]
+        keep.append(p0_draw)
+    st = MultiStreams(_ptr(blocks), _ptr(u), _ptr(zn), _ptr(invgamma), _ptr(p0_draw),
+                      _ptr(gamma_draw), nprop)
+    betas = np.zeros((N, p))
+    p0s, tau2s, sigma2s = np.zeros(N), np.zeros(N), np.zeros(N)
+    ylat = np.zeros((N, n)) if probit else None
+    nev = C.c_int64(0)
+    f = lib().orc_sample_spikeslab_multi
+    f.restype = C.c_int
+    rc = f(C.c_int(N), C.c_int(bsize), C.c_int(n), C.c_int(p), C.c_void_p(X.ctypes.data),
+           C.c_void_p(y.ctypes.data), C.c_void_p(zl.ctypes.data), C.c_int(int(probit)),
+           C.byref(hp), C.c_int(int(max_signals_per_block)), C.c_uint64(seed), C.c_uint32(chain),
+           C.byref(st), C.c_void_p(betas.ctypes.data), C.c_void_p(p0s.ctypes.data),
+           C.c_void_p(tau2s.ctypes.data), C.c_void_p(sigma2s.ctypes.data),
+           C.c_void_p(_ptr(ylat)), C.byref(nev))
+    if rc == 2:
+        raise RuntimeError("dpotrf failed: a block model's matrix is not positive definite")
+    if rc == 3:
+        raise ValueError("oracle supports 1 <= bsize <= 16")
+    if rc != 0:
+        raise MemoryError("oracle allocation failed")
+    out = {"betas": betas, "p0s": p0s, "tau2s": tau2s, "sigma2s": sigma2s, "n_events": nev.value}
+    if probit:
+        out["y_latent"] = ylat
+    return out

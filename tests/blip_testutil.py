@@ -14,6 +14,8 @@ SAMPLER_CASES = ["linear_c1", "linear_minp0", "linear_fixed", "linear_dense", "l
 LINEAR_CASES = [c for c in SAMPLER_CASES if c.startswith("linear")]
 PROBIT_CASES = [c for c in SAMPLER_CASES if c.startswith("probit")]
 COUNTING_CASES = ["hand", "sparse_a", "sparse_b", "wide", "float_vals"]
+MULTI_CASES = ["multi_b3", "multi_b5", "multi_b2_even", "multi_b4_wrap", "multi_b5_cap2", "multi_fixed",
+               "multi_probit_b3", "multi_probit_b2"]
 
 
 def load_sampler_case(name):
@@ -39,6 +41,21 @@ def stacked_streams(case):
         arr = np.stack([cd["streams"][k] for cd in case["chains_data"]])
         out["z" if k == "zn" else k] = arr
     return out
+
+
+def load_multi_case(name):
+    """Block-sampler fixture written by oracle/pin_multi.py (reference run + recorded stream)."""
+    case = load_sampler_case(name)
+    d = np.load(os.path.join(GOLDEN, name + ".npz"))
+    case["bsize"] = int(d["bsize"])
+    case["max_signals"] = int(d["max_signals"])
+    return case
+
+
+def latent_err(a, b):
+    """Error of probit latents against their unit scale (values near the truncation point cancel)."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1.0))) if a.size else 0.0
 
 
 def rel_err(a, b):

@@ -107,3 +107,35 @@ def test_nprior_oracle_replays_reference(name):
     assert np.array_equal(out["betas"] != 0, d["ref_betas"] != 0)
     for k in ("alphas", "ws", "betas", "sigma2s", "alpha0s", "p0s"):
         assert util.rel_err(out[k], d["ref_" + k]) <= 1e-9, (name, k)
+
+
+@pytest.mark.parametrize("name", util.MULTI_CASES)
+def test_block_oracle_replays_reference(name):
+    """oracle/multi_oracle.c against the reference's recorded `_sample_spikeslab_multi` runs
+    (oracle/pin_multi.py): identical indicators, 1e-9 on coefficients and hyper-parameters."""
+    case = util.load_multi_case(name)
+    probit = case["probit"]
+    for c, cd in enumerate(case["chains_data"]):
+        st = dict(cd["streams"])
+        out = go.sample_spikeslab_multi(
+            case["N"], case["bsize"], case["X"], y=None if probit else case["y"],
+            z=case["y"].astype(np.int64) if probit else None, probit=probit,
+            hp=go.hparams(**case["hp"]), max_signals_per_block=case["max_signals"],
+            seed=case["tn_seed"], chain=c, **st)
+        ref = cd["ref"]
+        assert np.array_equal(out["betas"] != 0, ref["betas"] != 0), (name, c)
+        for k in ("betas", "p0s", "tau2s", "sigma2s"):
+            assert util.rel_err(out[k], ref[k]) <= 1e-9, (name, c, k)
+        if probit:
+            assert util.latent_err(out["y_latent"], ref["y_latent"]) <= 1e-9, (name, c)
+
+
+def test_block_oracle_partition_and_models():
+    """Block table of the keyed stream: ceil(p/bsize) blocks of consecutive wrapping indices
+    (_linear_multi.pyx:298,395-402); models in itertools.combinations order (:405-409)."""
+    import itertools
+    assert [go.multi_nblock(p, b) for p, b in ((10, 3), (10, 4), (8, 4), (9, 3), (500, 5))] == [4, 3, 2, 3, 100]
+    for bsize, cap in ((3, 0), (5, 0), (5, 2), (4, 1)):
+        want = [sum(1 << j for j in comb) for m in range(1, (cap or bsize) + 1)
+                for comb in itertools.combinations(range(bsize), m)]
+        assert list(go.multi_models(bsize, cap)) == want
