@@ -130,6 +130,38 @@ int blipgpu_sample_spikeslab(blipgpu_ctx* ctx, blipgpu_design* design,
                              const blipgpu_sample_options* opts,
                              blipgpu_samples** out);
 
+/* ---- block spike-and-slab sampler (bsize > 1) ---------------------------- */
+/* Optional injected stream of the block sampler (HOST arrays, chain-major; NULL member =
+ * keyed Philox stream).  nblock = ceil(p / bsize); a block is `bsize` consecutive indices
+ * (wrapping at p) starting at a multiple of bsize. */
+typedef struct blipgpu_multi_streams {
+    const int32_t* blocks;    /* [chains][nblock][bsize] block table in visiting order (the
+                                 reference shuffles it once, in sweep 0, _linear_multi.pyx:426) */
+    const double* u;          /* [chains][sweeps][nblock]        uniform of _weighted_choice (:71)  */
+    const double* z;          /* [chains][sweeps][nblock][bsize] normals of the drawn model (:768)  */
+    const double* invgamma;   /* [chains][sweeps]                                                    */
+    const double* p0_draw;    /* [chains][sweeps][nprop]                                             */
+    const double* gamma_draw; /* [chains][sweeps]                                                    */
+    int32_t nprop;
+} blipgpu_multi_streams;
+
+/* Replaces `apply_pool(_sample_spikeslab_multi, constant_inputs, N=[N+burn]*chains)`
+ * (pyblip/linear/linear.py:149-164, pyblip/probit/probit.py:79-94; kernel
+ * pyblip/linear/_linear_multi.pyx:271-292): all chains of this rank in one call.
+ * 2 <= bsize <= 8 (larger blocks are rejected with BLIPGPU_ERR_UNSUPPORTED);
+ * max_signals_per_block = 0 means no cap (:403-404).  A failed Cholesky factorisation
+ * (reference: RuntimeError "dpotrf exited with INFO=...") returns BLIPGPU_ERR_NUMERIC.
+ * Everything else as blipgpu_sample_spikeslab; the result is the same samples handle. */
+int blipgpu_sample_spikeslab_multi(blipgpu_ctx* ctx, blipgpu_design* design,
+                                   const blipgpu_spikeslab_config* cfg, int32_t bsize,
+                                   int32_t max_signals_per_block,
+                                   const double* y, const int64_t* z, int32_t probit,
+                                   int64_t chains, int64_t chain_offset,
+                                   int64_t n_keep, int64_t burn, uint64_t seed,
+                                   const blipgpu_multi_streams* streams,
+                                   const blipgpu_sample_options* opts,
+                                   blipgpu_samples** out);
+
 /* ---- neuronized-prior sampler ------------------------------------------ */
 /* Scalars of `_nprior_sample` (pyblip/nprior/_nprior.pyx:56-73). */
 typedef struct blipgpu_nprior_config {

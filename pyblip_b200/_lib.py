@@ -26,7 +26,7 @@ SYMBOLS = [
     "blipgpu_ctx_counters", "blipgpu_ctx_event_record", "blipgpu_ctx_event_elapsed_ms",
     "blipgpu_design_upload", "blipgpu_design_changepoint", "blipgpu_design_build_gram",
     "blipgpu_design_get_gram", "blipgpu_design_get_xl2", "blipgpu_design_free",
-    "blipgpu_sample_spikeslab",
+    "blipgpu_sample_spikeslab", "blipgpu_sample_spikeslab_multi",
     "blipgpu_sample_nprior", "blipgpu_nprior_get", "blipgpu_nprior_info", "blipgpu_nprior_bits",
     "blipgpu_nprior_free",
     "blipgpu_samples_info_get", "blipgpu_samples_hyper", "blipgpu_samples_dense",
@@ -55,6 +55,15 @@ class SpikeSlabConfig(C.Structure):
 class Streams(C.Structure):
     _fields_ = [
         ("perm", C.c_void_p), ("u", C.c_void_p), ("z", C.c_void_p),
+        ("invgamma", C.c_void_p), ("p0_draw", C.c_void_p), ("gamma_draw", C.c_void_p),
+        ("nprop", C.c_int32),
+    ]
+
+
+class MultiStreams(C.Structure):
+    """``blipgpu_multi_streams``: injected stream of the block sampler."""
+    _fields_ = [
+        ("blocks", C.c_void_p), ("u", C.c_void_p), ("z", C.c_void_p),
         ("invgamma", C.c_void_p), ("p0_draw", C.c_void_p), ("gamma_draw", C.c_void_p),
         ("nprop", C.c_int32),
     ]
@@ -116,6 +125,8 @@ def check(rc):
         raise ValueError(msg)
     if rc == ERR_UNSUPPORTED:
         raise NotImplementedError(msg)
+    if rc == ERR_NUMERIC:        # the reference raises RuntimeError (dpotrf) in the same situations
+        raise RuntimeError(msg)
     raise BlipGpuError(f"libblipgpu error {rc}: {msg}")
 
 
@@ -308,8 +319,13 @@ class Samples:
 
 def sample_spikeslab(design, cfg, y=None, z=None, probit=False, chains=1, chain_offset=0,
                      n_keep=1, burn=0, seed=0, streams=None, mode=MODE_AUTO, chunk_sweeps=0,
-                     keep_latents=True, gram_refresh=0):
-    """All chains of this rank in one call (``blipgpu_sample_spikeslab``)."""
+                     keep_latents=True, gram_refresh=0, bsize=1, max_signals_per_block=0):
+    """All chains of this rank in one call (``blipgpu_sample_spikeslab``, or
+    ``blipgpu_sample_spikeslab_multi`` when ``bsize > 1``)."""
+    if bsize > 1:
+        return _sample_spikeslab_multi(design, cfg, y, z, probit, chains, chain_offset, n_keep, burn,
+                                       seed, streams, mode, chunk_sweeps, keep_latents, gram_refresh,
+                                       bsize, max_signals_per_block)
     n, p = design.n, design.p
     n_total = n_keep + burn
     keep = []
@@ -348,6 +364,55 @@ def sample_spikeslab(design, cfg, y=None, z=None, probit=False, chains=1, chain_
     h = C.c_void_p()
     check(load().blipgpu_sample_spikeslab(
         design.ctx._h, design._h, C.byref(cfg), C.c_void_p(yptr), C.c_void_p(zptr),
+        C.c_int32(int(bool(probit))), C.c_int64(chains), C.c_int64(chain_offset),
+        C.c_int64(n_keep), C.c_int64(burn), C.c_uint64(seed), st_ptr, C.byref(opts), C.byref(h)))
+    del keep
+    return Samples(design.ctx, h)
+
+
+def _sample_spikeslab_multi(design, cfg, y, z, probit, chains, chain_offset, n_keep, burn, seed,
+                            streams, mode, chunk_sweeps, keep_latents, gram_refresh, bsize,
+                            max_signals_per_block):
+    n, p = design.n, design.p
+    n_total = n_keep + burn
+    nblock = (p + bsize - 1) // bsize
+    keep = []
+    if probit:
+        z = np.ascontiguousarray(z, dtype=np.int64)
+        if z.shape != (n,):
+            raise ValueError("z must have shape (n,)")
+        yptr, zptr = None, z.ctypes.data
+    else:
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        if y.shape != (n,):
+            raise ValueError("y must have shape (n,)")
+        yptr, zptr = y.ctypes.data, None
+    st_ptr = None
+    if streams:
+        blocks = _opt_array(streams.get("blocks"), np.int32, (chains, nblock, bsize))
+        u = _opt_array(streams.get("u"), np.float64, (chains, n_total, nblock))
+        zn = _opt_array(streams.get("z"), np.float64, (chains, n_total, nblock, bsize))
+        ig = _opt_array(streams.get("invgamma"), np.float64, (chains, n_total))
+        gd = _opt_array(streams.get("gamma_draw"), np.float64, (chains, n_total))
+        p0d = streams.get("p0_draw")
+        nprop = 1
+        if p0d is not None:
+            p0d = np.ascontiguousarray(p0d, dtype=np.float64)
+            if p0d.ndim == 2:
+                p0d = p0d[:, :, None]
+            if p0d.shape[:2] != (chains, n_total):
+                raise ValueError("p0_draw must have shape (chains, sweeps[, nprop])")
+            p0d = np.ascontiguousarray(p0d)
+            nprop = p0d.shape[2]
+        keep += [blocks, u, zn, ig, gd, p0d]
+        ptr = lambda a: None if a is None else a.ctypes.data  # noqa: E731
+        st = MultiStreams(ptr(blocks), ptr(u), ptr(zn), ptr(ig), ptr(p0d), ptr(gd), nprop)
+        st_ptr = C.byref(st)
+    opts = SampleOptions(int(mode), int(chunk_sweeps), int(bool(keep_latents)), int(gram_refresh))
+    h = C.c_void_p()
+    check(load().blipgpu_sample_spikeslab_multi(
+        design.ctx._h, design._h, C.byref(cfg), C.c_int32(int(bsize)),
+        C.c_int32(int(max_signals_per_block or 0)), C.c_void_p(yptr), C.c_void_p(zptr),
         C.c_int32(int(bool(probit))), C.c_int64(chains), C.c_int64(chain_offset),
         C.c_int64(n_keep), C.c_int64(burn), C.c_uint64(seed), st_ptr, C.byref(opts), C.byref(h)))
     del keep

@@ -11,6 +11,7 @@
 #include <new>
 #include <vector>
 #include "gibbs_kernels.cuh"
+#include "gibbs_block.cuh"
 
 namespace {
 
@@ -72,6 +73,37 @@ __global__ void init_state_kernel(SweepParams P, const double* __restrict__ y, i
     }
 }
 
+// block sampler: block table in the keyed visiting order (the reference shuffles the rows of the
+// partition once, in sweep 0: _linear_multi.pyx:395-402, 426), one thread per (chain, position)
+__global__ void block_table_kernel(int32_t* blocks, int chains, int nblock, int bsize, int p, uint32_t k0,
+                                   uint32_t k1, uint32_t chain_offset)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)chains * nblock) return;
+    const int c = (int)(t / nblock), bi = (int)(t % nblock);
+    const PermKey K = perm_key(k0, k1, chain_offset + (uint32_t)c, 0u, (uint32_t)nblock);
+    const int64_t b = perm_at(K, (uint32_t)bi, (uint32_t)nblock);
+    for (int k = 0; k < bsize; ++k) blocks[t * bsize + k] = (int32_t)((b * bsize + k) % p);
+}
+
+// block sampler: gb[b][a][a2] = X_ja . X_ja2 for the members of original block b (one CTA per block,
+// one warp per entry); replaces the XTX[j, j2] gathers of _precompute_suff_stats (:117-121)
+__global__ void block_gram_kernel(const double* __restrict__ XT, double* __restrict__ gb, int64_t n, int64_t p,
+                                  int64_t ldx, int bsize)
+{
+    const int64_t b = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    for (int e = warp; e < bsize * bsize; e += nwarp) {
+        const int64_t ja = (b * bsize + e / bsize) % p, jb = (b * bsize + e % bsize) % p;
+        const double* xa = XT + ja * ldx;
+        const double* xb = XT + jb * ldx;
+        double s = 0.0;
+        for (int64_t i = lane; i < n; i += 32) s = fma(xa[i], xb[i], s);
+        s = warp_sum(s);
+        if (lane == 0) gb[b * bsize * bsize + e] = s;
+    }
+}
+
 struct DevBuf {
     void* ptr = nullptr; size_t bytes = 0;
     int alloc(size_t b) {
@@ -122,12 +154,16 @@ int blip_xty(cudaStream_t st, const blipgpu_design* d, const double* d_y, double
     return BLIP_OK;
 }
 
-extern "C" int blipgpu_sample_spikeslab(blipgpu_ctx* ctx, blipgpu_design* design,
-                                        const blipgpu_spikeslab_config* cfg, const double* y,
-                                        const int64_t* z, int32_t probit, int64_t chains,
-                                        int64_t chain_offset, int64_t n_keep, int64_t burn,
-                                        uint64_t seed, const blipgpu_streams* streams,
-                                        const blipgpu_sample_options* opts, blipgpu_samples** out)
+// Shared implementation of the single-site (bsize == 1) and block (bsize > 1) samplers.  For the
+// block sampler `streams` carries the hyper-parameter variates and u / z with nblock resp.
+// nblock*bsize entries per sweep, and `blocks_host` the optional injected block table.
+static int sample_impl(blipgpu_ctx* ctx, blipgpu_design* design,
+                       const blipgpu_spikeslab_config* cfg, const double* y,
+                       const int64_t* z, int32_t probit, int64_t chains,
+                       int64_t chain_offset, int64_t n_keep, int64_t burn,
+                       uint64_t seed, const blipgpu_streams* streams,
+                       const blipgpu_sample_options* opts, blipgpu_samples** out,
+                       int bsize, int max_signals, const int32_t* blocks_host)
 {
     BLIP_TRY(blip_ctx_activate(ctx));
     if (!design || !cfg || !out || chains <= 0 || n_keep <= 0 || burn < 0) {
@@ -140,9 +176,42 @@ extern "C" int blipgpu_sample_spikeslab(blipgpu_ctx* ctx, blipgpu_design* design
     if (n_total >= (int64_t)1 << 31 || chains * n_keep >= (int64_t)1 << 40) {
         blip_set_error("sample_spikeslab: too many sweeps"); return BLIP_ERR_ARG;
     }
-    if (streams && (streams->u || streams->z) && !streams->perm) {
-        // allowed: injected u/z with keyed permutations
+    const bool block = bsize > 1;
+    const int64_t nblock = block ? (p + bsize - 1) / bsize : 0;     // _linear_multi.pyx:298 (C integer division)
+    std::vector<uint32_t> model_masks;
+    if (block) {
+        if (bsize > BK_MAXB || bsize > p) {
+            blip_set_error("sample_spikeslab_multi: bsize %d is not supported (2 <= bsize <= min(%d, p))", bsize, BK_MAXB);
+            return BLIP_ERR_UNSUPPORTED;
+        }
+        if (design->kind != BLIPGPU_DESIGN_DENSE) {
+            blip_set_error("sample_spikeslab_multi: the block sampler needs a dense design"); return BLIP_ERR_UNSUPPORTED;
+        }
+        const int cap = max_signals <= 0 ? bsize : std::min(max_signals, bsize);   // :403-404
+        for (int m = 1; m <= cap; ++m) {                            // itertools.combinations order (:405-409)
+            std::vector<int> idx((size_t)m);
+            for (int t = 0; t < m; ++t) idx[(size_t)t] = t;
+            for (;;) {
+                uint32_t mask = 0;
+                for (int t = 0; t < m; ++t) mask |= 1u << idx[(size_t)t];
+                model_masks.push_back(mask);
+                int t = m - 1;
+                while (t >= 0 && idx[(size_t)t] == bsize - m + t) --t;
+                if (t < 0) break;
+                idx[(size_t)t]++;
+                for (int q2 = t + 1; q2 < m; ++q2) idx[(size_t)q2] = idx[(size_t)q2 - 1] + 1;
+            }
+        }
+        if (blocks_host) {
+            for (int64_t i = 0; i < chains * nblock; ++i) {
+                const int32_t j0 = blocks_host[i * bsize];
+                bool ok = j0 >= 0 && j0 < p && j0 % bsize == 0;
+                for (int k = 1; ok && k < bsize; ++k) ok = blocks_host[i * bsize + k] == (int32_t)((j0 + k) % p);
+                if (!ok) { blip_set_error("sample_spikeslab_multi: injected block %lld is not bsize consecutive indices starting at a multiple of bsize", (long long)i); return BLIP_ERR_ARG; }
+            }
+        }
     }
+    const int nmodel = (int)model_masks.size() + 1;
     int mode = opts ? opts->mode : BLIPGPU_MODE_AUTO;
     if (mode == BLIPGPU_MODE_AUTO) {
         if (probit) mode = BLIPGPU_MODE_RESIDUAL;
@@ -153,6 +222,12 @@ extern "C" int blipgpu_sample_spikeslab(blipgpu_ctx* ctx, blipgpu_design* design
             const double gram_bytes = 8.0 * (double)p * (double)round_up(p, 4);
             mode = (design->G || gram_bytes < 0.5 * (double)free_b) ? BLIPGPU_MODE_GRAM : BLIPGPU_MODE_RESIDUAL;
         }
+    }
+    if (block && mode == BLIPGPU_MODE_GRAM && (!opts || opts->mode == BLIPGPU_MODE_AUTO)) {
+        // the block kernel keeps q in shared memory; fall back to the residual form if it cannot
+        const size_t need = sizeof(double) * ((size_t)round_up(p, 2) + (size_t)GB_NWARP * ((nmodel + 1) & ~1)) +
+                            sizeof(uint32_t) * (size_t)((p + 31) / 32);
+        if (need > ctx->smem_optin) mode = BLIPGPU_MODE_RESIDUAL;
     }
     if (probit && mode == BLIPGPU_MODE_GRAM) {
         blip_set_error("sample_spikeslab: probit needs residual mode (every change redraws all latents)");
@@ -170,7 +245,10 @@ extern "C" int blipgpu_sample_spikeslab(blipgpu_ctx* ctx, blipgpu_design* design
     // ---- shared memory budget -> kernel variant
     size_t smem = 0;
     bool qsmem = true;
-    if (gram) {
+    if (block) {
+        const size_t state = gram ? (size_t)p2 : (size_t)(probit ? 3 : 1) * n2;
+        smem = sizeof(double) * (state + (size_t)GB_NWARP * ((nmodel + 1) & ~1)) + sizeof(uint32_t) * words;
+    } else if (gram) {
         smem = sizeof(double) * p2 + sizeof(uint32_t) * words;
         if (smem > ctx->smem_optin) { qsmem = false; smem = sizeof(uint32_t) * words; }
     } else {
@@ -203,6 +281,7 @@ extern "C" int blipgpu_sample_spikeslab(blipgpu_ctx* ctx, blipgpu_design* design
         PS = std::min<int64_t>(S * mult, round_up(n_total, S));
     }
     const bool inj_u = streams && streams->u, inj_z = streams && streams->z;
+    const int64_t u_len = block ? nblock : p, z_len = block ? nblock * bsize : p;   // injected variates per sweep
     const bool inj_ig = streams && streams->invgamma, inj_p0 = streams && streams->p0_draw;
     const bool inj_g = streams && streams->gamma_draw;
     const int nprop = streams ? std::max(1, (int)streams->nprop) : 1;
@@ -237,15 +316,15 @@ extern "C" int blipgpu_sample_spikeslab(blipgpu_ctx* ctx, blipgpu_design* design
     if (!probit) BLIP_TRY(d_y.alloc(sizeof(double) * n));
     // gram mode evaluates the keyed visiting order inside the sweep kernel (chain-private scratch);
     // the other kernels read permutation buffers filled ahead of them on the second stream
-    const bool perm_in_kernel = gram && !inj_perm;
-    const bool gen_perms = !inj_perm && !perm_in_kernel;
+    const bool perm_in_kernel = gram && !inj_perm && !block;
+    const bool gen_perms = !inj_perm && !perm_in_kernel && !block;
     if (perm_in_kernel) BLIP_TRY(d_scrP.alloc(perm_elt * chains * p));
-    else {
+    else if (!block) {
         BLIP_TRY(d_perm[0].alloc(perm_elt * chains * PS * p));
         if (!inj_perm && n_total > S) BLIP_TRY(d_perm[1].alloc(perm_elt * chains * PS * p));
     }
-    if (inj_u) BLIP_TRY(d_u.alloc(sizeof(double) * chains * S * p));
-    if (inj_z) BLIP_TRY(d_zn.alloc(sizeof(double) * chains * S * p));
+    if (inj_u) BLIP_TRY(d_u.alloc(sizeof(double) * chains * S * u_len));
+    if (inj_z) BLIP_TRY(d_zn.alloc(sizeof(double) * chains * S * z_len));
     if (inj_ig) BLIP_TRY(d_ig.alloc(sizeof(double) * chains * S));
     if (inj_p0) BLIP_TRY(d_p0.alloc(sizeof(double) * chains * S * nprop));
     if (inj_g) BLIP_TRY(d_g.alloc(sizeof(double) * chains * S));
@@ -304,6 +383,27 @@ extern "C" int blipgpu_sample_spikeslab(blipgpu_ctx* ctx, blipgpu_design* design
     P.hyper_out = smp->hyper; P.latents = smp->latents;
     P.gram_refresh = opts && opts->gram_refresh > 0 ? opts->gram_refresh : (opts && opts->gram_refresh < 0 ? 0 : 128);
 
+    // ---- block sampler tables
+    DevBuf d_blocks, d_gb, d_masks, d_numerr;
+    BLIP_TRY(d_numerr.alloc(sizeof(int)));
+    CUDA_TRY(cudaMemsetAsync(d_numerr.ptr, 0, sizeof(int), ctx->stream));
+    P.numeric_err = d_numerr.as<int>();
+    if (block) {
+        BLIP_TRY(d_blocks.alloc(sizeof(int32_t) * chains * nblock * bsize));
+        BLIP_TRY(d_gb.alloc(sizeof(double) * nblock * bsize * bsize));
+        BLIP_TRY(d_masks.alloc(sizeof(uint32_t) * model_masks.size()));
+        CUDA_TRY(cudaMemcpyAsync(d_masks.ptr, model_masks.data(), d_masks.bytes, cudaMemcpyHostToDevice, ctx->stream));
+        if (blocks_host) CUDA_TRY(cudaMemcpyAsync(d_blocks.ptr, blocks_host, d_blocks.bytes, cudaMemcpyHostToDevice, ctx->stream));
+        else block_table_kernel<<<(unsigned)((chains * nblock + 255) / 256), 256, 0, ctx->stream>>>(
+                d_blocks.as<int32_t>(), (int)chains, (int)nblock, bsize, (int)p, P.k0, P.k1, P.chain_offset);
+        block_gram_kernel<<<(unsigned)nblock, 256, 0, ctx->stream>>>(design->XT, d_gb.as<double>(), n, p, design->ldx, bsize);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));       // model_masks / blocks_host are host temporaries
+        P.blocks = d_blocks.as<int32_t>(); P.gb = d_gb.as<double>(); P.model_masks = d_masks.as<uint32_t>();
+        P.bsize = bsize; P.nblock = (int)nblock; P.nmodel = nmodel;
+        ctx->kernel_launches += blocks_host ? 1 : 2;
+    }
+
     // ---- data upload and initial state
     double yy = 0.0;
     if (!probit) {
@@ -335,7 +435,9 @@ extern "C" int blipgpu_sample_spikeslab(blipgpu_ctx* ctx, blipgpu_design* design
 
     // ---- kernel selection
     void (*kern)(SweepParams) = nullptr;
-    if (!gram) kern = probit ? gibbs_residual_kernel<true> : gibbs_residual_kernel<false>;
+    if (block) kern = gram ? gibbs_block_kernel<true, false>
+                           : (probit ? gibbs_block_kernel<false, true> : gibbs_block_kernel<false, false>);
+    else if (!gram) kern = probit ? gibbs_residual_kernel<true> : gibbs_residual_kernel<false>;
     else if (design->kind == BLIPGPU_DESIGN_CHANGEPOINT)
         kern = qsmem ? gibbs_gram_kernel<BLIPGPU_DESIGN_CHANGEPOINT, true> : gibbs_gram_kernel<BLIPGPU_DESIGN_CHANGEPOINT, false>;
     else
@@ -344,7 +446,7 @@ extern "C" int blipgpu_sample_spikeslab(blipgpu_ctx* ctx, blipgpu_design* design
     // gram mode: persistent CTAs (as many as are resident at once) draw (chain, 8-sweep) items
     // from a queue; with q in global memory (huge p) a chain stays on one CTA for the launch.
     int resident = 0;
-    if (gram) {
+    if (gram && !block) {
         int per_sm = 0;
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, GB_BLOCK, smem));
         resident = std::max(1, per_sm) * ctx->sm_count;
@@ -403,8 +505,8 @@ extern "C" int blipgpu_sample_spikeslab(blipgpu_ctx* ctx, blipgpu_design* design
             if (pc + 1 < n_perm_chunks)
                 BLIP_TRY(gen_perm(buf ^ 1, pstart[(size_t)pc + 1], (int)(pstart[(size_t)pc + 2] - pstart[(size_t)pc + 1])));
         }
-        if (inj_u) BLIP_TRY(upload_chunk(d_u.as<double>(), streams->u, chains, n_total * p, sweep0 * p, (int64_t)Sc * p, st));
-        if (inj_z) BLIP_TRY(upload_chunk(d_zn.as<double>(), streams->z, chains, n_total * p, sweep0 * p, (int64_t)Sc * p, st));
+        if (inj_u) BLIP_TRY(upload_chunk(d_u.as<double>(), streams->u, chains, n_total * u_len, sweep0 * u_len, (int64_t)Sc * u_len, st));
+        if (inj_z) BLIP_TRY(upload_chunk(d_zn.as<double>(), streams->z, chains, n_total * z_len, sweep0 * z_len, (int64_t)Sc * z_len, st));
         if (inj_ig) BLIP_TRY(upload_chunk(d_ig.as<double>(), streams->invgamma, chains, n_total, sweep0, (int64_t)Sc, st));
         if (inj_p0) BLIP_TRY(upload_chunk(d_p0.as<double>(), streams->p0_draw, chains, n_total * nprop, sweep0 * nprop, (int64_t)Sc * nprop, st));
         if (inj_g) BLIP_TRY(upload_chunk(d_g.as<double>(), streams->gamma_draw, chains, n_total, sweep0, (int64_t)Sc, st));
@@ -442,7 +544,7 @@ extern "C" int blipgpu_sample_spikeslab(blipgpu_ctx* ctx, blipgpu_design* design
         BLIP_TRY(copy_state(true));
 
         for (int attempt = 0;; ++attempt) {
-            P.perm = perm_in_kernel ? nullptr : d_perm[buf].ptr; P.perm16 = perm16 ? 1 : 0;
+            P.perm = (perm_in_kernel || block) ? nullptr : d_perm[buf].ptr; P.perm16 = perm16 ? 1 : 0;
             P.perm_S = PSc; P.perm_s0 = !gen_perms ? 0 : (int)(sweep0 - pc_sweep0);
             P.u = d_u.as<double>(); P.z = d_zn.as<double>(); P.invgamma = d_ig.as<double>();
             P.p0_draw = d_p0.as<double>(); P.gamma_draw = d_g.as<double>();
@@ -450,7 +552,7 @@ extern "C" int blipgpu_sample_spikeslab(blipgpu_ctx* ctx, blipgpu_design* design
             P.values = smp->values; P.arena_cap = smp->arena_cap;
             CUDA_TRY(cudaMemsetAsync(d_ovf.ptr, 0, sizeof(int), st));
             unsigned grid = (unsigned)chains;
-            if (gram) {
+            if (gram && !block) {
                 // no more chains than resident CTAs: one CTA per chain, spread by the hardware
                 P.sub_sweeps = (sub_sweeps_opt > 0 && chains > resident) ? std::min(sub_sweeps_opt, Sc) : Sc;
                 const int64_t n_items = chains * ((Sc + P.sub_sweeps - 1) / P.sub_sweeps);
@@ -472,6 +574,14 @@ extern "C" int blipgpu_sample_spikeslab(blipgpu_ctx* ctx, blipgpu_design* design
             CUDA_TRY(cudaMemcpyAsync(&ovf, d_ovf.ptr, sizeof(int), cudaMemcpyDeviceToHost, st));
             CUDA_TRY(cudaMemcpyAsync(&used, smp->arena_used, sizeof(used), cudaMemcpyDeviceToHost, st));
             CUDA_TRY(cudaStreamSynchronize(st));
+            if (block) {
+                int nerr = 0;
+                CUDA_TRY(cudaMemcpy(&nerr, d_numerr.ptr, sizeof(int), cudaMemcpyDeviceToHost));
+                if (nerr) {
+                    blip_set_error("dpotrf exited with INFO != 0: a block model's matrix is not positive definite. Try setting bsize=1.");
+                    return BLIP_ERR_NUMERIC;
+                }
+            }
             if (!ovf) {
                 max_chunk_use = std::max<int64_t>(max_chunk_use, (int64_t)(used - used_before));
                 used_before = used;
@@ -514,4 +624,36 @@ extern "C" int blipgpu_sample_spikeslab(blipgpu_ctx* ctx, blipgpu_design* design
     guard.s = nullptr;
     *out = smp;
     return BLIP_OK;
+}
+
+extern "C" int blipgpu_sample_spikeslab(blipgpu_ctx* ctx, blipgpu_design* design,
+                                        const blipgpu_spikeslab_config* cfg, const double* y,
+                                        const int64_t* z, int32_t probit, int64_t chains,
+                                        int64_t chain_offset, int64_t n_keep, int64_t burn,
+                                        uint64_t seed, const blipgpu_streams* streams,
+                                        const blipgpu_sample_options* opts, blipgpu_samples** out)
+{
+    return sample_impl(ctx, design, cfg, y, z, probit, chains, chain_offset, n_keep, burn, seed, streams,
+                       opts, out, 1, 0, nullptr);
+}
+
+extern "C" int blipgpu_sample_spikeslab_multi(blipgpu_ctx* ctx, blipgpu_design* design,
+                                              const blipgpu_spikeslab_config* cfg, int32_t bsize,
+                                              int32_t max_signals_per_block, const double* y,
+                                              const int64_t* z, int32_t probit, int64_t chains,
+                                              int64_t chain_offset, int64_t n_keep, int64_t burn,
+                                              uint64_t seed, const blipgpu_multi_streams* streams,
+                                              const blipgpu_sample_options* opts, blipgpu_samples** out)
+{
+    if (bsize < 2) { blip_set_error("sample_spikeslab_multi: bsize must be at least 2 (use sample_spikeslab)"); return BLIP_ERR_ARG; }
+    blipgpu_streams st;
+    memset(&st, 0, sizeof(st));
+    st.nprop = 1;
+    if (streams) {
+        st.u = streams->u; st.z = streams->z; st.invgamma = streams->invgamma;
+        st.p0_draw = streams->p0_draw; st.gamma_draw = streams->gamma_draw; st.nprop = streams->nprop;
+    }
+    return sample_impl(ctx, design, cfg, y, z, probit, chains, chain_offset, n_keep, burn, seed,
+                       streams ? &st : nullptr, opts, out, bsize, max_signals_per_block,
+                       streams ? streams->blocks : nullptr);
 }

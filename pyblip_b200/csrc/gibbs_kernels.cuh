@@ -60,6 +60,11 @@ struct SweepParams {
     double* values; int64_t arena_cap; unsigned long long* arena_used; int* overflow;
     double* hyper_out; double* latents;
     int gram_refresh;
+    // block sampler (bsize > 1, gibbs_block.cuh)
+    const int32_t* blocks;     // [chains][nblock][bsize] block table in visiting order
+    const double* gb;          // [nblock][bsize*bsize]   X_B^T X_B of the original block b = first member / bsize
+    const uint32_t* model_masks; // [nmodel-1] member bit sets of the non-empty models, reference order
+    int bsize, nblock, nmodel; int* numeric_err;
     // gram mode work queue: items (chain, sub-chunk of sub_sweeps sweeps) handed out in order;
     // progress[c] = sub-chunks of chain c completed in this launch
     int* queue; int* progress; int n_chains, sub_sweeps;

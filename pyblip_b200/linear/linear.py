@@ -101,10 +101,8 @@ class _SpikeSlabBase:
             Sweep formulation; probit always uses "residual".
         """
         bsize = min(bsize, self.X.shape[1])        # linear.py:149
-        if bsize > 1:
-            from .linear_multi import sample_blocks
-            return sample_blocks(self, N=N, burn=burn, chains=chains, bsize=bsize,
-                                 max_signals_per_block=max_signals_per_block or 0, seed=seed)
+        # bsize > 1 runs the block sampler (_linear_multi.pyx); None means "no cap" (linear.py:152-155)
+        block_kw = dict(bsize=int(bsize), max_signals_per_block=int(max_signals_per_block or 0)) if bsize > 1 else {}
         if seed is None:
             seed = int(np.random.randint(0, 2 ** 62))
         rank, world = dist.world()
@@ -125,13 +123,13 @@ class _SpikeSlabBase:
             smp = _lib.sample_spikeslab(
                 design, self._config(), z=np.asarray(self.y).astype(np.int64), probit=True,
                 chains=c1 - c0, chain_offset=c0, n_keep=N, burn=burn, seed=seed,
-                streams=_streams, mode=mode_id, chunk_sweeps=chunk_sweeps)
+                streams=_streams, mode=mode_id, chunk_sweeps=chunk_sweeps, **block_kw)
         else:
             smp = _lib.sample_spikeslab(
                 design, self._config(), y=np.asarray(self.y, dtype=np.float64), probit=False,
                 chains=c1 - c0, chain_offset=c0, n_keep=N, burn=burn, seed=seed,
                 streams=_streams, mode=mode_id, chunk_sweeps=chunk_sweeps,
-                gram_refresh=gram_refresh)
+                gram_refresh=gram_refresh, **block_kw)
         self._samples = smp
         self.p0s, self.tau2s, self.sigma2s = smp.hyper()
 
