@@ -239,8 +239,8 @@ def workload_config(args, impl="b200"):
             "burn": args.burn if impl == "b200" else 0,
             "parallelism": f"chains sharded over {args.gpus} GPU(s), no data-path collective",
             "mode": args.mode if impl == "b200" else "cython",
-            "l2_policy": "no flush: X'X (0.8 GB) + permutations (0.65 GB) + chain state exceed the "
-                         "126 MB L2; hot Gram columns legitimately stay L2-resident as in a real run"}
+            "l2_policy": "no flush: X'X (0.8 GB) + chain state and scratch (0.2 GB) + the sample store exceed "
+                         "the 126 MB L2; hot Gram columns legitimately stay L2-resident as in a real run"}
 
 
 def main():
@@ -329,8 +329,14 @@ def main():
     else:
         peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
     achieved = alg_bytes / (sweep_ms * 1e-3) / 1e9
+    # DRAM traffic of one launch from the committed ncu --set full capture (same launch shape:
+    # all 512 chains x 32 sweeps on one GPU); null for any other shape
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath) and world == 1 and kernel in json.load(open(tpath)):
+        traffic = float(json.load(open(tpath))[kernel]["dram_bytes_per_launch"])
     roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "launches": n_launch,
                 "avg_launch_ms": sweep_ms / max(n_launch, 1),
                 "alg_bytes_per_launch": alg_bytes / max(n_launch, 1),

@@ -133,6 +133,10 @@ __global__ void __launch_bounds__(CT_BLOCK) count_sequential_kernel(
     const uint32_t* c1 = (w + 1 < words) ? bits + (int64_t)(w + 1) * N_pad : nullptr;
     const uint32_t* c2 = (MAXM > 32 && w + 2 < words) ? bits + (int64_t)(w + 2) * N_pad : nullptr;
 
+    // Column-major view of a 32-row tile: after the in-warp transpose lane c holds column c (bit r =
+    // row r), so "window (j, m) is all zero in row r" is bit r of  ~(col_j | ... | col_{j+m}); the
+    // neighbouring columns come from a per-warp shared-memory line and the OR is built incrementally.
+    __shared__ uint32_t s_cw[CT_NWARP][96];
     int cnt[MAXM];      // lane b: rows (of the slow tiles) where window (32w+b, m) is all zero
 #pragma unroll
     for (int m = 0; m < MAXM; ++m) cnt[m] = 0;
@@ -145,18 +149,18 @@ __global__ void __launch_bounds__(CT_BLOCK) count_sequential_kernel(
         const uint32_t mid = (live && c1) ? c1[r] : 0u;
         const uint32_t hi = (live && c2) ? c2[r] : 0u;
         if (!__any_sync(0xffffffffu, (lo | mid | hi) != 0u)) { zero_rows += 32; continue; }
-        uint32_t acc = lo;                                  // OR of bits j..j+m
+        __syncwarp();
+        uint32_t acc = warp_transpose32(lo);                // OR of columns j..j+m, one bit per row
+        s_cw[warp][32 + lane] = warp_transpose32(mid);
+        if (MAXM > 32) s_cw[warp][64 + lane] = warp_transpose32(hi);
+        s_cw[warp][lane] = acc;
+        __syncwarp();
+        cnt[0] += __popc(~acc);
 #pragma unroll
-        for (int m = 0; m < MAXM; ++m) {
+        for (int m = 1; m < MAXM; ++m) {
             if (m < max_size) {
-                if (m > 0) {
-                    uint32_t sh;
-                    if (m < 32) sh = __funnelshift_r(lo, mid, m);
-                    else if (m == 32) sh = mid;
-                    else sh = __funnelshift_r(mid, hi, m - 32);
-                    acc |= sh;
-                }
-                cnt[m] += __popc(warp_transpose32(~acc));
+                acc |= s_cw[warp][lane + m];
+                cnt[m] += __popc(~acc);
             }
         }
     }

@@ -14,6 +14,7 @@
 // Every sweep starts from fresh w (joint draw or the reference's fresh 0.1*N(0,1) row,
 // :100,132-140), so q and rr are rebuilt from X^T y at every sweep and never drift.
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -33,7 +34,7 @@ struct blipgpu_nprior {
 namespace {
 
 constexpr int NP_BLOCK = 256;
-constexpr int NP_AMAX = 512;       // largest active set handled by the joint-W Cholesky
+constexpr int NP_AMAX_MIN = 512;   // the joint-W Cholesky workspace holds at least this many active coordinates
 
 struct NPParams {
     const double* G; int64_t ldg; const double* Xl2; const double* q0; double yy;
@@ -44,9 +45,10 @@ struct NPParams {
     double *alpha, *w, *beta;      // [chains][p]
     double* q;                     // [chains][p2]
     double* hs;                    // [chains][4]: sigma2, alpha0, p0, rr
-    double* chol;                  // [chains][NP_AMAX*NP_AMAX]
-    double* vec;                   // [chains][3*NP_AMAX]
-    int* act;                      // [chains][NP_AMAX]
+    int amax;                      // capacity of the active-set workspace (<= p, sized from free memory)
+    double* chol;                  // [chains][amax*amax]
+    double* vec;                   // [chains][3*amax]
+    int* act;                      // [chains][amax]
     int* err;                      // 1: active set too large, 2: Cholesky failed
     // streams
     uint32_t k0, k1, chain_offset;
@@ -134,6 +136,7 @@ __global__ void __launch_bounds__(NP_BLOCK) nprior_kernel(NPParams P)
     double* w = P.w + (int64_t)c * p;
     double* beta = P.beta + (int64_t)c * p;
     double* q = P.q + (int64_t)c * p2;
+    const int NP_AMAX = P.amax;
     double* L = P.chol + (int64_t)c * NP_AMAX * NP_AMAX;
     double* vec = P.vec + (int64_t)c * 3 * NP_AMAX;
     int* act = P.act + (int64_t)c * NP_AMAX;
@@ -454,6 +457,15 @@ extern "C" int blipgpu_sample_nprior(blipgpu_ctx* ctx, blipgpu_design* design, c
     BLIP_TRY(d_alpha.alloc(sizeof(double) * chains * p)); BLIP_TRY(d_w.alloc(sizeof(double) * chains * p));
     BLIP_TRY(d_beta.alloc(sizeof(double) * chains * p)); BLIP_TRY(d_q.alloc(sizeof(double) * chains * p2));
     BLIP_TRY(d_hs.alloc(sizeof(double) * chains * 4));
+    // active-set workspace: as large as p if a quarter of the free memory (at most 16 GB) allows
+    int64_t NP_AMAX = p;
+    {
+        size_t free_b = 0, total_b = 0;
+        CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+        const double budget = std::min(0.25 * (double)free_b, 16.0e9);
+        const int64_t fit = (int64_t)std::sqrt(budget / (8.0 * (double)chains));
+        NP_AMAX = std::max<int64_t>(std::min<int64_t>(p, NP_AMAX_MIN), std::min<int64_t>(p, fit));
+    }
     BLIP_TRY(d_chol.alloc(sizeof(double) * chains * NP_AMAX * NP_AMAX));
     BLIP_TRY(d_vec.alloc(sizeof(double) * chains * 3 * NP_AMAX)); BLIP_TRY(d_act.alloc(sizeof(int) * chains * NP_AMAX));
     BLIP_TRY(d_err.alloc(sizeof(int))); BLIP_TRY(d_q0.alloc(sizeof(double) * p));
@@ -470,6 +482,7 @@ extern "C" int blipgpu_sample_nprior(blipgpu_ctx* ctx, blipgpu_design* design, c
     P.min_alpha0 = norm_quantile_apprx_hd(cfg->min_p0);
     P.sigma_a = n / 2.0 + cfg->sigma_a0 + (cfg->sigma_prior_type != 0 ? p / 2.0 : 0.0);
     P.alpha = d_alpha.as<double>(); P.w = d_w.as<double>(); P.beta = d_beta.as<double>(); P.q = d_q.as<double>();
+    P.amax = (int)NP_AMAX;
     P.hs = d_hs.as<double>(); P.chol = d_chol.as<double>(); P.vec = d_vec.as<double>(); P.act = d_act.as<int>();
     P.err = d_err.as<int>();
     P.k0 = (uint32_t)seed; P.k1 = (uint32_t)(seed >> 32); P.chain_offset = (uint32_t)chain_offset;
@@ -517,7 +530,7 @@ extern "C" int blipgpu_sample_nprior(blipgpu_ctx* ctx, blipgpu_design* design, c
         int err = 0;
         CUDA_TRY(cudaMemcpyAsync(&err, d_err.ptr, sizeof(int), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
-        if (err == 1) { blip_set_error("sample_nprior: more than %d active coordinates in the joint W draw", NP_AMAX); return BLIP_ERR_UNSUPPORTED; }
+        if (err == 1) { blip_set_error("sample_nprior: more than %lld active coordinates in the joint W draw (workspace sized from free memory)", (long long)NP_AMAX); return BLIP_ERR_UNSUPPORTED; }
         if (err == 2) { blip_set_error("sample_nprior: Cholesky of the active-set precision failed"); return BLIP_ERR_NUMERIC; }
     }
     CUDA_TRY(cudaStreamSynchronize(st));
