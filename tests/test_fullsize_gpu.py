@@ -66,7 +66,6 @@ def test_c2_gram_and_residual_agree_and_match_oracle(gpu):
     bits.close()
     # prefix against the oracle (chain 100, 6 sweeps)
     orc = go.sample_spikeslab(6, X, y=y, hp=go.hparams(), seed=77, chain=100)
-    dev = g["smp"].dense()[:0]   # burn=4: recorded rows start at sweep 4
     first = _sample(design, cfg, _lib.MODE_GRAM, y=y, chains=1, chain_offset=100, n_keep=6, burn=0, seed=77)
     dev = first["smp"].dense()
     assert np.array_equal(dev != 0, orc["betas"] != 0)

@@ -139,3 +139,26 @@ def test_block_oracle_partition_and_models():
         want = [sum(1 << j for j in comb) for m in range(1, (cap or bsize) + 1)
                 for comb in itertools.combinations(range(bsize), m)]
         assert list(go.multi_models(bsize, cap)) == want
+
+
+def test_keyed_permutation_is_statistically_uniform():
+    """The point-wise Feistel visiting order: every coordinate is equally likely at
+    every position, consecutive positions are not correlated, one fixed point per permutation on average."""
+    import scipy.stats as st
+    p, N = 500, 6000
+    P = np.stack([go.permutation(11, 3, s, p) for s in range(N)])
+    assert all(sorted(go.permutation(5, 0, 0, q)) == list(range(q)) for q in (1, 2, 3, 17, 1000, 70001))
+    pvals = []
+    for col in (0, 1, p // 2, p - 1):                       # coordinate at a fixed position
+        h = np.bincount(P[:, col], minlength=p)
+        pvals.append(st.chi2.sf(((h - N / p) ** 2 / (N / p)).sum(), p - 1))
+    inv = np.argsort(P, axis=1)
+    for j in (0, 7, p - 1):                                 # position of a fixed coordinate
+        h = np.bincount(inv[:, j], minlength=p)
+        pvals.append(st.chi2.sf(((h - N / p) ** 2 / (N / p)).sum(), p - 1))
+    assert min(pvals) > 1e-4, pvals
+    assert abs(np.corrcoef(P[:, 0], P[:, 1])[0, 1]) < 0.06
+    assert abs(np.corrcoef(P[:-1, 0], P[1:, 0])[0, 1]) < 0.06
+    adj = (np.abs(np.diff(P, axis=1)) == 1).mean()
+    assert abs(adj - 2 / p) < 0.15 * 2 / p
+    assert abs((P == np.arange(p)).sum(1).mean() - 1.0) < 0.08
