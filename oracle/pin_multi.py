@@ -202,5 +202,34 @@ def main():
         print(f"[pin-multi] {case[0]:16s} OK  " + "  ".join(f"{k}={v:.2e}" for k, v in worst.items()))
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--longrun" not in sys.argv:
     main()
+
+
+# ---------------------------------------------------------------------------
+# long-run posterior summaries of the reference's block sampler (native RNG), for the
+# "PIPs within 4 Monte-Carlo standard errors" gate:  python oracle/pin_multi.py --longrun
+# ---------------------------------------------------------------------------
+def longrun_reference():
+    ref_loader.load()
+    from pyblip.linear import _linear_multi as mod
+    rng = np.random.default_rng(4242)                       # same data as longrun_reference.npz (linear)
+    X, y, beta = make_data(rng, 100, 60, 5, rho=0.9, coef_scale=1.0)
+    chains, burn, N, bsize = 48, 300, 1200, 3
+    pips, means, p0m = [], [], []
+    for c in range(chains):
+        np.random.seed(700 + c)
+        r = mod._sample_spikeslab_multi(N=N + burn, bsize=bsize, X=X, y=y.copy(), z=np.zeros(1, dtype=np.int64),
+                                        probit=0, tau2=1.0, update_tau2=1, tau2_a0=2.0, tau2_b0=1.0, sigma2=1.0,
+                                        update_sigma2=1, sigma2_a0=2.0, sigma2_b0=1.0, p0=0.9, update_p0=1,
+                                        min_p0=0.0, p0_a0=1.0, p0_b0=1.0, max_signals_per_block=0)
+        b = r["betas"][burn:]
+        pips.append((b != 0).mean(0)); means.append(b.mean(0)); p0m.append(r["p0s"][burn:].mean())
+    out = dict(X=X, y=y, beta=beta, pips=np.array(pips), means=np.array(means), p0=np.array(p0m),
+               burn=np.int32(burn), N=np.int32(N), bsize=np.int32(bsize))
+    np.savez_compressed(os.path.join(GOLDEN, "longrun_multi_reference.npz"), **out)
+    print("[pin-multi] longrun: PIP range", out["pips"].mean(0).min(), out["pips"].mean(0).max())
+
+
+if __name__ == "__main__" and "--longrun" in sys.argv:
+    longrun_reference()

@@ -75,16 +75,18 @@ __host__ __device__ __forceinline__ uint4 philox4x32_10(uint32_t k0, uint32_t k1
 // half modulo its radix (multiply-shift range reduction, no division).  The reference
 // shuffles with NumPy's Fisher-Yates (pyblip/linear/_linear.pyx:132); any permutation law
 // gives a valid sampler, and parity runs inject the reference's own permutations.
-struct PermKey { uint32_t rk[6]; uint32_t a, b; };
+struct PermKey { uint32_t rk[6]; uint32_t a, b; float inv_b; };
 
 __host__ __device__ __forceinline__ PermKey perm_key(uint32_t k0, uint32_t k1, uint32_t chain,
                                                      uint32_t sweep, uint32_t p)
 {
     PermKey K;
-    uint32_t a = 1;
-    while ((uint64_t)a * a < (uint64_t)p) ++a;       // p <= 2^31: a <= 46341
+    uint32_t a = (uint32_t)sqrt((double)p);          // a = ceil(sqrt(p)); p <= 2^31: a <= 46341
+    while ((uint64_t)a * a < (uint64_t)p) ++a;
+    while (a > 1 && (uint64_t)(a - 1) * (a - 1) >= (uint64_t)p) --a;
     K.a = a;
     K.b = (p + a - 1) / a;
+    K.inv_b = 1.0f / (float)K.b;
     const uint4 x = philox4x32_10(k0, k1, 0u, sweep, chain, 2u << 24);
     const uint4 y = philox4x32_10(k0, k1, 1u, sweep, chain, 2u << 24);
     K.rk[0] = x.x; K.rk[1] = x.y; K.rk[2] = x.z; K.rk[3] = x.w; K.rk[4] = y.x; K.rk[5] = y.y;
@@ -104,7 +106,13 @@ __host__ __device__ __forceinline__ uint32_t perm_at(const PermKey& K, uint32_t 
 {
     uint32_t x = pos;
     do {
-        uint32_t L = x / K.b, R = x - L * K.b;        // L in [0,a), R in [0,b)
+        // L = x / b, R = x % b without an integer division: x < a*b < 2^31.5 but a float quotient is
+        // only good to a few units, so it is corrected (at most twice each way)
+        uint32_t L = (uint32_t)((float)x * K.inv_b);
+        if (L >= K.a) L = K.a - 1;
+        while ((uint64_t)L * K.b > x) --L;
+        while ((uint64_t)(L + 1) * K.b <= x) ++L;
+        uint32_t R = x - L * K.b;                     // L in [0,a), R in [0,b)
 #pragma unroll
         for (int r = 0; r < 6; r += 2) {
             L += perm_round(R, K.rk[r], K.a);     if (L >= K.a) L -= K.a;

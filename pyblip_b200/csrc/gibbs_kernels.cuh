@@ -446,7 +446,10 @@ struct GramBcast { double delta; };
 #define PH_DECL
 #define PH(i) do {} while (0)
 #endif
-constexpr int GB_AXU = 10;         // 16-byte Gram loads a thread keeps in flight
+#ifndef BLIP_GB_AXU
+#define BLIP_GB_AXU 10
+#endif
+constexpr int GB_AXU = BLIP_GB_AXU;    // 16-byte Gram loads a thread keeps in flight
 #ifndef BLIP_GB_PEND
 #define BLIP_GB_PEND 2
 #endif
@@ -506,7 +509,34 @@ __device__ __forceinline__ void gram_flush(const SweepParams& P, double* q, cons
     int pj[GB_PEND]; double pd[GB_PEND];
 #pragma unroll
     for (int k = 0; k < GB_PEND; ++k) { pj[k] = k < npend ? pj_s[k] : 0; pd[k] = k < npend ? pd_s[k] : 0.0; }
-    for (int k0 = 2 * threadIdx.x; k0 < p2; k0 += 2 * GB_BLOCK * GB_FLUSH_SLOTS) {
+    int k0 = 2 * threadIdx.x;
+    if (DESIGN == BLIPGPU_DESIGN_DENSE && npend == GB_PEND) {
+        // the common case, a full list on a stored Gram matrix: per-thread column pointers with
+        // immediate offsets and no bounds tests while every thread of the block is in range
+        const double2* col[GB_PEND];
+#pragma unroll
+        for (int k = 0; k < GB_PEND; ++k)
+            col[k] = reinterpret_cast<const double2*>(P.G + (int64_t)pj[k] * P.ldg) + threadIdx.x;
+        double2* qv = reinterpret_cast<double2*>(q) + threadIdx.x;
+        const int nfull = (p2 / 2) / GB_BLOCK;             // slots in which all 256 threads are in range
+        int slot = 0;
+        for (; slot + GB_FLUSH_SLOTS <= nfull; slot += GB_FLUSH_SLOTS) {
+            double2 g[GB_FLUSH_SLOTS][GB_PEND];
+#pragma unroll
+            for (int u = 0; u < GB_FLUSH_SLOTS; ++u)
+#pragma unroll
+                for (int k = 0; k < GB_PEND; ++k) g[u][k] = __ldg(col[k] + (slot + u) * GB_BLOCK);
+#pragma unroll
+            for (int u = 0; u < GB_FLUSH_SLOTS; ++u) {
+                double2 qq = qv[(slot + u) * GB_BLOCK];
+#pragma unroll
+                for (int k = 0; k < GB_PEND; ++k) { qq.x = fma(-pd[k], g[u][k].x, qq.x); qq.y = fma(-pd[k], g[u][k].y, qq.y); }
+                qv[(slot + u) * GB_BLOCK] = qq;
+            }
+        }
+        k0 += slot * 2 * GB_BLOCK;
+    }
+    for (; k0 < p2; k0 += 2 * GB_BLOCK * GB_FLUSH_SLOTS) {
         double2 g[GB_FLUSH_SLOTS][GB_PEND];
 #pragma unroll
         for (int u = 0; u < GB_FLUSH_SLOTS; ++u) {
@@ -569,7 +599,7 @@ __global__ void __maxnreg__(GB_GRAM_REGS) gibbs_gram_kernel(SweepParams P)
     extern __shared__ __align__(16) double sm[];
     __shared__ SweepShared sh;
     __shared__ GramBcast bc;
-    __shared__ unsigned flags[2][GB_NWARP];
+    __shared__ int s_first[3];                  // rotating slots: smallest changing offset of a window
     __shared__ int sj[GB_BLOCK];                // coordinate of the position each thread owns
     __shared__ int act_pos[GB_BLOCK];           // positions of the currently active coordinates
     __shared__ int act_n;
@@ -589,6 +619,8 @@ __global__ void __maxnreg__(GB_GRAM_REGS) gibbs_gram_kernel(SweepParams P)
     const int subs = (P.S + P.sub_sweeps - 1) / P.sub_sweeps;
     const int n_items = P.n_chains * subs;
     int parity = 0;
+    if (tid < 3) s_first[tid] = GB_BLOCK;
+    __syncthreads();
     PH_DECL
   for (;;) {
     if (tid == 0) s_item = atomicAdd(P.queue, 1);
@@ -714,7 +746,9 @@ __global__ void __maxnreg__(GB_GRAM_REGS) gibbs_gram_kernel(SweepParams P)
         // guard band below is 1e-4 relative.  Anything that reaches a coefficient or an
         // exact decision stays in fp64.
         int c_pos = -1, c_j = 0, n_j = 0, nn_j = 0, npend = 0;
-        bool c_act = false, c_pref = false;
+        bool c_act = false;
+        int n_def = 0;                    // pending changes still to be replayed into q_pos
+        double d_g[GB_PEND], d_d[GB_PEND];
         float f_A = 0.f, f_c1 = 0.f, f_L = 0.f, n_L = 0.f;
         double c_xl2 = 0.0, n_xl2 = 0.0, c_bold = 0.0;
         double2 c_zp = make_double2(0.0, 0.0);   // (sqrt(post_var) * z, post_var) of an active position
@@ -728,9 +762,12 @@ __global__ void __maxnreg__(GB_GRAM_REGS) gibbs_gram_kernel(SweepParams P)
             c_j = n_j;
             sj[tid] = n_j;
             const double gnow = jnow >= 0 ? gram_entry<DESIGN>(P, jnow, c_j) : 0.0;
-            double gp[GB_PEND];
+            // the pending changes are not in q yet: request their Gram entries now, apply them
+            // (replay) right before q_pos is next used, so that the loads are never waited for here
 #pragma unroll
-            for (int k = 0; k < GB_PEND; ++k) gp[k] = k < npend ? gram_entry<DESIGN>(P, pend_j[k], c_j) : 0.0;
+            for (int k = 0; k < GB_PEND; ++k)
+                if (k < npend) { d_g[k] = gram_entry<DESIGN>(P, pend_j[k], c_j); d_d[k] = pend_d[k]; }
+            n_def = npend;
             q_pos = q[c_j];
             c_xl2 = n_xl2;
             f_L = n_L;
@@ -744,20 +781,12 @@ __global__ void __maxnreg__(GB_GRAM_REGS) gibbs_gram_kernel(SweepParams P)
             const float xl2f = (float)c_xl2;
             f_A = f_logodds + 0.5f * __logf(1.0f + __fdividef(f_tau2 * xl2f, f_sigma2));
             f_c1 = __fdividef(f_ts, 2.0f * (f_sigma2 + f_tau2 * xl2f));
-#pragma unroll
-            for (int k = 0; k < GB_PEND; ++k) if (k < npend) q_pos = fma(-pend_d[k], gp[k], q_pos);
-            // A position that would change if it were decided now very likely changes when its turn
-            // comes (an active one certainly does): start moving its Gram column into L2 a window
-            // ahead, so that neither the gathers nor the flush of that change wait for HBM.
-#ifdef BLIP_FILL_PREFETCH
-            c_pref = c_act || !(f_A - f_c1 * (float)(q_pos * q_pos) > f_L);
-#else
-            c_pref = false;
-#endif
-            if (DESIGN == BLIPGPU_DESIGN_DENSE && c_pref)
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(P.G + (int64_t)c_j * P.ldg),
-                             "r"((unsigned)(p2 * sizeof(double))) : "memory");
             return gnow;
+        };
+        auto replay = [&]() {             // apply the deferred pending changes, oldest first
+#pragma unroll
+            for (int k = 0; k < GB_PEND; ++k) if (k < n_def) q_pos = fma(-d_d[k], d_g[k], q_pos);
+            n_def = 0;
         };
         if (tid < p) {
             n_j = perm_s[tid]; n_xl2 = P.Xl2[n_j]; n_L = __ldcg(Ls + tid);
@@ -779,6 +808,7 @@ __global__ void __maxnreg__(GB_GRAM_REGS) gibbs_gram_kernel(SweepParams P)
                     if (pos + GB_BLOCK < p) nn_j = perm_s[pos + GB_BLOCK];
                     fill(pos, -1);
                 }
+                replay();
                 XjTr = c_act ? q_pos + c_bold * c_xl2 : q_pos;      // X_j . (r + beta_j X_j)
                 const double x2c = (double)f_c1 * (XjTr * XjTr);
                 const double E = (double)f_A - x2c;
@@ -793,31 +823,25 @@ __global__ void __maxnreg__(GB_GRAM_REGS) gibbs_gram_kernel(SweepParams P)
                 }
                 change = c_act || !spike;
             }
+            // first changed position in window order (= smallest cyclic offset from pos0): every
+            // warp posts the smallest offset among its lanes with one shared-memory atomicMin
             const unsigned m = __ballot_sync(0xffffffffu, change);
-            if (lane == 0) flags[parity][warp] = m;
+            const int r = pos0 & (GB_BLOCK - 1);
+            if (m && lane == 0) {
+                int l;
+                if (warp == (r >> 5)) {                 // the warp that holds the window start: lanes
+                    const unsigned hi = m & (0xffffffffu << (r & 31));   // at/after it come first
+                    l = hi ? __ffs(hi) - 1 : __ffs(m) - 1;
+                } else l = __ffs(m) - 1;
+                atomicMin(&s_first[parity], (32 * warp + l - r) & (GB_BLOCK - 1));
+            }
             PH(2);
             __syncthreads();
             PH(3);
-            // first changed position in window order = first set bit at/after bit r, cyclically:
-            // lane i < 9 looks at the i-th word after the one that holds bit r
-            const int r = pos0 & (GB_BLOCK - 1);
-            int first = -1;
-            {
-                const int w0 = r >> 5, b0 = r & 31;
-                unsigned f = 0u;
-                if (lane <= GB_NWARP) {
-                    f = flags[parity][(w0 + lane) & (GB_NWARP - 1)];
-                    if (lane == 0) f &= (0xffffffffu << b0);
-                    else if (lane == GB_NWARP) f &= ~(0xffffffffu << b0);   // b0 == 0 -> empty
-                }
-                const unsigned nz = __ballot_sync(0xffffffffu, f != 0u);
-                if (nz) {
-                    const int i = __ffs(nz) - 1;
-                    const unsigned fi = __shfl_sync(0xffffffffu, f, i);
-                    first = ((32 * ((w0 + i) & (GB_NWARP - 1)) + __ffs(fi) - 1) - r) & (GB_BLOCK - 1);
-                }
-            }
-            parity ^= 1;
+            int first = s_first[parity];
+            if (first >= GB_BLOCK) first = -1;
+            if (tid == 0) s_first[parity == 0 ? 2 : parity - 1] = GB_BLOCK;   // slot of the window after next
+            parity = parity == 2 ? 0 : parity + 1;
             PH(4);
             if (first < 0) {                                  // the whole window was null
                 pos0 += GB_BLOCK;
@@ -849,7 +873,7 @@ __global__ void __maxnreg__(GB_GRAM_REGS) gibbs_gram_kernel(SweepParams P)
                 if (bnew != 0) mask_s[c_j >> 5] |= (1u << (c_j & 31));
                 else mask_s[c_j >> 5] &= ~(1u << (c_j & 31));
                 // a column that is not L2-resident is on its way by the time it is flushed
-                if (DESIGN == BLIPGPU_DESIGN_DENSE && !c_pref)
+                if (DESIGN == BLIPGPU_DESIGN_DENSE)
                     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(P.G + (int64_t)c_j * P.ldg),
                                  "r"((unsigned)(p2 * sizeof(double))) : "memory");
             }
@@ -863,6 +887,7 @@ __global__ void __maxnreg__(GB_GRAM_REGS) gibbs_gram_kernel(SweepParams P)
             PH(7);
             __syncthreads();
             PH(8);
+            replay();
             q_pos = fma(-bc.delta, gj, q_pos);
             ++npend;
             PH(9);
