@@ -130,3 +130,26 @@ def test_block_sampler_through_the_reference_api(gpu):
     assert pm.betas.shape == (400, p) and pm.Z.shape == (400, n)
     with pytest.raises(NotImplementedError):
         LinearSpikeSlab(X=X, y=y).sample(N=10, burn=0, chains=1, bsize=9)
+
+
+def test_block_longrun_pips_within_4_mc_standard_errors(gpu):
+    """Long-run posterior summaries of the device block sampler (bsize=3, keyed stream, both forms)
+    against the reference's `_sample_spikeslab_multi` run with its native RNG
+    (tests/golden/longrun_multi_reference.npz, written by oracle/pin_multi.py --longrun)."""
+    import os
+    from pyblip_b200 import LinearSpikeSlab
+    d = np.load(os.path.join(util.GOLDEN, "longrun_multi_reference.npz"))
+    burn, N, bsize = int(d["burn"]), int(d["N"]), int(d["bsize"])
+    chains = d["pips"].shape[0]
+
+    def gate(dev, ref, floor):
+        se = np.sqrt(dev.var(0, ddof=1) / dev.shape[0] + ref.var(0, ddof=1) / ref.shape[0])
+        return np.abs(dev.mean(0) - ref.mean(0)) <= 4 * np.maximum(se, floor)
+
+    for mode in ("gram", "residual"):
+        lm = LinearSpikeSlab(d["X"], d["y"])
+        lm.sample(N=N, burn=burn, chains=chains, bsize=bsize, seed=79, mode=mode)
+        b = lm.betas.reshape(chains, N, -1)
+        assert gate((b != 0).mean(1), d["pips"], 2e-3).all(), mode
+        assert gate(b.mean(1), d["means"], 2e-3).all(), mode
+        assert gate(lm.p0s.reshape(chains, N).mean(1, keepdims=True), d["p0"][:, None], 1e-3).all(), mode
