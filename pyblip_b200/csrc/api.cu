@@ -3,6 +3,10 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <algorithm>
+#include <cstring>
+#include <thread>
+#include <vector>
 #include "internal.cuh"
 
 static thread_local char g_err[1024] = "";
@@ -42,6 +46,51 @@ int blip_ctx_activate(blipgpu_ctx* ctx)
     return BLIP_OK;
 }
 
+int blip_d2h(blipgpu_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes)
+{
+    const size_t kChunk = (size_t)32 << 20;
+    if (bytes < 2 * kChunk) {                      // small: the driver's own staging is fine
+        CUDA_TRY(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        return BLIP_OK;
+    }
+    if (!ctx->pinned[0]) {
+        for (int i = 0; i < 4; ++i) {
+            CUDA_TRY(cudaHostAlloc(&ctx->pinned[i], kChunk, cudaHostAllocDefault));
+            CUDA_TRY(cudaEventCreateWithFlags(&ctx->pinned_ev[i], cudaEventDisableTiming));
+        }
+        ctx->pinned_bytes = kChunk;
+    }
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // the source is produced on the main stream
+    const size_t nchunk = (bytes + kChunk - 1) / kChunk;
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const unsigned nthread = std::min(8u, hw);
+    auto issue = [&](size_t c) -> cudaError_t {
+        const size_t off = c * kChunk, len = std::min(kChunk, bytes - off);
+        cudaError_t e = cudaMemcpyAsync(ctx->pinned[c & 3], (const char*)src_dev + off, len, cudaMemcpyDeviceToHost, ctx->stream2);
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->pinned_ev[c & 3], ctx->stream2);
+        return e;
+    };
+    for (size_t c = 0; c < std::min<size_t>(3, nchunk); ++c) CUDA_TRY(issue(c));
+    for (size_t c = 0; c < nchunk; ++c) {
+        if (c + 3 < nchunk) CUDA_TRY(issue(c + 3)); // buffer (c+3)&3 was drained in the previous iteration
+        CUDA_TRY(cudaEventSynchronize(ctx->pinned_ev[c & 3]));
+        const size_t off = c * kChunk, len = std::min(kChunk, bytes - off);
+        const char* src = (const char*)ctx->pinned[c & 3];
+        char* dst = (char*)dst_host + off;
+        const size_t part = ((len + nthread - 1) / nthread + 4095) & ~(size_t)4095;
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < nthread; ++t) {
+            const size_t a = (size_t)t * part;
+            if (a >= len) break;
+            th.emplace_back([=] { memcpy(dst + a, src + a, std::min(part, len - a)); });
+        }
+        memcpy(dst, src, std::min(part, len));
+        for (auto& t : th) t.join();
+    }
+    return BLIP_OK;
+}
+
 extern "C" int blipgpu_ctx_create(int device, blipgpu_ctx** out)
 {
     if (!out) { blip_set_error("out is NULL"); return BLIP_ERR_ARG; }
@@ -70,6 +119,8 @@ extern "C" int blipgpu_ctx_create(int device, blipgpu_ctx** out)
     ctx->sweep_launches = ctx->other_launches = 0;
     ctx->kernel_launches = ctx->h2d_bytes = ctx->d2h_bytes = 0;
     for (int i = 0; i < 8; ++i) CUDA_TRY(cudaEventCreate(&ctx->ev[i]));
+    for (int i = 0; i < 4; ++i) { ctx->pinned[i] = nullptr; ctx->pinned_ev[i] = nullptr; }
+    ctx->pinned_bytes = 0;
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
     *out = ctx;
@@ -85,6 +136,7 @@ extern "C" int blipgpu_ctx_destroy(blipgpu_ctx* ctx)
     cudaStreamDestroy(ctx->stream);
     cudaStreamDestroy(ctx->stream2);
     for (int i = 0; i < 8; ++i) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 4; ++i) { if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]); if (ctx->pinned_ev[i]) cudaEventDestroy(ctx->pinned_ev[i]); }
     delete ctx;
     return BLIP_OK;
 }

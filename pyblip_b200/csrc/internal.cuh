@@ -15,6 +15,8 @@ struct blipgpu_ctx {
     int64_t sweep_launches, other_launches;
     int64_t kernel_launches, h2d_bytes, d2h_bytes;
     cudaEvent_t ev[8];
+    // pinned bounce buffers of blip_d2h (allocated on first use)
+    void* pinned[4]; cudaEvent_t pinned_ev[4]; size_t pinned_bytes;
 };
 
 struct blipgpu_design {
@@ -55,6 +57,9 @@ struct blipgpu_bits {
 
 // helpers implemented in api.cu
 int blip_ctx_activate(blipgpu_ctx* ctx);
+// Large device -> pageable host copy: pipelined through pinned bounce buffers on ctx->stream2 and
+// scattered into the destination by several host threads (first-touch page faults in parallel).
+int blip_d2h(blipgpu_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
 // helpers implemented in gibbs.cu
 int blip_fill_perms(cudaStream_t st, void* buf, int perm16, int64_t chains, int S, int64_t p,
                     int64_t sweep0, uint32_t k0, uint32_t k1, uint32_t chain_offset);

@@ -148,10 +148,10 @@ extern "C" int blipgpu_samples_csr(blipgpu_samples* s, int64_t* indptr, int32_t*
     s->ctx->kernel_launches += 1;
     s->ctx->d2h_bytes += (int64_t)(sizeof(int32_t) + sizeof(double)) * total + (int64_t)sizeof(int32_t) * s->rows;
     s->ctx->h2d_bytes += (int64_t)sizeof(int64_t) * (s->rows + 1);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(indices, d_idx, sizeof(int32_t) * total, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(values, d_val, sizeof(double) * total, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) { blip_set_error("samples_csr: %s", cudaGetErrorString(e)); rc = BLIP_ERR_CUDA; }
+    if (rc == BLIP_OK) rc = blip_d2h(s->ctx, indices, d_idx, sizeof(int32_t) * total);
+    if (rc == BLIP_OK) rc = blip_d2h(s->ctx, values, d_val, sizeof(double) * total);
     cudaFree(d_indptr); cudaFree(d_idx); cudaFree(d_val);
     return rc;
 }
