@@ -225,7 +225,7 @@ static int sample_impl(blipgpu_ctx* ctx, blipgpu_design* design,
     }
     if (block && mode == BLIPGPU_MODE_GRAM && (!opts || opts->mode == BLIPGPU_MODE_AUTO)) {
         // the block kernel keeps q in shared memory; fall back to the residual form if it cannot
-        const size_t need = sizeof(double) * ((size_t)round_up(p, 2) + (size_t)GB_NWARP * ((nmodel + 1) & ~1)) +
+        const size_t need = sizeof(double) * ((size_t)round_up(p, 2) + (size_t)GB_NWARP * std::max(32, (nmodel + 1) & ~1)) +
                             sizeof(uint32_t) * (size_t)((p + 31) / 32);
         if (need > ctx->smem_optin) mode = BLIPGPU_MODE_RESIDUAL;
     }
@@ -247,7 +247,7 @@ static int sample_impl(blipgpu_ctx* ctx, blipgpu_design* design,
     bool qsmem = true;
     if (block) {
         const size_t state = gram ? (size_t)p2 : (size_t)(probit ? 3 : 1) * n2;
-        smem = sizeof(double) * (state + (size_t)GB_NWARP * ((nmodel + 1) & ~1)) + sizeof(uint32_t) * words;
+        smem = sizeof(double) * (state + (size_t)GB_NWARP * std::max(32, (nmodel + 1) & ~1)) + sizeof(uint32_t) * words;
     } else if (gram) {
         smem = sizeof(double) * p2 + sizeof(uint32_t) * words;
         if (smem > ctx->smem_optin) { qsmem = false; smem = sizeof(uint32_t) * words; }
@@ -401,6 +401,10 @@ static int sample_impl(blipgpu_ctx* ctx, blipgpu_design* design,
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));       // model_masks / blocks_host are host temporaries
         P.blocks = d_blocks.as<int32_t>(); P.gb = d_gb.as<double>(); P.model_masks = d_masks.as<uint32_t>();
         P.bsize = bsize; P.nblock = (int)nblock; P.nmodel = nmodel;
+        P.npad = 1; while (P.npad < nmodel) P.npad <<= 1;
+        // blocks a warp scores at once: one lane per model, limited by the per-warp scratch
+        // (64 doubles of Gram blocks, 16 of X_A^T r)
+        P.blocks_per_warp = P.npad <= 32 ? std::max(1, std::min({ 32 / P.npad, 64 / (bsize * bsize), 16 / bsize })) : 1;
         ctx->kernel_launches += blocks_host ? 1 : 2;
     }
 

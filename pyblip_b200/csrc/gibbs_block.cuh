@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(GB_BLOCK, 2) gibbs_block_kernel(SweepParams P)
     __shared__ SweepShared sh;
     __shared__ BlockShared bs;
     __shared__ double scratch[40];
-    __shared__ double w_x[GB_NWARP][BK_MAXB];
+    __shared__ double w_x[GB_NWARP][16];         // X_A^T r of the (up to 8) blocks a warp scores
     __shared__ double w_A[GB_NWARP][BK_MAXB * BK_MAXB];
 
     const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(GB_BLOCK, 2) gibbs_block_kernel(SweepParams P)
     double* y_s = PROBIT ? st_s + 2 * n2 : nullptr;
     double* q = GRAM ? st_s : nullptr;
     double* probs_all = st_s + state_len;                       // [GB_NWARP][nmodel_pad]
-    const int nmodel_pad = (P.nmodel + 1) & ~1;
+    const int nmodel_pad = max(32, (P.nmodel + 1) & ~1);
     double* probs = probs_all + warp * nmodel_pad;
     uint32_t* mask_s = (uint32_t*)(probs_all + GB_NWARP * nmodel_pad);
 
@@ -284,35 +284,100 @@ __global__ void __launch_bounds__(GB_BLOCK, 2) gibbs_block_kernel(SweepParams P)
         int pos0 = 0;
         while (pos0 < nblock) {
             ++n_windows;
-            // ---- speculative scoring: warp w looks at block pos0 + w
-            const int bi_w = pos0 + warp;
-            bool change = false, bad = false;
-            if (bi_w < nblock) {
-                const int j = lane < bsize ? blocks[bi_w * bsize + lane] : 0;
-                const bool act = lane < bsize && ((mask_s[j >> 5] >> (j & 31)) & 1u);
-                if (__any_sync(0xffffffffu, act)) change = true;       // must be zeroed: a certain change
-                else {
-                    const int j0 = __shfl_sync(0xffffffffu, j, 0);
+            // ---- speculative scoring.  A block needs one lane per model, so a warp scores
+            // G = 32 / npad blocks at once (npad = models per block rounded up to a power of two;
+            // bsize 3 -> 8 models -> 4 blocks per warp); beyond 32 models a warp takes one block
+            // and its lanes stride over the models.
+            const int npad = P.npad;
+            const int G = P.blocks_per_warp;                            // <= 32 / npad, bounded by the scratch
+            const int WB = GB_NWARP * G;                                // blocks per window
+            unsigned changed = 0u;                                      // bit g: block g of this warp changes
+            if (npad <= 32) {
+                const int grp = lane / npad, gl = lane - grp * npad;
+                const int bi_g = pos0 + warp * G + grp;
+                const bool valid = grp < G && bi_g < nblock;
+                const unsigned gmask = (npad == 32 ? 0xffffffffu : ((1u << npad) - 1u)) << (grp * npad);
+                const int j = (valid && gl < bsize) ? blocks[bi_g * bsize + gl] : 0;
+                const bool act = valid && gl < bsize && ((mask_s[j >> 5] >> (j & 31)) & 1u);
+                const unsigned actb = __ballot_sync(0xffffffffu, act);
+                const bool certain = (actb & gmask) != 0u;             // must be zeroed: a certain change
+                const bool score = valid && !certain;
+                const unsigned scoreb = __ballot_sync(0xffffffffu, score && gl == 0);
+                double* gx = w_x[warp] + grp * bsize;
+                double* gA = w_A[warp] + grp * bsize * bsize;
+                if (score) {
+                    const int j0 = __shfl_sync(gmask, j, grp * npad);
                     const double* gb = P.gb + (int64_t)(j0 / bsize) * bsize * bsize;
-                    for (int e = lane; e < bsize * bsize; e += 32) w_A[warp][e] = gb[e];
-                    for (int k = 0; k < bsize; ++k) {
-                        const int jk = __shfl_sync(0xffffffffu, j, k);
-                        const double d = GRAM ? q[jk] : warp_dot(jk);
-                        if (lane == 0) w_x[warp][k] = d;
-                    }
-                    __syncwarp();
-                    const double denom = block_score(P, w_A[warp], w_x[warp], tau2, sigma2, logp0, log1p0, probs, &bad);
-                    const double u = u_s ? u_s[bi_w] : rng_uniform(key, KIND_BLOCK, bi_w, sweep, 0);
-                    change = bad || !(0.0 + probs[0] / denom >= u);    // model 0 is drawn iff its share reaches u
+                    for (int e = gl; e < bsize * bsize; e += npad) gA[e] = gb[e];
+                    if (GRAM && gl < bsize) gx[gl] = q[j];
                 }
+                if (!GRAM) {                                            // dots need the whole warp
+                    for (int g = 0; g < G; ++g) {
+                        if (!((scoreb >> (g * npad)) & 1u)) continue;   // warp-uniform
+                        for (int k = 0; k < bsize; ++k) {
+                            const int jk = __shfl_sync(0xffffffffu, j, g * npad + k);
+                            const double d = warp_dot(jk);
+                            if (lane == 0) w_x[warp][g * bsize + k] = d;
+                        }
+                    }
+                }
+                __syncwarp();
+                double lp = 0.0;
+                bool fail = false;
+                if (score && gl < P.nmodel) {
+                    lp = gl == 0 ? bsize * logp0
+                                 : block_model_lp(P.model_masks[gl - 1], bsize, gA, gx, tau2, sigma2, logp0, log1p0);
+                    fail = lp != lp;
+                }
+                double mx = fmax(lp, 0.0);                              // max_log_prob starts at 0.0 (:62)
+                for (int o = npad >> 1; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                double* gp = probs + grp * npad;                        // 32 doubles per warp
+                if (score && gl < P.nmodel) gp[gl] = exp(lp - mx);
+                const unsigned failb = __ballot_sync(0xffffffffu, fail);
+                __syncwarp();
+                bool chg = false;
+                if (valid && gl == 0) {
+                    if (certain || (failb & gmask)) chg = true;
+                    else {
+                        double denom = 0.0;
+                        for (int mj = 0; mj < P.nmodel; ++mj) denom += gp[mj];
+                        const double u = u_s ? u_s[bi_g] : rng_uniform(key, KIND_BLOCK, bi_g, sweep, 0);
+                        chg = !(0.0 + gp[0] / denom >= u);              // model 0 is drawn iff its share reaches u
+                    }
+                }
+                const unsigned chgb = __ballot_sync(0xffffffffu, chg);
+                for (int g = 0; g < G; ++g) if ((chgb >> (g * npad)) & 1u) changed |= 1u << g;
+            } else {
+                const int bi_w = pos0 + warp;
+                bool change = false, bad = false;
+                if (bi_w < nblock) {
+                    const int j = lane < bsize ? blocks[bi_w * bsize + lane] : 0;
+                    const bool act = lane < bsize && ((mask_s[j >> 5] >> (j & 31)) & 1u);
+                    if (__any_sync(0xffffffffu, act)) change = true;
+                    else {
+                        const int j0 = __shfl_sync(0xffffffffu, j, 0);
+                        const double* gb = P.gb + (int64_t)(j0 / bsize) * bsize * bsize;
+                        for (int e = lane; e < bsize * bsize; e += 32) w_A[warp][e] = gb[e];
+                        for (int k = 0; k < bsize; ++k) {
+                            const int jk = __shfl_sync(0xffffffffu, j, k);
+                            const double d = GRAM ? q[jk] : warp_dot(jk);
+                            if (lane == 0) w_x[warp][k] = d;
+                        }
+                        __syncwarp();
+                        const double denom = block_score(P, w_A[warp], w_x[warp], tau2, sigma2, logp0, log1p0, probs, &bad);
+                        const double u = u_s ? u_s[bi_w] : rng_uniform(key, KIND_BLOCK, bi_w, sweep, 0);
+                        change = bad || !(0.0 + probs[0] / denom >= u);
+                    }
+                }
+                changed = change ? 1u : 0u;
             }
-            if (lane == 0) bs.flags[warp] = change ? 1u : 0u;
+            if (lane == 0) bs.flags[warp] = changed;
             __syncthreads();
             int first = -1;
 #pragma unroll
-            for (int w = GB_NWARP - 1; w >= 0; --w) if (bs.flags[w]) first = w;
+            for (int w = GB_NWARP - 1; w >= 0; --w) if (bs.flags[w]) first = w * G + __ffs(bs.flags[w]) - 1;
             __syncthreads();
-            if (first < 0) { pos0 += GB_NWARP; continue; }
+            if (first < 0) { pos0 += WB; continue; }
 
             // ---- apply block bi exactly like the reference
             ++n_changes;

@@ -64,7 +64,7 @@ struct SweepParams {
     const int32_t* blocks;     // [chains][nblock][bsize] block table in visiting order
     const double* gb;          // [nblock][bsize*bsize]   X_B^T X_B of the original block b = first member / bsize
     const uint32_t* model_masks; // [nmodel-1] member bit sets of the non-empty models, reference order
-    int bsize, nblock, nmodel; int* numeric_err;
+    int bsize, nblock, nmodel, npad, blocks_per_warp; int* numeric_err;   // npad: nmodel rounded up to a power of two
     // gram mode work queue: items (chain, sub-chunk of sub_sweeps sweeps) handed out in order;
     // progress[c] = sub-chunks of chain c completed in this launch
     int* queue; int* progress; int n_chains, sub_sweeps;
