@@ -8,7 +8,8 @@ spike-and-slab sampler (BASELINE.json metric) on N B200s.
     python bench.py --impl reference ...      # the reference's Cython sampler on the host cores
 
 Workload (BASELINE.json configs[1]): LinearSpikeSlab, n=1000,
-p=10000, AR(1) rho=0.95 design, 50 signals, 512 chains sharded over the ranks, default
+p=10000, AR(1) rho=0.95 design, 50 signals, 512 chains per rank (weak scaling: chains are
+independent units; `--scaling strong` splits one set of 512 chains over the ranks), default
 hyper-priors.  One step = one full sampler pass of `--sweeps` recorded sweeps after
 `--burn` burn-in sweeps for every chain -- by default the configuration's full job,
 N=5000 after 100 burn-in sweeps.  Rank 0 prints ONE JSON line.
@@ -230,10 +231,13 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, impl="b200"):
+def workload_config(args, impl="b200", chains=None):
     c = dict(CONFIG)
+    if chains is not None:
+        c["chains"] = chains
+    weak = chains is not None and chains != CONFIG["chains"]
     return {"workload": "LinearSpikeSlab n=1000 p=10000 AR1 rho=0.95, 512 chains "
-                        "(BASELINE.json configs[1])",
+                        "(BASELINE.json configs[1])" + (f" on every rank: {chains} chains in total (weak scaling)" if weak else ""),
             "n": c["n"], "p": c["p"], "chains": c["chains"], "signals": c["k"],
             "sweeps_per_step": (args.sweeps + args.burn) if impl == "b200" else args.ref_sweeps,
             "burn": args.burn if impl == "b200" else 0,
@@ -257,6 +261,10 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-clocks", action="store_true")
     ap.add_argument("--debug", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["strong", "weak"],
+                    help="weak (default): chains are independent units, every rank runs the configuration's 512 "
+                         "chains (global chain ids rank*512 ..), no data-path collective; strong: the same 512 "
+                         "chains are split over the ranks (64 per GPU at N=8: fewer chains than SMs)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -267,7 +275,7 @@ def main():
 
     X, y, _ = make_data()
     n, p = X.shape
-    chains = CONFIG["chains"]
+    chains = CONFIG["chains"] * (world if args.scaling == "weak" else 1)
     c0, c1 = bdist.shard_chains(chains, rank, world)
     nloc = c1 - c0
     ctx = _lib.Context.get(local_rank)
@@ -385,8 +393,8 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args), "clocks": clock_info, "e2e": e2e,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, chains=chains), "clocks": clock_info, "e2e": e2e,
             "gpu_launches": int(counters["kernel_launches"]),
             "roofline": roofline, "cpu_baseline": cpu,
         }
