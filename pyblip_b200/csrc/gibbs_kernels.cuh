@@ -757,10 +757,10 @@ __global__ void __maxnreg__(GB_GRAM_REGS) gibbs_gram_kernel(SweepParams P)
         const float f_ts = (float)ts;
         // needs n_j, n_xl2, n_L = perm / Xl2 / logit of `pos` (prefetched).  If jnow >= 0 a change
         // at coordinate jnow is being decided: its Gram entry for the new position is fetched too.
-        auto fill = [&](int pos, int jnow) -> double {
+        auto fill = [&](int pos, int jnow, bool publish = true) -> double {
             c_pos = pos;
             c_j = n_j;
-            sj[tid] = n_j;
+            if (publish) sj[tid] = n_j;   // (the owner of a change publishes after the barrier, see below)
             const double gnow = jnow >= 0 ? gram_entry<DESIGN>(P, jnow, c_j) : 0.0;
             // the pending changes are not in q yet: request their Gram entries now, apply them
             // (replay) right before q_pos is next used, so that the loads are never waited for here
@@ -881,12 +881,15 @@ __global__ void __maxnreg__(GB_GRAM_REGS) gibbs_gram_kernel(SweepParams P)
             // over the positions one window further (the owner after its draw, in the same
             // divergent pass as the other lanes of its warp).  The current change is not on the
             // pending list they replay yet; it reaches them through gj below like everybody else.
+            // The owner's slot of sj is the one everybody reads jstar from: it is rewritten only after
+            // the barrier, when all those reads are done.
             if (off <= first) {
-                if (pos + GB_BLOCK < p) gj = fill(pos + GB_BLOCK, jstar); else c_pos = -1;
+                if (pos + GB_BLOCK < p) gj = fill(pos + GB_BLOCK, jstar, off != first); else c_pos = -1;
             }
             PH(7);
             __syncthreads();
             PH(8);
+            if (off == first && c_pos >= 0) sj[tid] = c_j;
             replay();
             q_pos = fma(-bc.delta, gj, q_pos);
             ++npend;
