@@ -494,6 +494,7 @@ static int sample_impl(blipgpu_ctx* ctx, blipgpu_design* design,
     if (gen_perms) BLIP_TRY(gen_perm(0, 0, (int)(pstart[1] - pstart[0])));
     int64_t pc = 0;
     int64_t max_chunk_use = 0;
+    double max_per_sweep = 0.0;       // most values one kept sweep (all chains) has added to the arena
     unsigned long long used_before = 0;
     for (int64_t ch = 0; ch < nchunks; ++ch) {
         const int64_t sweep0 = ch * S;
@@ -517,11 +518,16 @@ static int sample_impl(blipgpu_ctx* ctx, blipgpu_design* design,
 
         // grow the value arena ahead of need (kept sweeps in this chunk only)
         const int64_t kept_in_chunk = std::max<int64_t>(0, std::min<int64_t>(sweep0 + Sc, n_total) - std::max<int64_t>(sweep0, burn));
-        int64_t need = std::max<int64_t>(2 * max_chunk_use, chains * kept_in_chunk * std::max<int64_t>(64, p / 16));
+        // Free space wanted before the launch: twice what a kept sweep has needed at most so far, or --
+        // while nothing has been recorded yet -- a generous guess (p/16 non-zeros per row).  A launch that
+        // still overflows is replayed below.
+        int64_t need = max_per_sweep > 0 ? (int64_t)(2.0 * max_per_sweep * (double)kept_in_chunk) + chains * 64
+                                         : chains * kept_in_chunk * std::max<int64_t>(64, p / 16);
         auto grow = [&](int64_t min_free) -> int {
             if (smp->arena_cap - (int64_t)used_before >= min_free) return BLIP_OK;
-            const int64_t remaining_chunks = nchunks - ch;
-            int64_t newcap = (int64_t)used_before + std::max<int64_t>(min_free, (int64_t)(1.25 * remaining_chunks * std::max<int64_t>(max_chunk_use, 1)));
+            // room for the rest of the run at the observed rate (+25 %), so that one growth is the norm
+            const int64_t remaining_kept = n_total - std::max<int64_t>(sweep0, burn);
+            int64_t newcap = (int64_t)used_before + std::max<int64_t>(min_free, (int64_t)(1.25 * max_per_sweep * (double)remaining_kept));
             double* nv = nullptr;
             cudaError_t e = cudaMalloc(&nv, sizeof(double) * newcap);
             if (e != cudaSuccess) { blip_set_error("sample_spikeslab: cannot grow the value arena to %lld doubles: %s", (long long)newcap, cudaGetErrorString(e)); return BLIP_ERR_NOMEM; }
@@ -529,6 +535,7 @@ static int sample_impl(blipgpu_ctx* ctx, blipgpu_design* design,
             CUDA_TRY(cudaStreamSynchronize(st));
             CUDA_TRY(cudaFree(smp->values));
             smp->values = nv; smp->arena_cap = newcap;
+            if (launch_log) fprintf(stderr, "[blipgpu] value arena grown to %lld doubles at sweep %lld\n", (long long)newcap, (long long)sweep0);
             return BLIP_OK;
         };
         BLIP_TRY(grow(need));
@@ -588,6 +595,7 @@ static int sample_impl(blipgpu_ctx* ctx, blipgpu_design* design,
             }
             if (!ovf) {
                 max_chunk_use = std::max<int64_t>(max_chunk_use, (int64_t)(used - used_before));
+                if (kept_in_chunk > 0) max_per_sweep = std::max(max_per_sweep, (double)(used - used_before) / (double)kept_in_chunk);
                 used_before = used;
                 break;
             }
@@ -598,6 +606,7 @@ static int sample_impl(blipgpu_ctx* ctx, blipgpu_design* design,
             BLIP_TRY(copy_state(false));
             CUDA_TRY(cudaStreamSynchronize(st));
             max_chunk_use = std::max<int64_t>(max_chunk_use, wanted);
+            if (kept_in_chunk > 0) max_per_sweep = std::max(max_per_sweep, (double)wanted / (double)kept_in_chunk);
             BLIP_TRY(grow(wanted + wanted / 4 + 1024));
         }
         if (gen_perms && sweep0 + Sc >= pc_end)
