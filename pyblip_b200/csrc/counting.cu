@@ -91,30 +91,71 @@ __global__ void unpack_kernel(const uint32_t* __restrict__ bits, int64_t N, int6
 }
 
 // ---- column counts -------------------------------------------------------
-// grid (words, chunks); each warp walks 32-row tiles of its chunk.
+// grid (words, chunks); each warp walks 32-row tiles of its chunk, lane = row.  A lane never
+// transposes its words: it adds them into a bit-sliced ("vertical") counter -- plane k holds bit
+// k of the 32 per-column counts -- with a carry-save adder tree over 16 words at a time
+// (Harley-Seal) and a ripple into the upper planes, ~4 logic instructions per word, so the kernel
+// streams.  Only the final planes are transposed (lane = column) and pop-counted.
+#define CSA(h, l, a, b, c) do { const uint32_t _u = (a) ^ (b); h = ((a) & (b)) | (_u & (c)); l = _u ^ (c); } while (0)
+constexpr int CC_PLANES = 20;      // upper planes: weights 16 .. 16 * 2^19 words per lane
 __global__ void __launch_bounds__(CT_BLOCK) count_columns_kernel(
     const uint32_t* __restrict__ bits, int64_t N, int64_t N_pad, int64_t p, int64_t rows_per_block,
     unsigned long long* __restrict__ counts)
 {
-    __shared__ int s_cnt[CT_NWARP][32];
+    __shared__ unsigned long long s_cnt[CT_NWARP][32];
     const int w = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t r_begin = (int64_t)blockIdx.y * rows_per_block;
     const int64_t r_end = min(N, r_begin + rows_per_block);
     const uint32_t* col = bits + (int64_t)w * N_pad;
-    int cnt = 0;
-    for (int64_t r0 = r_begin + 32 * warp; r0 < r_end; r0 += 32 * CT_NWARP) {
-        const int64_t r = r0 + lane;
-        uint32_t x = (r < r_end) ? col[r] : 0u;
-        if (__any_sync(0xffffffffu, x != 0u)) cnt += __popc(warp_transpose32(x));
+    uint32_t ones = 0u, twos = 0u, fours = 0u, eights = 0u, hi[CC_PLANES];
+#pragma unroll
+    for (int k = 0; k < CC_PLANES; ++k) hi[k] = 0u;
+    const int64_t step = 32 * CT_NWARP;
+    int64_t r = r_begin + 32 * warp + lane;
+    for (; r + 15 * step < r_end; r += 16 * step) {        // 16 live words
+        uint32_t x[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) x[i] = col[r + i * step];
+        uint32_t twosA, twosB, foursA, foursB, eightsA, eightsB, sixteens;
+        CSA(twosA, ones, ones, x[0], x[1]);    CSA(twosB, ones, ones, x[2], x[3]);
+        CSA(foursA, twos, twos, twosA, twosB);
+        CSA(twosA, ones, ones, x[4], x[5]);    CSA(twosB, ones, ones, x[6], x[7]);
+        CSA(foursB, twos, twos, twosA, twosB);
+        CSA(eightsA, fours, fours, foursA, foursB);
+        CSA(twosA, ones, ones, x[8], x[9]);    CSA(twosB, ones, ones, x[10], x[11]);
+        CSA(foursA, twos, twos, twosA, twosB);
+        CSA(twosA, ones, ones, x[12], x[13]);  CSA(twosB, ones, ones, x[14], x[15]);
+        CSA(foursB, twos, twos, twosA, twosB);
+        CSA(eightsB, fours, fours, foursA, foursB);
+        CSA(sixteens, eights, eights, eightsA, eightsB);
+        uint32_t carry = sixteens;                         // ripple into the planes of weight >= 16
+#pragma unroll
+        for (int k = 0; k < CC_PLANES; ++k) { const uint32_t t = hi[k] & carry; hi[k] ^= carry; carry = t; }
     }
-    s_cnt[warp][lane] = cnt;
+    for (; r < r_end; r += step) {                         // remaining words, one at a time
+        uint32_t carry = col[r], t;
+        t = ones & carry; ones ^= carry; carry = t;
+        t = twos & carry; twos ^= carry; carry = t;
+        t = fours & carry; fours ^= carry; carry = t;
+        t = eights & carry; eights ^= carry; carry = t;
+#pragma unroll
+        for (int k = 0; k < CC_PLANES; ++k) { t = hi[k] & carry; hi[k] ^= carry; carry = t; }
+    }
+    // per-column totals of this warp: transpose every plane (lane c <- column c), pop-count over rows
+    unsigned long long tot = (unsigned long long)__popc(warp_transpose32(ones)) +
+                             2ull * __popc(warp_transpose32(twos)) + 4ull * __popc(warp_transpose32(fours)) +
+                             8ull * __popc(warp_transpose32(eights));
+#pragma unroll
+    for (int k = 0; k < CC_PLANES; ++k)
+        if (__any_sync(0xffffffffu, hi[k] != 0u)) tot += ((unsigned long long)__popc(warp_transpose32(hi[k]))) << (4 + k);
+    s_cnt[warp][lane] = tot;
     __syncthreads();
     if (warp == 0) {
-        int t = 0;
+        unsigned long long t = 0;
 #pragma unroll
         for (int i = 0; i < CT_NWARP; ++i) t += s_cnt[i][lane];
         const int64_t j = 32LL * w + lane;
-        if (j < p && t) atomicAdd(counts + j, (unsigned long long)t);
+        if (j < p && t) atomicAdd(counts + j, t);
     }
 }
 
