@@ -41,7 +41,8 @@ typedef struct blipgpu_bits blipgpu_bits;       /* bit-packed indicator matrix  
 
 int blipgpu_abi_version(void);
 /* sizeof() of the ABI structs as compiled, for binding self-checks:
- * 0 spikeslab_config, 1 streams, 2 sample_options, 3 samples_info. */
+ * 0 spikeslab_config, 1 streams, 2 sample_options, 3 samples_info, 4 multi_streams,
+ * 5 nprior_config, 6 nprior_streams. */
 int blipgpu_sizeof(int which);
 const char* blipgpu_last_error(void);
 int blipgpu_device_count(int* count);

@@ -28,6 +28,9 @@ extern "C" int blipgpu_sizeof(int which)
         case 1: return (int)sizeof(blipgpu_streams);
         case 2: return (int)sizeof(blipgpu_sample_options);
         case 3: return (int)sizeof(blipgpu_samples_info);
+        case 4: return (int)sizeof(blipgpu_multi_streams);
+        case 5: return (int)sizeof(blipgpu_nprior_config);
+        case 6: return (int)sizeof(blipgpu_nprior_streams);
         default: return -1;
     }
 }

@@ -27,7 +27,8 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header_sizes():
     lib = _lib.load()
     for which, cls in enumerate([_lib.SpikeSlabConfig, _lib.Streams, _lib.SampleOptions,
-                                 _lib.SamplesInfo]):
+                                 _lib.SamplesInfo, _lib.MultiStreams, _lib.NPriorConfig,
+                                 _lib.NPriorStreams]):
         assert ctypes.sizeof(cls) == lib.blipgpu_sizeof(which), cls.__name__
     # 13 scalars of _sample_spikeslab: 10 doubles + 3 int32 (each padded to 8)
     assert ctypes.sizeof(_lib.SpikeSlabConfig) == 104
