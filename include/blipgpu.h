@@ -258,6 +258,11 @@ int blipgpu_count_sequential(blipgpu_bits* b, int32_t max_size, int64_t* zero_co
  * (create_groups.py:459, blip.py:270-275).  offsets/members are host arrays. */
 int blipgpu_count_groups(blipgpu_bits* b, const int64_t* offsets, const int64_t* members,
                          int64_t n_groups, int64_t* any_counts, int32_t out_is_device);
+/* pair_counts[a][b] = #rows with columns a and b both non-zero, layout [p][p], symmetric, the
+ * diagonal holds the column counts.  The integer content of `np.corrcoef(precorr.T)` in
+ * `_samples_dist_matrix` (create_groups.py:523-535): the correlation matrix follows from these
+ * counts and N exactly.  p <= 16384 (use blipgpu_bits_select_columns first). */
+int blipgpu_count_pairs(blipgpu_bits* b, int64_t* pair_counts, int32_t out_is_device);
 int blipgpu_bits_free(blipgpu_bits* b);
 
 /* ---- continuous-space candidate regions -------------------------------- */

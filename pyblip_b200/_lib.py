@@ -33,7 +33,7 @@ SYMBOLS = [
     "blipgpu_samples_csr", "blipgpu_samples_latents", "blipgpu_samples_free",
     "blipgpu_bits_from_samples", "blipgpu_bits_from_dense", "blipgpu_bits_shape",
     "blipgpu_bits_select_columns", "blipgpu_bits_to_dense",
-    "blipgpu_count_columns", "blipgpu_count_sequential", "blipgpu_count_groups",
+    "blipgpu_count_columns", "blipgpu_count_sequential", "blipgpu_count_groups", "blipgpu_count_pairs",
     "blipgpu_bits_free",
     "blipgpu_grid_count", "blipgpu_gridcounts_sizes", "blipgpu_gridcounts_get", "blipgpu_gridcounts_free",
 ]
@@ -511,6 +511,13 @@ class Bits:
             check(load().blipgpu_count_groups(self._h, C.c_void_p(offsets.ctypes.data),
                                               C.c_void_p(members.ctypes.data), C.c_int64(G),
                                               C.c_void_p(out.ctypes.data), C.c_int32(0)))
+        return out
+
+    def count_pairs(self):
+        """#rows in which both columns are non-zero, for every pair of columns (int64[p, p])."""
+        out = np.zeros((self.p, self.p), dtype=np.int64)
+        if self.p:
+            check(load().blipgpu_count_pairs(self._h, C.c_void_p(out.ctypes.data), C.c_int32(0)))
         return out
 
     def close(self):

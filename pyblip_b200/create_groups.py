@@ -86,6 +86,9 @@ class _DeviceSamples:
             return np.zeros(0, dtype=np.int64)
         return dist.allreduce_counts(self.bits.count_groups(groups))
 
+    def pair_counts(self):
+        return dist.allreduce_counts(self.bits.count_pairs())
+
     def to_dense(self):
         return self.bits.to_dense()
 
@@ -283,6 +286,33 @@ def _samples_dist_matrix(samples):
     return np.corrcoef(precorr.T) + 1
 
 
+# above this many indicator entries the correlation matrix comes from integer pair counts on the
+# device instead of a dense host copy (the reference's np.corrcoef needs 8 bytes per entry on the host)
+_DEVICE_CORR_MIN_ENTRIES = 50_000_000
+
+
+def _samples_dist_matrix_device(dev):
+    """The matrix of `_samples_dist_matrix` from exact integer counts: with the all-zero and the
+    all-one row appended (:527-533) there are N' = N + 2 rows, column sums c + 1 and co-occurrence
+    counts n11 + 1, and the Pearson correlation of two 0/1 columns is
+    (N' n11' - c_a' c_b') / sqrt((N' c_a' - c_a'^2)(N' c_b' - c_b'^2)).
+    All products stay below 2^53, so every entry is one correctly rounded expression of exact
+    integers (np.corrcoef's own result depends on BLAS summation order in the last bits)."""
+    n11 = dev.pair_counts().astype(np.float64) + 1.0
+    c = np.diag(n11).copy()                         # = column counts + 1
+    Np = float(dev.N + 2)
+    var = Np * c - c * c
+    corr = (Np * n11 - np.outer(c, c)) / np.sqrt(np.outer(var, var))
+    np.clip(corr, -1.0, 1.0, out=corr)              # np.corrcoef clips too
+    return corr + 1
+
+
+def _sample_dist_matrix_auto(dev):
+    if dev.N * dev.p >= _DEVICE_CORR_MIN_ENTRIES and dev.p <= 16384:
+        return _samples_dist_matrix_device(dev)
+    return _samples_dist_matrix(_gathered_dense(dev))
+
+
 def hierarchical_groups(
     samples,
     dist_matrix=None,
@@ -306,7 +336,7 @@ def hierarchical_groups(
             pep = 1 - dev.column_counts()[0] / dev.N
             return [CandidateGroup(group=set([0]), pep=pep)]
         if dist_matrix is None:
-            dist_matrix = _samples_dist_matrix(_gathered_dense(dev))
+            dist_matrix = _sample_dist_matrix_auto(dev)
         groups = _dist_matrices_to_groups(dist_matrix, **kwargs)
 
         kept = []
@@ -373,7 +403,7 @@ def all_cand_groups(
             try:
                 cgs = sequential_groups(sub, q=q, max_pep=max_pep, max_size=max_size,
                                         prenarrow=prenarrow)
-                dms = [_samples_dist_matrix(_gathered_dense(sub))]
+                dms = [_sample_dist_matrix_auto(sub)]
                 if X is not None:
                     dms.append(np.abs(1 - np.corrcoef(X[:, rel_features].T)))
                 cgs.extend(hierarchical_groups(sub, dist_matrix=dms, max_pep=max_pep,

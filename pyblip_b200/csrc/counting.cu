@@ -253,6 +253,55 @@ __global__ void __launch_bounds__(CT_BLOCK) count_groups_kernel(
     }
 }
 
+// ---- pair (co-occurrence) counts -----------------------------------------
+// pair_counts[a][b] = #rows with columns a and b both non-zero: the integer content of the
+// reference's np.corrcoef(samples) (create_groups.py:523-535).  grid (word pairs wa <= wb, chunks);
+// a warp transposes a 32-row tile of both words (lane = column) and walks the 32 cyclic diagonals,
+// so lane a accumulates the pairs (a, a+s mod 32) without any broadcast.
+__global__ void __launch_bounds__(CT_BLOCK) count_pairs_kernel(
+    const uint32_t* __restrict__ bits, int64_t N, int64_t N_pad, int64_t p, int words,
+    int64_t rows_per_block, unsigned long long* __restrict__ pair_counts)
+{
+    __shared__ int s_cnt[32][33];
+    // unrank the word pair (wa <= wb) from blockIdx.x
+    int wa = 0, rem = blockIdx.x;
+    while (rem >= words - wa) { rem -= words - wa; ++wa; }
+    const int wb = wa + rem;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t r_begin = (int64_t)blockIdx.y * rows_per_block;
+    const int64_t r_end = min(N, r_begin + rows_per_block);
+    const uint32_t* ca = bits + (int64_t)wa * N_pad;
+    const uint32_t* cb = bits + (int64_t)wb * N_pad;
+    int cnt[32];
+#pragma unroll
+    for (int s = 0; s < 32; ++s) cnt[s] = 0;
+    for (int64_t r0 = r_begin + 32 * warp; r0 < r_end; r0 += 32 * CT_NWARP) {
+        const int64_t r = r0 + lane;
+        const uint32_t xa = r < r_end ? ca[r] : 0u;
+        const uint32_t xb = r < r_end ? cb[r] : 0u;
+        if (!__any_sync(0xffffffffu, xa != 0u) || !__any_sync(0xffffffffu, xb != 0u)) continue;
+        const uint32_t ta = warp_transpose32(xa);
+        const uint32_t tb = wa == wb ? ta : warp_transpose32(xb);
+#pragma unroll
+        for (int s = 0; s < 32; ++s) cnt[s] += __popc(ta & __shfl_sync(0xffffffffu, tb, (lane + s) & 31));
+    }
+    // block reduction through shared memory: s_cnt[a][b]
+    for (int e = threadIdx.x; e < 32 * 33; e += CT_BLOCK) (&s_cnt[0][0])[e] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < 32; ++s) if (cnt[s]) atomicAdd(&s_cnt[lane][(lane + s) & 31], cnt[s]);
+    __syncthreads();
+    for (int e = threadIdx.x; e < 1024; e += CT_BLOCK) {
+        const int a = e >> 5, b = e & 31;
+        const int64_t ja = 32LL * wa + a, jb = 32LL * wb + b;
+        const int v = s_cnt[a][b];
+        if (v && ja < p && jb < p) {
+            atomicAdd(pair_counts + ja * p + jb, (unsigned long long)v);
+            if (wa != wb) atomicAdd(pair_counts + jb * p + ja, (unsigned long long)v);
+        }
+    }
+}
+
 int alloc_bits(blipgpu_ctx* ctx, int64_t N, int64_t p, blipgpu_bits** out)
 {
     blipgpu_bits* b = new (std::nothrow) blipgpu_bits();
@@ -441,6 +490,21 @@ extern "C" int blipgpu_count_sequential(blipgpu_bits* b, int32_t max_size, int64
             count_sequential_kernel<32><<<grid, CT_BLOCK, 0, b->ctx->stream>>>(b->bits, b->N, b->N_pad, b->p, (int)b->words, max_size, rpb, dev);
         else
             count_sequential_kernel<64><<<grid, CT_BLOCK, 0, b->ctx->stream>>>(b->bits, b->N, b->N_pad, b->p, (int)b->words, max_size, rpb, dev);
+    });
+}
+
+extern "C" int blipgpu_count_pairs(blipgpu_bits* b, int64_t* pair_counts, int32_t out_is_device)
+{
+    if (!b || !pair_counts) { blip_set_error("count_pairs: bad arguments"); return BLIP_ERR_ARG; }
+    BLIP_TRY(blip_ctx_activate(b->ctx));
+    if (b->p > 16384) { blip_set_error("count_pairs: at most 16384 columns (select the relevant ones first)"); return BLIP_ERR_UNSUPPORTED; }
+    const int64_t npair = b->words * (b->words + 1) / 2;
+    const int64_t rpb = pick_rows_per_block(b->N, npair, b->ctx->sm_count);
+    const unsigned chunks = (unsigned)std::max<int64_t>(1, (b->N + rpb - 1) / rpb);
+    return with_output(b->ctx, b->p * b->p, pair_counts, out_is_device, [&](unsigned long long* dev) {
+        if (b->N == 0 || b->p == 0) return;
+        count_pairs_kernel<<<dim3((unsigned)npair, chunks), CT_BLOCK, 0, b->ctx->stream>>>(
+            b->bits, b->N, b->N_pad, b->p, (int)b->words, rpb, dev);
     });
 }
 

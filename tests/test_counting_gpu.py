@@ -91,3 +91,49 @@ def test_sampler_handle_counting_equals_dense_path(gpu):
     dense[:, 0] = 0
     c2 = util.cg_list(cg.sequential_groups(dense, max_pep=0.9))
     assert c1 == c2
+
+
+def test_pair_counts_and_device_correlation_path(gpu, monkeypatch):
+    """Co-occurrence counts on the device equal S^T S; the correlation matrix built from the exact
+    integers equals np.corrcoef of the reference's `_samples_dist_matrix` to rounding; groups proposed
+    through the device path carry bit-exact PEPs."""
+    from pyblip_b200 import _lib, create_groups as cg
+    rng = np.random.default_rng(11)
+    for N, p in [(1, 1), (33, 5), (5000, 70), (40013, 131)]:
+        S = rng.random((N, p)) < 0.05
+        if p > 3:
+            S[:, 2] = True
+            S[:, 3] = False
+        bits = _lib.Bits.from_dense(S)
+        pc = bits.count_pairs()
+        bits.close()
+        Si = S.astype(np.int64)
+        assert np.array_equal(pc, Si.T @ Si), (N, p)
+    S = rng.random((3000, 40)) < 0.1
+    S[:, 5] = S[:, 4]                                 # identical columns: exact tie
+    dev = cg._as_device(S)
+    d_dev = cg._samples_dist_matrix_device(dev)
+    d_host = cg._samples_dist_matrix(S)
+    dev.close()
+    assert np.max(np.abs(d_dev - d_host)) < 1e-12
+    # The trees built from the two matrices need not be the same: np.corrcoef's rounding noise breaks
+    # the exact ties of sparse indicator columns one way, exact integers leave them tied (scipy then
+    # takes the first pair).  The default therefore keeps the host path wherever the reference itself
+    # can run (parity), and the device path above _DEVICE_CORR_MIN_ENTRIES must give VALID groups:
+    # PEPs bit-exact for the groups it proposes, size and PEP limits respected.
+    monkeypatch.setattr(cg, "_DEVICE_CORR_MIN_ENTRIES", 0)      # force the device path
+    for name in util.COUNTING_CASES:
+        samples = util.load_counting_case(name)["samples"]
+        ind = samples != 0
+        groups = cg.hierarchical_groups(samples.copy(), max_pep=0.5, max_size=10)
+        assert len(groups) > 0 or ind.shape[1] < 2
+        for g in groups:
+            cols = sorted(g.group)
+            assert len(cols) <= 10 and g.pep < 0.5
+            assert g.pep == 1 - ind[:, cols].any(axis=1).sum() / ind.shape[0]
+        both = cg.all_cand_groups(samples.copy(), max_pep=0.5, max_size=10)
+        for g in both:
+            cols = sorted(g.group)
+            cnt, N = ind[:, cols].any(axis=1).sum(), ind.shape[0]
+            # hierarchical groups: 1 - mean(any) (:459); sequential groups: mean(all zero) (:329-332)
+            assert g.pep in (1 - cnt / N, (N - cnt) / N)

@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from pyblip_b200 import ProbitSpikeSlab, LinearSpikeSlab, changepoint, create_groups  # noqa: E402
 
-which = set(sys.argv[1:]) or {"c3", "c4", "c5"}
+which = set(sys.argv[1:]) or {"c2", "c3", "c4", "c5"}
 
 
 def ar1(rng, n, p, rho):
@@ -33,6 +33,24 @@ def report(name, chains, p, sweeps, wall, lm, extra=""):
           f"sweep kernels {i.sweep_ms / 1e3:.2f} s) = {chains * p * sweeps / wall:.3e} coordinate updates/s; "
           f"changes/chain-sweep {i.n_changes / i.n_sweeps_total:.1f}; nnz/row {i.nnz / i.rows:.1f} {extra}", flush=True)
 
+
+if "c2" in which:      # bench workload, then all_cand_groups on the device samples
+    import bench
+    X, y, beta = bench.make_data()
+    lm = LinearSpikeSlab(X, y)
+    t0 = time.perf_counter()
+    lm.sample(N=5000, burn=100, chains=512, seed=1)
+    wall = time.perf_counter() - t0
+    report("C2 linear n=1000 p=10000", 512, 10000, 5100, wall, lm)
+    t0 = time.perf_counter()
+    groups = create_groups.all_cand_groups(lm.samples_handle, X=None, q=0.1,
+                                           prefilter_thresholds=[0.01, 0.02, 0.03, 0.05, 0.1, 0.2])
+    dt = time.perf_counter() - t0
+    true = set(np.flatnonzero(beta).tolist())
+    hit = sum(1 for j in true if any(j in g.group for g in groups))
+    print(f"   all_cand_groups on 2 560 000 x 10 000 device indicators (thresholds 0.01..0.2; correlation from device "
+          f"pair counts): {len(groups)} groups in {dt:.2f} s; {hit}/{len(true)} true signals covered", flush=True)
+    lm._release(); lm._design.close()
 
 if "c3" in which:      # probit n=2000 p=5000, N=2000, 256 chains
     rng = np.random.default_rng(1003)
