@@ -122,11 +122,118 @@ __device__ inline NPVisit np_visit(const NPParams& P, const RngKey& key, int pos
     return v;
 }
 
+// In-place lower Cholesky of the A x A matrix L (row-major, lower triangle valid) by one CTA,
+// right-looking with 32-wide panels: the panel is factored / solved against a 32 x 32 diagonal
+// block held in shared memory, and the trailing matrix is updated tile by tile (64 x 64 tiles,
+// 4 x 4 outputs per thread, both panel strips in shared memory), so that the trailing matrix is
+// read and written once per PANEL instead of once per column.  Used for large active sets, where
+// the column-by-column version streams A^3/6 elements through L2.
+constexpr int NPC_NB = 32, NPC_T = 64;
+struct NpCholSmem { double D[NPC_NB][NPC_NB + 1]; double Pr[NPC_T][NPC_NB + 1]; double Pc[NPC_T][NPC_NB + 1]; };
+
+__device__ inline void np_cholesky_blocked(double* L, int A, int* err, NpCholSmem* sm)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int kb = 0; kb < A; kb += NPC_NB) {
+        const int nb = min(NPC_NB, A - kb);
+        // (1) diagonal block: load, factor (warp 0, lane = row), store
+        for (int e = tid; e < nb * nb; e += NP_BLOCK) {
+            const int r = e / nb, c2 = e % nb;
+            sm->D[r][c2] = c2 <= r ? L[(int64_t)(kb + r) * A + kb + c2] : 0.0;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            for (int k = 0; k < nb; ++k) {
+                const double dk = sm->D[k][k];
+                if (lane == 0 && !(dk > 0)) *err = 2;
+                const double d = sqrt(dk);
+                __syncwarp();
+                if (lane == k) sm->D[k][k] = d;
+                if (lane > k && lane < nb) sm->D[lane][k] /= d;
+                __syncwarp();
+                if (lane > k && lane < nb) {
+                    const double lrk = sm->D[lane][k];
+                    for (int c2 = k + 1; c2 <= lane; ++c2) sm->D[lane][c2] -= lrk * sm->D[c2][k];
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        for (int e = tid; e < nb * nb; e += NP_BLOCK) {
+            const int r = e / nb, c2 = e % nb;
+            if (c2 <= r) L[(int64_t)(kb + r) * A + kb + c2] = sm->D[r][c2];
+        }
+        // (2) panel below the block: row r of the panel solves x D^T = a (one thread per row)
+        const int r0 = kb + nb;
+        for (int r = r0 + tid; r < A; r += NP_BLOCK) {
+            double* row = L + (int64_t)r * A + kb;
+            double x[NPC_NB];
+#pragma unroll
+            for (int j = 0; j < NPC_NB; ++j) x[j] = j < nb ? row[j] : 0.0;
+#pragma unroll
+            for (int j = 0; j < NPC_NB; ++j) {
+                if (j < nb) {
+                    double sacc = x[j];
+#pragma unroll
+                    for (int i = 0; i < NPC_NB; ++i) if (i < j) sacc -= x[i] * sm->D[j][i];
+                    x[j] = sacc / sm->D[j][j];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < NPC_NB; ++j) if (j < nb) row[j] = x[j];
+        }
+        __syncthreads();
+        // (3) trailing update L[r][c] -= sum_j P[r][j] P[c][j], r >= c >= r0, 64 x 64 tiles
+        const int tr = (tid >> 4) * 4, tc = (tid & 15) * 4;          // this thread's 4 x 4 outputs in a tile
+        for (int rb = r0; rb < A; rb += NPC_T) {
+            for (int e = tid; e < NPC_T * NPC_NB; e += NP_BLOCK) {    // panel strip of the row block
+                const int r = e / NPC_NB, j = e % NPC_NB;
+                sm->Pr[r][j] = (rb + r < A && j < nb) ? L[(int64_t)(rb + r) * A + kb + j] : 0.0;
+            }
+            for (int cb = r0; cb <= rb; cb += NPC_T) {
+                __syncthreads();
+                for (int e = tid; e < NPC_T * NPC_NB; e += NP_BLOCK) {
+                    const int r = e / NPC_NB, j = e % NPC_NB;
+                    sm->Pc[r][j] = (cb + r < A && j < nb) ? L[(int64_t)(cb + r) * A + kb + j] : 0.0;
+                }
+                __syncthreads();
+                double acc[4][4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+#pragma unroll 8
+                for (int j = 0; j < NPC_NB; ++j) {
+                    double pr[4], pc[4];
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) { pr[a] = sm->Pr[tr + a][j]; pc[a] = sm->Pc[tc + a][j]; }
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) acc[a][b] = fma(pr[a], pc[b], acc[a][b]);
+                }
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    const int r = rb + tr + a;
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const int c2 = cb + tc + b;
+                        if (r < A && c2 <= r) L[(int64_t)r * A + c2] -= acc[a][b];
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
 __global__ void __launch_bounds__(NP_BLOCK) nprior_kernel(NPParams P)
 {
     __shared__ double scratch[40];
     __shared__ double s_sigma2, s_alpha0, s_p0, s_rr, s_delta, s_w;
-    __shared__ int s_j, s_A, s_first;
+    __shared__ int s_j, s_A;
+    __shared__ unsigned s_flags[NP_BLOCK / 32];
+    __shared__ NpCholSmem s_chol;
     __shared__ int s_scan[NP_BLOCK / 32 + 2];
 
     const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -150,6 +257,7 @@ __global__ void __launch_bounds__(NP_BLOCK) nprior_kernel(NPParams P)
         const int64_t soff = ((int64_t)c * P.n_total + sweep) * p;      // injected arrays: full length
         const PermView perm_s = { P.perm, ((int64_t)c * P.perm_S + P.perm_s0 + s) * p, P.perm16 };
         const double sigma2 = s_sigma2, alpha0 = s_alpha0, p0 = s_p0;
+        if (*reinterpret_cast<volatile int*>(P.err) == 1) return;   // another chain outgrew the workspace: this launch is replayed
 
         // ---- step 1: w of this sweep (:132-140 joint draw, or the fresh 0.1*N(0,1) row :100)
         int nact = 0;
@@ -175,7 +283,7 @@ __global__ void __launch_bounds__(NP_BLOCK) nprior_kernel(NPParams P)
         __syncthreads();
         const int A = nact;
         if (cf.joint_sample_W == 1 && A > 0) {
-            if (A > NP_AMAX) { if (tid == 0) *P.err = 1; return; }
+            if (A > NP_AMAX) { if (tid == 0) { atomicMax(P.err + 1, A); *P.err = 1; } return; }
             // precision PTP = T G_AA T + I / tauw2  (:307-337), lower triangle
             for (int e = tid; e < A * A; e += NP_BLOCK) {
                 const int r = e / A, cc = e % A;
@@ -187,8 +295,12 @@ __global__ void __launch_bounds__(NP_BLOCK) nprior_kernel(NPParams P)
                 }
             }
             __syncthreads();
-            // right-looking Cholesky in place
-            for (int k = 0; k < A; ++k) {
+            // right-looking Cholesky in place.  Column k is scaled into a contiguous scratch vector
+            // first; the trailing update then walks the rows with the threads along a row
+            // (contiguous, coalesced) and two warps' worth of rows in flight per pass.
+            double* colk = vec + 2 * NP_AMAX;
+            if (A > 64) np_cholesky_blocked(L, A, P.err, &s_chol);
+            else for (int k = 0; k < A; ++k) {
                 if (tid == 0) {
                     const double d = L[k * A + k];
                     if (!(d > 0)) *P.err = 2;
@@ -196,12 +308,13 @@ __global__ void __launch_bounds__(NP_BLOCK) nprior_kernel(NPParams P)
                 }
                 __syncthreads();
                 const double d = L[k * A + k];
-                for (int r = k + 1 + tid; r < A; r += NP_BLOCK) L[r * A + k] /= d;
+                for (int r = k + 1 + tid; r < A; r += NP_BLOCK) { const double v = L[r * A + k] / d; L[r * A + k] = v; colk[r] = v; }
                 __syncthreads();
-                const int m = A - k - 1;
-                for (int e = tid; e < m * m; e += NP_BLOCK) {
-                    const int r = k + 1 + e / m, cc = k + 1 + e % m;
-                    if (cc <= r) L[r * A + cc] -= L[r * A + k] * L[cc * A + k];
+                // rows are dealt to the warps, lanes run along the row (cc <= r)
+                for (int r = k + 1 + warp; r < A; r += NP_BLOCK / 32) {
+                    const double lrk = colk[r];
+                    double* row = L + (int64_t)r * A;
+                    for (int cc = k + 1 + lane; cc <= r; cc += 32) row[cc] -= lrk * colk[cc];
                 }
                 __syncthreads();
             }
@@ -213,7 +326,30 @@ __global__ void __launch_bounds__(NP_BLOCK) nprior_kernel(NPParams P)
                 wt[a] = P.joint_act ? P.joint_act[soff + a] : rng_normal(key, NP_JOINT_ACT, a, sweep, 0);
             }
             __syncthreads();
-            if (warp == 0) {
+            if (A > 64) {
+                // large systems: the whole block works on one row of L at a time (contiguous loads).
+                // forward  L v = tmu  by rows, with the partial sums reduced over the block;
+                // backward L^T m = v, L^T s = z  in axpy form: once x_r is known, row r of L updates
+                // the right-hand sides of all m < r.
+                for (int r = 0; r < A; ++r) {
+                    double acc = 0.0;
+                    for (int m = tid; m < r; m += NP_BLOCK) acc = fma(L[(int64_t)r * A + m], tmu[m], acc);
+                    acc = block_sum(acc, scratch);
+                    if (tid == 0) tmu[r] = (tmu[r] - acc) / L[(int64_t)r * A + r];
+                    __syncthreads();
+                }
+                for (int r = A - 1; r >= 0; --r) {
+                    const double lrr = L[(int64_t)r * A + r];
+                    const double xm = tmu[r] / lrr, xs = wt[r] / lrr;
+                    __syncthreads();
+                    if (tid == 0) { tmu[r] = xm; wt[r] = xs; }
+                    for (int m = tid; m < r; m += NP_BLOCK) {
+                        const double l = L[(int64_t)r * A + m];
+                        tmu[m] = fma(-l, xm, tmu[m]); wt[m] = fma(-l, xs, wt[m]);
+                    }
+                    __syncthreads();
+                }
+            } else if (warp == 0) {
                 for (int r = 0; r < A; ++r) {               // L v = tmu
                     double acc = 0.0;
                     for (int m = lane; m < r; m += 32) acc = fma(L[r * A + m], tmu[m], acc);
@@ -265,39 +401,41 @@ __global__ void __launch_bounds__(NP_BLOCK) nprior_kernel(NPParams P)
         }
         __syncthreads();
 
-        // ---- coordinate loop (:163-198), windows of 32 in warp 0
+        // ---- coordinate loop (:163-198): a window of NP_BLOCK upcoming positions, one per thread, is
+        // evaluated against the current state; the leading visits that stay inactive are committed
+        // (they redraw alpha_j and w_j but leave r alone) and the first one that touches r is applied
         int pos0 = 0;
         while (pos0 < p) {
-            const int T = min(32, p - pos0);
-            if (warp == 0) {
-                NPVisit v; v.stays_inactive = false;
-                int j = 0; double a_old = 0, w_old = 0, xl2 = 0, qj = 0;
-                bool change = false;
-                if (lane < T) {
-                    j = perm_s[pos0 + lane];
-                    a_old = alpha[j]; w_old = w[j]; xl2 = P.Xl2[j]; qj = q[j];
-                    if (w_old * fmax(a_old - alpha0, 0.0) != 0.0) change = true;     // active before: certain change
-                    else {
-                        v = np_visit(P, key, pos0 + lane, sweep, soff, a_old, w_old, xl2, qj, s_rr, sigma2, alpha0, p0);
-                        change = !v.stays_inactive;
-                    }
+            const int T = min(NP_BLOCK, p - pos0);
+            NPVisit v; v.stays_inactive = false;
+            int j = 0; double a_old = 0, w_old = 0, xl2 = 0, qj = 0;
+            bool change = false;
+            if (tid < T) {
+                j = perm_s[pos0 + tid];
+                a_old = alpha[j]; w_old = w[j]; xl2 = P.Xl2[j]; qj = q[j];
+                if (w_old * fmax(a_old - alpha0, 0.0) != 0.0) change = true;     // active before: certain change
+                else {
+                    v = np_visit(P, key, pos0 + tid, sweep, soff, a_old, w_old, xl2, qj, s_rr, sigma2, alpha0, p0);
+                    change = !v.stays_inactive;
                 }
-                const unsigned m = __ballot_sync(0xffffffffu, change);
-                const int first = m ? __ffs(m) - 1 : -1;
-                if (lane < T && (first < 0 || lane < first)) { alpha[j] = v.alpha_new; w[j] = v.w_new; }
-                if (first >= 0 && lane == first) {
-                    // an active coordinate was not evaluated speculatively; a flipping one was evaluated
-                    // against the same state, re-evaluating is identical (keyed draws) and keeps one path
-                    v = np_visit(P, key, pos0 + lane, sweep, soff, a_old, w_old, xl2, qj, s_rr, sigma2, alpha0, p0);
-                    const double b_old = w_old * fmax(a_old - alpha0, 0.0);
-                    alpha[j] = v.alpha_new; w[j] = v.w_new; beta[j] = v.beta_new;
-                    s_rr = v.rr_back - 2.0 * v.beta_new * v.qj_back + v.beta_new * v.beta_new * xl2;
-                    s_delta = v.beta_new - b_old; s_j = j;
-                }
-                if (lane == 0) s_first = first;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, change);
+            if (lane == 0) s_flags[warp] = m;
+            __syncthreads();
+            int first = -1;
+#pragma unroll
+            for (int wv = NP_BLOCK / 32 - 1; wv >= 0; --wv) if (s_flags[wv]) first = 32 * wv + __ffs(s_flags[wv]) - 1;
+            if (tid < T && (first < 0 || tid < first)) { alpha[j] = v.alpha_new; w[j] = v.w_new; }
+            if (first >= 0 && tid == first) {
+                // an active coordinate was not evaluated speculatively; a flipping one was evaluated
+                // against the same state, re-evaluating is identical (keyed draws) and keeps one path
+                v = np_visit(P, key, pos0 + tid, sweep, soff, a_old, w_old, xl2, qj, s_rr, sigma2, alpha0, p0);
+                const double b_old = w_old * fmax(a_old - alpha0, 0.0);
+                alpha[j] = v.alpha_new; w[j] = v.w_new; beta[j] = v.beta_new;
+                s_rr = v.rr_back - 2.0 * v.beta_new * v.qj_back + v.beta_new * v.beta_new * xl2;
+                s_delta = v.beta_new - b_old; s_j = j;
             }
             __syncthreads();
-            const int first = s_first;
             if (first < 0) { pos0 += T; continue; }
             const double delta = s_delta; const int jstar = s_j;
             if (delta != 0) for (int k = tid; k < p; k += NP_BLOCK) q[k] = fma(-delta, P.G[(int64_t)jstar * P.ldg + k], q[k]);
@@ -457,20 +595,33 @@ extern "C" int blipgpu_sample_nprior(blipgpu_ctx* ctx, blipgpu_design* design, c
     BLIP_TRY(d_alpha.alloc(sizeof(double) * chains * p)); BLIP_TRY(d_w.alloc(sizeof(double) * chains * p));
     BLIP_TRY(d_beta.alloc(sizeof(double) * chains * p)); BLIP_TRY(d_q.alloc(sizeof(double) * chains * p2));
     BLIP_TRY(d_hs.alloc(sizeof(double) * chains * 4));
-    // active-set workspace: as large as p if a quarter of the free memory (at most 16 GB) allows
-    int64_t NP_AMAX = p;
+    // active-set workspace of the joint W draw: starts small and is doubled (with a replay of the
+    // launch, see below) when a chain's active set outgrows it; the limit is what a quarter of the
+    // free memory (at most 16 GB) can hold
+    int64_t amax_limit = p;
     {
         size_t free_b = 0, total_b = 0;
         CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
         const double budget = std::min(0.25 * (double)free_b, 16.0e9);
         const int64_t fit = (int64_t)std::sqrt(budget / (8.0 * (double)chains));
-        NP_AMAX = std::max<int64_t>(std::min<int64_t>(p, NP_AMAX_MIN), std::min<int64_t>(p, fit));
+        amax_limit = std::max<int64_t>(std::min<int64_t>(p, NP_AMAX_MIN), std::min<int64_t>(p, fit));
     }
-    BLIP_TRY(d_chol.alloc(sizeof(double) * chains * NP_AMAX * NP_AMAX));
-    BLIP_TRY(d_vec.alloc(sizeof(double) * chains * 3 * NP_AMAX)); BLIP_TRY(d_act.alloc(sizeof(int) * chains * NP_AMAX));
-    BLIP_TRY(d_err.alloc(sizeof(int))); BLIP_TRY(d_q0.alloc(sizeof(double) * p));
+    int64_t NP_AMAX = std::min<int64_t>(amax_limit, 256);
+    auto alloc_workspace = [&]() -> int {
+        if (d_chol.ptr) { cudaFree(d_chol.ptr); d_chol.ptr = nullptr; }
+        if (d_vec.ptr) { cudaFree(d_vec.ptr); d_vec.ptr = nullptr; }
+        if (d_act.ptr) { cudaFree(d_act.ptr); d_act.ptr = nullptr; }
+        BLIP_TRY(d_chol.alloc(sizeof(double) * chains * NP_AMAX * NP_AMAX));
+        BLIP_TRY(d_vec.alloc(sizeof(double) * chains * 3 * NP_AMAX)); BLIP_TRY(d_act.alloc(sizeof(int) * chains * NP_AMAX));
+        return BLIP_OK;
+    };
+    BLIP_TRY(alloc_workspace());
+    DBuf s_alpha, s_w, s_beta, s_q, s_hs;            // state snapshot for the replay
+    BLIP_TRY(s_alpha.alloc(d_alpha.bytes)); BLIP_TRY(s_w.alloc(d_w.bytes)); BLIP_TRY(s_beta.alloc(d_beta.bytes));
+    BLIP_TRY(s_q.alloc(d_q.bytes)); BLIP_TRY(s_hs.alloc(d_hs.bytes));
+    BLIP_TRY(d_err.alloc(2 * sizeof(int))); BLIP_TRY(d_q0.alloc(sizeof(double) * p));
     BLIP_TRY(d_y.upload(y, sizeof(double) * n, st));
-    CUDA_TRY(cudaMemsetAsync(d_err.ptr, 0, sizeof(int), st));
+    CUDA_TRY(cudaMemsetAsync(d_err.ptr, 0, 2 * sizeof(int), st));
     BLIP_TRY(blip_xty(st, design, d_y.as<double>(), d_q0.as<double>()));
     double yy = 0.0;
     for (int64_t i = 0; i < n; ++i) yy += y[i] * y[i];
@@ -523,15 +674,38 @@ extern "C" int blipgpu_sample_nprior(blipgpu_ctx* ctx, blipgpu_design* design, c
         }
         P.perm = d_perm.ptr; P.perm16 = perm16 ? 1 : 0; P.perm_S = Sc; P.perm_s0 = 0;
         P.sweep0 = (int)sweep0; P.S = Sc;
-        ScopedTimer timer(ctx, true);
-        nprior_kernel<<<(unsigned)chains, NP_BLOCK, 0, st>>>(P);
-        CUDA_TRY(cudaGetLastError());
-        res->sweep_ms += timer.stop(1);
-        int err = 0;
-        CUDA_TRY(cudaMemcpyAsync(&err, d_err.ptr, sizeof(int), cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
-        if (err == 1) { blip_set_error("sample_nprior: more than %lld active coordinates in the joint W draw (workspace sized from free memory)", (long long)NP_AMAX); return BLIP_ERR_UNSUPPORTED; }
-        if (err == 2) { blip_set_error("sample_nprior: Cholesky of the active-set precision failed"); return BLIP_ERR_NUMERIC; }
+        auto copy_state = [&](bool save) -> int {
+            DBuf* live[5] = { &d_alpha, &d_w, &d_beta, &d_q, &d_hs };
+            DBuf* snap[5] = { &s_alpha, &s_w, &s_beta, &s_q, &s_hs };
+            for (int i = 0; i < 5; ++i)
+                CUDA_TRY(cudaMemcpyAsync(save ? snap[i]->ptr : live[i]->ptr, save ? live[i]->ptr : snap[i]->ptr,
+                                         live[i]->bytes, cudaMemcpyDeviceToDevice, st));
+            return BLIP_OK;
+        };
+        BLIP_TRY(copy_state(true));
+        for (;;) {
+            P.amax = (int)NP_AMAX; P.chol = d_chol.as<double>(); P.vec = d_vec.as<double>(); P.act = d_act.as<int>();
+            ScopedTimer timer(ctx, true);
+            nprior_kernel<<<(unsigned)chains, NP_BLOCK, 0, st>>>(P);
+            CUDA_TRY(cudaGetLastError());
+            res->sweep_ms += timer.stop(1);
+            int errv[2] = { 0, 0 };
+            CUDA_TRY(cudaMemcpyAsync(errv, d_err.ptr, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            const int err = errv[0];
+            if (err == 2) { blip_set_error("sample_nprior: Cholesky of the active-set precision failed"); return BLIP_ERR_NUMERIC; }
+            if (err == 0) break;
+            // a chain's active set outgrew the workspace: enlarge it and replay the launch from the
+            // snapshot (keyed draws make the replay identical)
+            if (NP_AMAX >= amax_limit) {
+                blip_set_error("sample_nprior: more than %lld active coordinates in the joint W draw (workspace limited by free memory)", (long long)NP_AMAX);
+                return BLIP_ERR_UNSUPPORTED;
+            }
+            NP_AMAX = std::min<int64_t>(amax_limit, std::max<int64_t>(2 * NP_AMAX, (int64_t)errv[1] + errv[1] / 4 + 32));
+            BLIP_TRY(alloc_workspace());
+            BLIP_TRY(copy_state(false));
+            CUDA_TRY(cudaMemsetAsync(d_err.ptr, 0, 2 * sizeof(int), st));
+        }
     }
     CUDA_TRY(cudaStreamSynchronize(st));
     guard.r = nullptr;

@@ -95,3 +95,30 @@ def test_nprior_api_and_signal_recovery(gpu):
     groups = cg.sequential_groups(nlm, max_pep=0.1)
     found = {tuple(g.group)[0] for g in groups if len(g.group) == 1}
     assert set(np.where(beta != 0)[0]) <= found
+
+
+def test_nprior_workspace_grows_and_replays(gpu):
+    """More than 256 active coordinates: the joint-W workspace starts at 256, the launch that outgrows
+    it is replayed from the state snapshot with a larger one -- results still equal the oracle's."""
+    from oracle import gibbs_oracle as go
+    from pyblip_b200 import _lib
+    rng = np.random.default_rng(21)
+    n, p, N = 120, 420, 4
+    X = rng.standard_normal((n, p))
+    y = X @ rng.standard_normal(p) + 0.1 * rng.standard_normal(n)
+    kw = dict(tauw2=1.0, p0_init=0.3, min_p0=1e-10, update_p0=1, sigma_a0=5.0, sigma_b0=1.0,
+              sigma_prior_type=0, joint_sample_W=1, group_alpha_update=1)
+    cfg = _lib.NPriorConfig(kw["tauw2"], kw["p0_init"], kw["min_p0"], kw["update_p0"], kw["sigma_a0"],
+                            kw["sigma_b0"], kw["sigma_prior_type"], kw["joint_sample_W"],
+                            kw["group_alpha_update"], 0)
+    design = _lib.Design.upload(X)
+    smp = _lib.sample_nprior(design, cfg, y, chains=2, n_keep=N, burn=0, seed=5)
+    out = {k: smp.get(k) for k in ("alphas", "ws", "betas", "sigma2s")}
+    smp.close(); design.close()
+    assert ((out["betas"] != 0).sum(1) > 256).any(), "the case must outgrow the initial workspace"
+    for c in range(2):
+        orc = go.nprior_sample(N, X, y, seed=5, chain=c, **kw)
+        sl = slice(c * N, (c + 1) * N)
+        assert np.array_equal(out["betas"][sl] != 0, orc["betas"] != 0)
+        for k in ("alphas", "ws", "sigma2s"):
+            assert util.rel_err(out[k][sl], orc[k]) <= 1e-7, k    # 300x300 Cholesky: conditioning, not logic
