@@ -26,6 +26,10 @@ class NumpyDeviceSamples:
             return np.zeros(0, dtype=np.int64)
         return dist.allreduce_counts(co.group_any_counts(self.S, groups))
 
+    def pair_counts(self):
+        Si = self.S.astype(np.int64)
+        return dist.allreduce_counts(Si.T @ Si)
+
     def to_dense(self):
         return self.S
 

@@ -90,3 +90,27 @@ def test_shard_chains_partition():
                 assert a1 == b0 and a1 >= a0
             sizes = [b - a for a, b in parts]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_correlation_from_integer_pair_counts(monkeypatch):
+    """`_samples_dist_matrix_device` (exact integer co-occurrence counts) reproduces the reference's
+    np.corrcoef-based `_samples_dist_matrix` (create_groups.py:523-535) to rounding, including constant
+    columns (the appended all-zero / all-one rows make every column non-constant)."""
+    import fake_device
+    from pyblip_b200 import create_groups as cg
+    fake_device.install(monkeypatch)
+    rng = np.random.default_rng(3)
+    S = rng.random((400, 30)) < 0.15
+    S[:, 4] = True
+    S[:, 5] = False
+    S[:, 7] = S[:, 6]
+    dev = cg._as_device(S)
+    d_int = cg._samples_dist_matrix_device(dev)
+    d_ref = cg._samples_dist_matrix(S)
+    assert np.max(np.abs(d_int - d_ref)) < 1e-12
+    assert d_int[6, 7] == 2.0 and np.allclose(np.diag(d_int), 2.0)
+    # the size switch: small problems keep the host path (parity with the reference's tie-breaking)
+    monkeypatch.setattr(cg, "_DEVICE_CORR_MIN_ENTRIES", 10 ** 9)
+    assert np.array_equal(cg._sample_dist_matrix_auto(dev), d_ref)
+    monkeypatch.setattr(cg, "_DEVICE_CORR_MIN_ENTRIES", 0)
+    assert np.array_equal(cg._sample_dist_matrix_auto(dev), d_int)
