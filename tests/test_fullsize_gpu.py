@@ -155,3 +155,52 @@ def test_c5_global_q_gram_kernel_equals_residual(gpu):
     _csr_equal(g["csr"], r["csr"], tol=5e-9)
     assert util.rel_err(g["hyper"], r["hyper"]) <= RTOL
     g["smp"].close(); r["smp"].close(); design.close()
+
+
+def test_c2_block_sampler_forms_agree_and_match_oracle(gpu):
+    """configs[1] shape with bsize=3 / bsize=5: the gram and residual forms of the block kernel --
+    different state, different arithmetic -- produce the same indicators and coefficients.  (The block
+    oracle is compared at sizes it can handle in tests/test_block_gpu.py: its X'X is a naive O(n p^2) loop.)"""
+    from pyblip_b200 import _lib
+    from pyblip_b200.linear import LinearSpikeSlab
+    import bench
+    X, y, _ = bench.make_data()
+    cfg = LinearSpikeSlab(X, y)._config()
+    design = _lib.Design.upload(X)
+    for bsize in (3, 5):
+        kw = dict(y=y, chains=3, chain_offset=7, n_keep=6, burn=0, seed=13, bsize=bsize)
+        g = _sample(design, cfg, _lib.MODE_GRAM, **kw)
+        r = _sample(design, cfg, _lib.MODE_RESIDUAL, **kw)
+        # first sweeps from beta = 0: ~1000 active coordinates, 5 x 5 blocks of rho = 0.95 columns --
+        # indicators identical, small coefficients agree to ~1e-8 element-wise
+        _csr_equal(g["csr"], r["csr"], tol=2e-8)
+        assert util.rel_err(g["hyper"], r["hyper"]) <= RTOL
+        g["smp"].close(); r["smp"].close()
+    design.close()
+
+
+def test_nprior_p2000_matches_oracle_prefix(gpu):
+    """Neuronized prior at p=2000 (blocked Cholesky path is reached by some chains during burn-in):
+    chain 0, first 4 sweeps against the oracle under the keyed stream."""
+    from oracle import gibbs_oracle as go
+    from pyblip_b200 import _lib
+    import bench
+    X, _, _ = bench.make_data()
+    Xn = np.ascontiguousarray(X[:, :2000])
+    rng = np.random.default_rng(7)
+    b = np.zeros(2000)
+    b[rng.choice(2000, 20, replace=False)] = rng.standard_normal(20)
+    yn = Xn @ b + rng.standard_normal(Xn.shape[0])
+    kw = dict(tauw2=1.0, p0_init=1 - 1 / 2000, min_p0=1e-10, update_p0=1, sigma_a0=5.0, sigma_b0=1.0,
+              sigma_prior_type=0, joint_sample_W=1, group_alpha_update=1)
+    cfg = _lib.NPriorConfig(kw["tauw2"], kw["p0_init"], kw["min_p0"], kw["update_p0"], kw["sigma_a0"],
+                            kw["sigma_b0"], kw["sigma_prior_type"], kw["joint_sample_W"],
+                            kw["group_alpha_update"], 0)
+    design = _lib.Design.upload(Xn)
+    smp = _lib.sample_nprior(design, cfg, yn, chains=2, n_keep=4, burn=0, seed=1)
+    out = {k: smp.get(k) for k in ("alphas", "ws", "betas", "sigma2s", "p0s")}
+    smp.close(); design.close()
+    orc = go.nprior_sample(4, Xn, yn, seed=1, chain=0, **kw)
+    assert np.array_equal(out["betas"][:4] != 0, orc["betas"] != 0)
+    for k in ("alphas", "ws", "sigma2s", "p0s"):
+        assert util.rel_err(out[k][:4], orc[k]) <= 1e-8, k
