@@ -63,6 +63,74 @@ __device__ __forceinline__ double block_model_lp(uint32_t mask, int bsize, const
     return lp;
 }
 
+// The same score with the block size as a compile-time constant: the model is embedded in the
+// full BS x BS matrix with identity rows for the members it leaves out.  Every operation on a
+// member entry is the one block_model_lp performs (the extra terms are exact zeros), so the
+// result is bit-identical, but all loops unroll and the small matrices live in registers instead
+// of dynamically indexed local memory.
+template <int BS>
+__device__ __forceinline__ double block_model_lp_t(uint32_t mask, const double* A, const double* x,
+                                                   double tau2, double sigma2, double logp0, double log1p0)
+{
+    const double cm = tau2 / sigma2;
+    double Q[BS][BS], yv[BS];
+#pragma unroll
+    for (int a = 0; a < BS; ++a)
+#pragma unroll
+        for (int b = 0; b <= a; ++b) {
+            const bool in = ((mask >> a) & 1u) && ((mask >> b) & 1u);
+            Q[a][b] = (a == b ? 1.0 : 0.0) + (in ? cm * A[a * BS + b] : 0.0);
+        }
+    double logdet = 0.0;
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < BS; ++j) {
+        double d = Q[j][j];
+#pragma unroll
+        for (int k = 0; k < j; ++k) d -= Q[j][k] * Q[j][k];
+        if (!(d > 0.0)) ok = false;
+        d = sqrt(d);
+        Q[j][j] = d;
+        if ((mask >> j) & 1u) logdet += 2.0 * log(d);
+#pragma unroll
+        for (int i = j + 1; i < BS; ++i) {
+            double sacc = Q[i][j];
+#pragma unroll
+            for (int k = 0; k < j; ++k) sacc -= Q[i][k] * Q[j][k];
+            Q[i][j] = sacc / d;
+        }
+    }
+    if (!ok) return nan("");
+    double nrm2 = 0.0;
+#pragma unroll
+    for (int a = 0; a < BS; ++a) {
+        double sacc = ((mask >> a) & 1u) ? x[a] : 0.0;
+#pragma unroll
+        for (int k = 0; k < a; ++k) sacc -= Q[a][k] * yv[k];
+        yv[a] = sacc / Q[a][a];
+        if ((mask >> a) & 1u) nrm2 += yv[a] * yv[a];
+    }
+    const int m = __popc(mask);
+    double nrm = sqrt(nrm2);
+    double lp = tau2 * nrm * nrm / (2 * sigma2 * sigma2) - logdet / 2;
+    lp += (BS - m) * logp0;
+    lp += m * log1p0;
+    return lp;
+}
+
+__device__ __noinline__ double block_model_lp_any(uint32_t mask, int bsize, const double* A, const double* x,
+                                                  double tau2, double sigma2, double logp0, double log1p0)
+{
+    switch (bsize) {
+        case 2: return block_model_lp_t<2>(mask, A, x, tau2, sigma2, logp0, log1p0);
+        case 3: return block_model_lp_t<3>(mask, A, x, tau2, sigma2, logp0, log1p0);
+        case 4: return block_model_lp_t<4>(mask, A, x, tau2, sigma2, logp0, log1p0);
+        case 5: return block_model_lp_t<5>(mask, A, x, tau2, sigma2, logp0, log1p0);
+        case 6: return block_model_lp_t<6>(mask, A, x, tau2, sigma2, logp0, log1p0);
+        default: return block_model_lp(mask, bsize, A, x, tau2, sigma2, logp0, log1p0);
+    }
+}
+
 // Scores all models of one block with one warp: probs[mj] = exp(lp_mj - max(0, max lp)) in shared
 // memory (model 0 = empty), returns the sequentially accumulated normaliser (same order as
 // _weighted_choice, :55-79) in every lane; *bad is set if a factorisation failed.
@@ -74,7 +142,7 @@ __device__ __forceinline__ double block_score(const SweepParams& P, const double
     bool fail = false;
     for (int mj = lane; mj < P.nmodel; mj += 32) {
         double lp = mj == 0 ? P.bsize * logp0
-                            : block_model_lp(P.model_masks[mj - 1], P.bsize, A, x, tau2, sigma2, logp0, log1p0);
+                            : block_model_lp_any(P.model_masks[mj - 1], P.bsize, A, x, tau2, sigma2, logp0, log1p0);
         if (lp != lp) fail = true;
         probs[mj] = lp;
         mx = fmax(lp, mx);
@@ -326,7 +394,7 @@ __global__ void __launch_bounds__(GB_BLOCK, 2) gibbs_block_kernel(SweepParams P)
                 bool fail = false;
                 if (score && gl < P.nmodel) {
                     lp = gl == 0 ? bsize * logp0
-                                 : block_model_lp(P.model_masks[gl - 1], bsize, gA, gx, tau2, sigma2, logp0, log1p0);
+                                 : block_model_lp_any(P.model_masks[gl - 1], bsize, gA, gx, tau2, sigma2, logp0, log1p0);
                     fail = lp != lp;
                 }
                 double mx = fmax(lp, 0.0);                              // max_log_prob starts at 0.0 (:62)
@@ -388,22 +456,35 @@ __global__ void __launch_bounds__(GB_BLOCK, 2) gibbs_block_kernel(SweepParams P)
                 bs.bold[tid] = ((mask_s[j >> 5] >> (j & 31)) & 1u) ? __ldcg(beta_g + j) : 0.0;
             }
             __syncthreads();
-            for (int k = 0; k < bsize; ++k) {                          // zero the block (:430-442)
-                const double bold = bs.bold[k];
-                if (bold != 0) {                                       // block-uniform
-                    const int j = bs.mem[k];
-                    add_column(j, bold);
-                    if (tid == 0) { __stcg(beta_g + j, 0.0); mask_s[j >> 5] &= ~(1u << (j & 31)); }
+            if (!GRAM) {
+                for (int k = 0; k < bsize; ++k) {                      // zero the block (:430-442)
+                    const double bold = bs.bold[k];
+                    if (bold != 0) {                                   // block-uniform
+                        const int j = bs.mem[k];
+                        add_column(j, bold);
+                        if (tid == 0) { __stcg(beta_g + j, 0.0); mask_s[j >> 5] &= ~(1u << (j & 31)); }
+                    }
                 }
             }
-            // sufficient statistics of the zeroed block (:83-160)
+            // sufficient statistics of the zeroed block (:83-160).  Gram form: the block is not
+            // zeroed by a pass over q; X_A^T r of the zeroed block follows from q and the block of
+            // X^T X alone (q_m + sum_k beta_k G[m][k], the same fma chain as the passes), and the
+            // old coefficients are folded into the write-back below -- one Gram column per member
+            // whose coefficient actually changes instead of two.
             {
                 const double* gb = P.gb + (int64_t)(bs.mem[0] / bsize) * bsize * bsize;
                 if (tid < bsize * bsize) bs.A[tid] = gb[tid];
-                if (GRAM) { if (tid < bsize) bs.xatr[tid] = q[bs.mem[tid]]; }
-                else if (warp < bsize) { const double d = warp_dot(bs.mem[warp]); if (lane == 0) bs.xatr[warp] = d; }
+                if (!GRAM && warp < bsize) { const double d = warp_dot(bs.mem[warp]); if (lane == 0) bs.xatr[warp] = d; }
             }
             __syncthreads();
+            if (GRAM) {
+                if (tid < bsize) {
+                    double x = q[bs.mem[tid]];
+                    for (int k = 0; k < bsize; ++k) if (bs.bold[k] != 0) x = fma(bs.bold[k], bs.A[tid * bsize + k], x);
+                    bs.xatr[tid] = x;
+                }
+                __syncthreads();
+            }
             if (warp == 0) {
                 bool bad2 = false;
                 const double denom = block_score(P, bs.A, bs.xatr, tau2, sigma2, logp0, log1p0, probs, &bad2);
@@ -428,7 +509,22 @@ __global__ void __launch_bounds__(GB_BLOCK, 2) gibbs_block_kernel(SweepParams P)
             }
             __syncthreads();
             const int mj = bs.mj;
-            if (mj > 0) {                                              // write back (:850-884)
+            if (GRAM) {                                                // zeroing and write-back in one update
+                const uint32_t msk = mj > 0 ? P.model_masks[mj - 1] : 0u;
+                for (int k = 0; k < bsize; ++k) {
+                    const double bold = bs.bold[k];
+                    const bool sel = (msk >> k) & 1u;
+                    if (bold == 0 && !sel) continue;                   // block-uniform
+                    const int j = bs.mem[k];
+                    const double bnew = sel ? bs.bnew[k] : 0.0;
+                    if (bnew != bold) add_column(j, bold - bnew);
+                    if (tid == 0) {
+                        __stcg(beta_g + j, bnew);
+                        if (bnew != 0) mask_s[j >> 5] |= (1u << (j & 31));
+                        else mask_s[j >> 5] &= ~(1u << (j & 31));
+                    }
+                }
+            } else if (mj > 0) {                                       // write back (:850-884)
                 const uint32_t msk = P.model_masks[mj - 1];
                 for (int k = 0; k < bsize; ++k) {
                     if (!(msk & (1u << k))) continue;
@@ -441,6 +537,8 @@ __global__ void __launch_bounds__(GB_BLOCK, 2) gibbs_block_kernel(SweepParams P)
                         else mask_s[j >> 5] &= ~(1u << (j & 31));
                     }
                 }
+            }
+            if (mj > 0) {
                 if (PROBIT) {
                     for (int k = tid; k < n; k += GB_BLOCK) {
                         const double m = mu_s[k];
