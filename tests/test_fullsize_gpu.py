@@ -204,3 +204,32 @@ def test_nprior_p2000_matches_oracle_prefix(gpu):
     assert np.array_equal(out["betas"][:4] != 0, orc["betas"] != 0)
     for k in ("alphas", "ws", "sigma2s", "p0s"):
         assert util.rel_err(out[k][:4], orc[k]) <= 1e-8, k
+
+
+def test_c2_queue_scheduling_is_deterministic(gpu):
+    """The persistent work queue hands (chain, 8-sweep) items to whichever CTA is free, so two runs
+    schedule differently; a race on shared state would show up as run-to-run differences.  400 chains
+    x 40 sweeps twice with one seed, and once as two half-size calls with chain offsets: identical
+    indicators, coefficients and hyper-parameters, bit for bit."""
+    from pyblip_b200 import _lib
+    from pyblip_b200.linear import LinearSpikeSlab
+    import bench
+    X, y, _ = bench.make_data()
+    cfg = LinearSpikeSlab(X, y)._config()
+    design = _lib.Design.upload(X)
+    kw = dict(y=y, n_keep=30, burn=10, seed=123)
+    a = _sample(design, cfg, _lib.MODE_GRAM, chains=400, chain_offset=0, **kw)
+    b = _sample(design, cfg, _lib.MODE_GRAM, chains=400, chain_offset=0, **kw)
+    for k in range(3):
+        assert np.array_equal(a["csr"][k], b["csr"][k])
+    assert np.array_equal(a["hyper"], b["hyper"])
+    c1 = _sample(design, cfg, _lib.MODE_GRAM, chains=150, chain_offset=0, **kw)       # one CTA per chain
+    c2 = _sample(design, cfg, _lib.MODE_GRAM, chains=250, chain_offset=150, **kw)
+    n1 = int(c1["csr"][0][-1])
+    assert np.array_equal(a["csr"][0][:150 * 30 + 1], c1["csr"][0])
+    assert np.array_equal(a["csr"][1][:n1], c1["csr"][1][:n1]) and np.array_equal(a["csr"][2][:n1], c1["csr"][2][:n1])
+    assert np.array_equal(a["csr"][2][n1:int(a["csr"][0][-1])], c2["csr"][2][:int(c2["csr"][0][-1])])
+    assert np.array_equal(a["hyper"], np.concatenate([c1["hyper"], c2["hyper"]], axis=1))
+    for o in (a, b, c1, c2):
+        o["smp"].close()
+    design.close()
