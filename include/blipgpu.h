@@ -286,6 +286,14 @@ int blipgpu_gridcounts_get(blipgpu_gridcounts* r, uint64_t* codes, uint32_t* cou
                            uint64_t* pair_codes, uint32_t* pair_mult);
 int blipgpu_gridcounts_free(blipgpu_gridcounts* r);
 
+/* Overlap (constraint) matrix of G candidate regions, the O(G^2) step of `grid_peps_to_cand_groups`
+ * (pyblip/create_groups_cts.py:283-308), in the reference's float32 arithmetic.  centers: HOST
+ * [d][G] float32, radii: HOST [G] float32; circle == 0: squares (all |c_a - c_b| < r_a + r_b),
+ * else Euclidean distance < r_a + r_b.  out_bits: HOST [G][ceil(G/32)] uint32, bit b of word
+ * [a][b/32] set iff regions a and b overlap (the diagonal is set). */
+int blipgpu_overlap_bits(blipgpu_ctx* ctx, const float* centers, const float* radii, int64_t G,
+                         int32_t d, int32_t circle, uint32_t* out_bits);
+
 #ifdef __cplusplus
 }
 #endif

@@ -36,6 +36,7 @@ SYMBOLS = [
     "blipgpu_count_columns", "blipgpu_count_sequential", "blipgpu_count_groups", "blipgpu_count_pairs",
     "blipgpu_bits_free",
     "blipgpu_grid_count", "blipgpu_gridcounts_sizes", "blipgpu_gridcounts_get", "blipgpu_gridcounts_free",
+    "blipgpu_overlap_bits",
 ]
 
 
@@ -649,3 +650,16 @@ def grid_count(locs, grid_sizes, circle, extra_centers=None, extra_radii=None, e
     finally:
         load().blipgpu_gridcounts_free(h)
     return codes[:nk.value], counts[:nk.value], pcodes[:npair.value], pmult[:npair.value]
+
+
+def overlap_bits(centers, radii, circle, ctx=None):
+    """``blipgpu_overlap_bits``: centers (d, G) float32, radii (G,) float32 -> (G, ceil(G/32)) uint32."""
+    ctx = ctx or Context.get()
+    centers = np.ascontiguousarray(centers, dtype=np.float32)
+    radii = np.ascontiguousarray(radii, dtype=np.float32)
+    d, G = centers.shape
+    out = np.empty((G, (G + 31) // 32), dtype=np.uint32)
+    check(load().blipgpu_overlap_bits(ctx._h, C.c_void_p(centers.ctypes.data), C.c_void_p(radii.ctypes.data),
+                                      C.c_int64(G), C.c_int32(d), C.c_int32(int(bool(circle))),
+                                      C.c_void_p(out.ctypes.data)))
+    return out

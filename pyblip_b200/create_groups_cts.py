@@ -158,3 +158,155 @@ def grid_peps(
             val['pip'] = total
             filtered[key] = val
     return filtered
+
+
+# ---------------------------------------------------------------------------
+# grid_peps output -> candidate groups for BLiP (create_groups_cts.py:228-384)
+# ---------------------------------------------------------------------------
+def _edge_clique_cover(nbrs):
+    """Greedy edge clique cover of an undirected graph with self-loops on nodes 0..n-1
+    (``nbrs[v]``: ascending neighbour list, v itself included), with the decisions of the
+    reference's heuristic (pyblip/ecc.py:8-64): edges are visited in (u, v >= u) order, a clique
+    starts from a still uncovered edge and is extended by the common neighbour of highest remaining
+    degree (ties: smallest index).  Returns a list of sets."""
+    n = len(nbrs)
+    nset = [set(x) for x in nbrs]
+    rem = [set(x) for x in nbrs]                       # the graph with covered edges deleted (G2)
+    degrees = np.array([len(x) + (1 if v in nset[v] else 0) for v, x in enumerate(nbrs)], dtype=np.int64)
+    cliques = []
+    for v1 in range(n):
+        for v2 in nbrs[v1]:
+            if v2 < v1:
+                continue
+            if v2 not in rem[v1]:
+                continue
+            rem[v1].discard(v2); rem[v2].discard(v1)
+            degrees[v1] -= 1; degrees[v2] -= 1
+            for v in (v1, v2):
+                if v in rem[v]:
+                    rem[v].discard(v)
+                    degrees[v] -= 1
+            c = [v1, v2]
+            neighbors = (nset[v1] & nset[v2]) - {v1, v2}
+            if neighbors and np.any(degrees[list(neighbors)] > 0):
+                while len(neighbors) > 0:
+                    ln = sorted(neighbors)
+                    vnew = ln[int(np.argmax(degrees[ln]))]
+                    c.append(vnew)
+                    for vold in c:
+                        if vnew in rem[vold]:
+                            rem[vold].discard(vnew); rem[vnew].discard(vold)
+                            degrees[vold] -= 1
+                            if vnew != vold:
+                                degrees[vnew] -= 1
+                    neighbors = (neighbors & nset[vnew]) - {vnew}
+            cliques.append(set(c))
+    return cliques
+
+
+def grid_peps_to_cand_groups(
+    filtered_peps,
+    time0=None,
+    min_blip_size=1000,
+    verbose=False,
+    shape='square',
+    max_pep=0.25,
+    min_pep=0.001,
+):
+    """
+    Turns the output of ``grid_peps`` into a list of lists of CandidateGroups, one sub-list per
+    (merged) connected component of the overlap graph, plus the components themselves
+    (create_groups_cts.py:228-384; same parameters, same return value).  The O(ngroups^2) overlap
+    matrix is computed on the device in the reference's float32 arithmetic
+    (``blipgpu_overlap_bits``); components are found in the order networkx's BFS yields them and
+    the clique cover follows pyblip/ecc.py, so group ids and list orders are the reference's.
+    ``time0`` / ``verbose`` are accepted and ignored.
+    """
+    import copy
+    from .create_groups import CandidateGroup
+    ngroups = len(filtered_peps)
+    if ngroups == 0:
+        return [], []
+    keys = sorted(filtered_peps.keys())
+    if isinstance(filtered_peps[keys[0]], dict):
+        count_signals = True
+        peps_arr = 1 - np.array([filtered_peps[k]['pip'] for k in keys])
+    else:
+        count_signals = False
+        peps_arr = np.array([filtered_peps[k] for k in keys])
+    if shape not in ('square', 'circle'):
+        raise ValueError(f"Unrecognized shape={shape}, must be one of 'square', 'circle'")
+
+    # Step 1: overlap matrix on the device
+    d = len(keys[0]) - 1
+    centers = np.zeros((d, ngroups))
+    radii = np.array([float(k[-1]) for k in keys])
+    for j in range(d):
+        centers[j] = np.array([k[j] for k in keys])
+        if centers[j].max() > 1 or centers[j].min() < 0:
+            raise ValueError("centers must be between 0 and 1 but this is not true")
+    radii = radii.astype(np.float32)
+    centers = centers.astype(np.float32)
+    bits = _lib.overlap_bits(centers, radii, circle=(shape == 'circle'))
+    dense = np.unpackbits(bits.view(np.uint8), axis=1, bitorder='little')[:, :ngroups].astype(bool)
+    nbrs = [np.flatnonzero(dense[v]).tolist() for v in range(ngroups)]     # ascending, self included
+
+    # Step 2: connected components, in networkx's order (components by smallest node; inside a
+    # component the nodes come out of a Python set filled in BFS order, as in the reference)
+    seen_all = np.zeros(ngroups, dtype=bool)
+    components = []
+    for v in range(ngroups):
+        if seen_all[v]:
+            continue
+        seen = {v}
+        nextlevel = [v]
+        while nextlevel:
+            thislevel, nextlevel = nextlevel, []
+            for u in thislevel:
+                for w in nbrs[u]:
+                    if w not in seen:
+                        seen.add(w)
+                        nextlevel.append(w)
+        for u in seen:
+            seen_all[u] = True
+        components.append(seen)
+    merged_components = [[]]
+    for c in components:
+        if len(merged_components[-1]) + len(c) > min_blip_size:
+            merged_components.append([])
+        merged_components[-1].extend(list(c))
+
+    # Step 3: candidate groups, locations = cliques of the (heuristic) edge clique cover
+    all_cand_groups = []
+    for component in merged_components:
+        component_cand_groups = []
+        component_groups = [[] for _ in component]
+        local = {g: i for i, g in enumerate(component)}
+        sub_nbrs = [sorted(local[w] for w in nbrs[g] if w in local) for g in component]
+        for cliquenum, clique in enumerate(_edge_clique_cover(sub_nbrs)):
+            for j in clique:
+                component_groups[j].append(cliquenum)
+        for ii, j in enumerate(component):
+            group = set(component_groups[ii])
+            data_dict = dict(radius=radii[j])
+            for k in range(d):
+                data_dict[f'dim{k}'] = centers[k, j]
+            data_dict['center'] = centers[:, j].tolist()
+            if count_signals:
+                key = keys[j]
+                nsignals = np.array([x for x in filtered_peps[key].keys() if x != 'pip'])
+                props = np.array([filtered_peps[key][n] for n in nsignals])
+                inds = np.argsort(-1 * props)
+                nsignals = nsignals[inds]
+                cumprops = np.cumsum(props[inds])
+                for ell in range(len(nsignals)):
+                    if cumprops[ell] >= 1 - max_pep:
+                        data_dict['nsignals'] = set(nsignals[0:(ell + 1)].tolist())
+                        component_cand_groups.append(CandidateGroup(
+                            group=group, pep=max(0, 1 - cumprops[ell]), data=copy.deepcopy(data_dict)))
+                    if cumprops[ell] >= 1 - min_pep:
+                        break
+            else:
+                component_cand_groups.append(CandidateGroup(group=group, pep=peps_arr[j], data=data_dict))
+        all_cand_groups.append(component_cand_groups)
+    return all_cand_groups, merged_components

@@ -302,3 +302,74 @@ extern "C" int blipgpu_gridcounts_free(blipgpu_gridcounts* r)
     delete r;
     return BLIP_OK;
 }
+
+
+// ---------------------------------------------------------------------------
+// Overlap (constraint) matrix of candidate regions: the O(G^2) step of
+// /root/reference/pyblip/create_groups_cts.py:283-308, in the reference's float32 arithmetic
+// (the file is compiled with -fmad=false, sqrtf is correctly rounded):
+//   squares: all_j |c_a[j] - c_b[j]| < r_a + r_b        circles: sqrt(sum_j (c_a[j] - c_b[j])^2) < r_a + r_b
+// Output: bit-packed rows, bit b of word [a][b / 32].  One warp per (row, 32-column word):
+// lane = column, one ballot per word.
+// ---------------------------------------------------------------------------
+namespace {
+__global__ void overlap_bits_kernel(const float* __restrict__ centers, const float* __restrict__ radii,
+                                    int64_t G, int d, int circle, int words, uint32_t* __restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t gw = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (gw >= G * words) return;
+    const int64_t a = gw / words;
+    const int w = (int)(gw % words);
+    const int64_t b = 32LL * w + lane;
+    bool hit = false;
+    if (b < G) {
+        const float delta = radii[a] + radii[b];
+        if (circle) {
+            float ssum = 0.f;
+            for (int j = 0; j < d; ++j) {
+                const float diff = centers[(int64_t)j * G + a] - centers[(int64_t)j * G + b];
+                const float sq = diff * diff;
+                ssum = j == 0 ? sq : ssum + sq;
+            }
+            hit = sqrtf(ssum) < delta;
+        } else {
+            hit = true;
+            for (int j = 0; j < d; ++j)
+                hit = hit && (fabsf(centers[(int64_t)j * G + a] - centers[(int64_t)j * G + b]) < delta);
+        }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (lane == 0) out[a * words + w] = m;
+}
+} // namespace
+
+extern "C" int blipgpu_overlap_bits(blipgpu_ctx* ctx, const float* centers, const float* radii, int64_t G,
+                                    int32_t d, int32_t circle, uint32_t* out_bits)
+{
+    BLIP_TRY(blip_ctx_activate(ctx));
+    if (!centers || !radii || !out_bits || G <= 0 || d <= 0) { blip_set_error("overlap_bits: bad arguments"); return BLIP_ERR_ARG; }
+    if (G > 131072) { blip_set_error("overlap_bits: at most 131072 regions (the bit matrix would exceed 2 GB)"); return BLIP_ERR_UNSUPPORTED; }
+    const int words = (int)((G + 31) / 32);
+    float *d_c = nullptr, *d_r = nullptr; uint32_t* d_o = nullptr;
+    cudaError_t e = cudaMalloc(&d_c, sizeof(float) * d * G);
+    if (e == cudaSuccess) e = cudaMalloc(&d_r, sizeof(float) * G);
+    if (e == cudaSuccess) e = cudaMalloc(&d_o, sizeof(uint32_t) * G * words);
+    cudaStream_t st = ctx->stream;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_c, centers, sizeof(float) * d * G, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_r, radii, sizeof(float) * G, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        ScopedTimer timer(ctx, false);
+        const int64_t nwarp = G * words;
+        overlap_bits_kernel<<<(unsigned)((nwarp + 7) / 8), 256, 0, st>>>(d_c, d_r, G, d, circle, words, d_o);
+        e = cudaGetLastError();
+        timer.stop(1);
+    }
+    int rc = BLIP_OK;
+    if (e == cudaSuccess) rc = blip_d2h(ctx, out_bits, d_o, sizeof(uint32_t) * G * words);
+    if (e != cudaSuccess) { blip_set_error("overlap_bits: %s", cudaGetErrorString(e)); rc = BLIP_ERR_CUDA; }
+    ctx->h2d_bytes += (int64_t)sizeof(float) * (d + 1) * G;
+    ctx->d2h_bytes += (int64_t)sizeof(uint32_t) * G * words;
+    cudaFree(d_c); cudaFree(d_r); cudaFree(d_o);
+    return rc;
+}
