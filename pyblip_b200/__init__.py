@@ -4,7 +4,7 @@ Same Python API as amspector100/pyblip for the multi-chain Gibbs samplers and th
 candidate-group PIP counting; everything numeric runs in libblipgpu.so
 (hand-written CUDA for sm_100a).  There is no CPU fallback.
 """
-from . import linear, probit, nprior, create_groups, changepoint
+from . import linear, probit, nprior, create_groups, create_groups_cts, changepoint
 from .linear import LinearSpikeSlab
 from .probit import ProbitSpikeSlab
 from .nprior import NPrior
