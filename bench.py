@@ -220,9 +220,11 @@ def run_reference_arm(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * res["seconds"], "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": 1e3 * res["seconds"], "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, impl="reference"),
+        "config": workload_config(args, impl="reference",
+                                  chains=CONFIG["chains"] * (int(os.environ.get("WORLD_SIZE", "1"))
+                                                             if args.scaling == "weak" else 1)),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": res["cores"], "kind": res["kind"],
                          "sample": res["sample"]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
