@@ -263,6 +263,11 @@ int blipgpu_count_groups(blipgpu_bits* b, const int64_t* offsets, const int64_t*
  * `_samples_dist_matrix` (create_groups.py:523-535): the correlation matrix follows from these
  * counts and N exactly.  p <= 16384 (use blipgpu_bits_select_columns first). */
 int blipgpu_count_pairs(blipgpu_bits* b, int64_t* pair_counts, int32_t out_is_device);
+/* *count = #rows in which at least one of the given groups has no non-zero column: the exact
+ * family-wise error count of a selection of groups (pyblip/blip.py:270-276, evaluated up to 100
+ * times by the FWER binary search).  offsets/members as in blipgpu_count_groups. */
+int blipgpu_count_false_rows(blipgpu_bits* b, const int64_t* offsets, const int64_t* members,
+                             int64_t n_groups, int64_t* count, int32_t out_is_device);
 int blipgpu_bits_free(blipgpu_bits* b);
 
 /* ---- continuous-space candidate regions -------------------------------- */

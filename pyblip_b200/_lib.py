@@ -33,7 +33,7 @@ SYMBOLS = [
     "blipgpu_samples_csr", "blipgpu_samples_latents", "blipgpu_samples_free",
     "blipgpu_bits_from_samples", "blipgpu_bits_from_dense", "blipgpu_bits_shape",
     "blipgpu_bits_select_columns", "blipgpu_bits_to_dense",
-    "blipgpu_count_columns", "blipgpu_count_sequential", "blipgpu_count_groups", "blipgpu_count_pairs",
+    "blipgpu_count_columns", "blipgpu_count_sequential", "blipgpu_count_groups", "blipgpu_count_pairs", "blipgpu_count_false_rows",
     "blipgpu_bits_free",
     "blipgpu_grid_count", "blipgpu_gridcounts_sizes", "blipgpu_gridcounts_get", "blipgpu_gridcounts_free",
     "blipgpu_overlap_bits",
@@ -513,6 +513,21 @@ class Bits:
                                               C.c_void_p(members.ctypes.data), C.c_int64(G),
                                               C.c_void_p(out.ctypes.data), C.c_int32(0)))
         return out
+
+    def count_false_rows(self, groups):
+        """#rows in which at least one of `groups` has no non-zero column (exact FWER numerator)."""
+        G = len(groups)
+        offsets = np.zeros(G + 1, dtype=np.int64)
+        for i, g in enumerate(groups):
+            offsets[i + 1] = offsets[i] + len(g)
+        members = np.fromiter((int(j) for g in groups for j in g), dtype=np.int64, count=int(offsets[-1]))
+        if members.size == 0:
+            members = np.zeros(1, dtype=np.int64)
+        out = np.zeros(1, dtype=np.int64)
+        check(load().blipgpu_count_false_rows(self._h, C.c_void_p(offsets.ctypes.data),
+                                              C.c_void_p(members.ctypes.data), C.c_int64(G),
+                                              C.c_void_p(out.ctypes.data), C.c_int32(0)))
+        return int(out[0])
 
     def count_pairs(self):
         """#rows in which both columns are non-zero, for every pair of columns (int64[p, p])."""

@@ -86,6 +86,10 @@ class _DeviceSamples:
             return np.zeros(0, dtype=np.int64)
         return dist.allreduce_counts(self.bits.count_groups(groups))
 
+    def false_rows(self, groups):
+        return int(dist.allreduce_scalar(self.bits.count_false_rows(groups)) if dist.world()[1] > 1
+                   else self.bits.count_false_rows(groups))
+
     def pair_counts(self):
         return dist.allreduce_counts(self.bits.count_pairs())
 
@@ -429,3 +433,18 @@ def all_cand_groups(
 def _prefilter(cand_groups, max_pep):
     """Returns the subset of cand_groups with a pep below max_pep."""
     return [x for x in cand_groups if x.pep < max_pep]
+
+
+def selection_fwer(samples, groups):
+    """Exact family-wise error rate of a selection: the fraction of posterior samples in which
+    at least one selected group contains no signal -- the quantity the reference's FWER binary
+    search recomputes from the full sample matrix in every iteration (blip.py:270-276).
+    ``samples``: array, fitted sampler or device handle; ``groups``: iterable of index collections
+    (or CandidateGroups)."""
+    dev = _as_device(samples)
+    try:
+        glist = [sorted(getattr(g, "group", g)) for g in groups]
+        return dev.false_rows(glist) / dev.N
+    finally:
+        if dev is not samples:
+            dev.close()

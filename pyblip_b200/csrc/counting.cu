@@ -302,6 +302,39 @@ __global__ void __launch_bounds__(CT_BLOCK) count_pairs_kernel(
     }
 }
 
+// ---- exact FWER of a selection: rows in which SOME selected group holds no signal ------------
+// (blip.py:270-275: false_disc |= all(samples[:, group] == 0, axis=1), then the mean).
+// grid (chunks); lane = row; every thread walks all selected groups for its row and stops at the
+// first empty one.  Group lists are small (a selection), member words are re-read from L1/L2.
+__global__ void __launch_bounds__(CT_BLOCK) count_false_rows_kernel(
+    const uint32_t* __restrict__ bits, int64_t N, int64_t N_pad, const int64_t* __restrict__ offsets,
+    const int32_t* __restrict__ members, int n_groups, unsigned long long* __restrict__ out)
+{
+    __shared__ int s_cnt[CT_NWARP];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int cnt = 0;
+    for (int64_t r = (int64_t)blockIdx.x * CT_BLOCK + threadIdx.x; r < N; r += (int64_t)gridDim.x * CT_BLOCK) {
+        bool false_disc = false;
+        for (int g = 0; g < n_groups && !false_disc; ++g) {
+            uint32_t any = 0u;
+            for (int64_t k = offsets[g]; k < offsets[g + 1] && !any; ++k) {
+                const int cidx = members[k];
+                any = (bits[(int64_t)(cidx >> 5) * N_pad + r] >> (cidx & 31)) & 1u;
+            }
+            false_disc = !any;
+        }
+        cnt += false_disc ? 1 : 0;
+    }
+    cnt = warp_sum_int(cnt);
+    if (lane == 0) s_cnt[warp] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int i = 0; i < CT_NWARP; ++i) t += s_cnt[i];
+        if (t) atomicAdd(out, (unsigned long long)t);
+    }
+}
+
 int alloc_bits(blipgpu_ctx* ctx, int64_t N, int64_t p, blipgpu_bits** out)
 {
     blipgpu_bits* b = new (std::nothrow) blipgpu_bits();
@@ -533,6 +566,34 @@ extern "C" int blipgpu_count_groups(blipgpu_bits* b, const int64_t* offsets, con
         if (b->N == 0) return;
         // grid.x is limited to 2^31-1 groups; grid.y to 65535 chunks
         count_groups_kernel<<<dim3((unsigned)n_groups, chunks), CT_BLOCK, 0, st>>>(b->bits, b->N, b->N_pad, d_off, d_mem, rpb, dev);
+    });
+    cudaFree(d_off); cudaFree(d_mem);
+    return rc;
+}
+
+extern "C" int blipgpu_count_false_rows(blipgpu_bits* b, const int64_t* offsets, const int64_t* members,
+                                        int64_t n_groups, int64_t* count, int32_t out_is_device)
+{
+    if (!b || n_groups < 0 || !count || (n_groups > 0 && (!offsets || !members))) { blip_set_error("count_false_rows: bad arguments"); return BLIP_ERR_ARG; }
+    BLIP_TRY(blip_ctx_activate(b->ctx));
+    const int64_t total = n_groups > 0 ? offsets[n_groups] : 0;
+    std::vector<int32_t> m32((size_t)std::max<int64_t>(total, 1));
+    for (int64_t i = 0; i < total; ++i) {
+        if (members[i] < 0 || members[i] >= b->p) { blip_set_error("count_false_rows: member %lld out of range", (long long)members[i]); return BLIP_ERR_ARG; }
+        m32[(size_t)i] = (int32_t)members[i];
+    }
+    int64_t* d_off = nullptr; int32_t* d_mem = nullptr;
+    cudaStream_t st = b->ctx->stream;
+    cudaError_t e = cudaMalloc(&d_off, sizeof(int64_t) * (n_groups + 1));
+    if (e == cudaSuccess) e = cudaMalloc(&d_mem, sizeof(int32_t) * std::max<int64_t>(total, 1));
+    const int64_t zero = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_off, n_groups > 0 ? offsets : &zero, sizeof(int64_t) * (n_groups + 1), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && total > 0) e = cudaMemcpyAsync(d_mem, m32.data(), sizeof(int32_t) * total, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) { cudaFree(d_off); cudaFree(d_mem); blip_set_error("count_false_rows: %s", cudaGetErrorString(e)); return BLIP_ERR_CUDA; }
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((b->N + CT_BLOCK - 1) / CT_BLOCK, 8LL * b->ctx->sm_count));
+    int rc = with_output(b->ctx, 1, count, out_is_device, [&](unsigned long long* dev) {
+        if (b->N == 0 || n_groups == 0) return;
+        count_false_rows_kernel<<<grid, CT_BLOCK, 0, st>>>(b->bits, b->N, b->N_pad, d_off, d_mem, (int)n_groups, dev);
     });
     cudaFree(d_off); cudaFree(d_mem);
     return rc;

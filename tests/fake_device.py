@@ -26,6 +26,12 @@ class NumpyDeviceSamples:
             return np.zeros(0, dtype=np.int64)
         return dist.allreduce_counts(co.group_any_counts(self.S, groups))
 
+    def false_rows(self, groups):
+        fd = np.zeros(self.S.shape[0], dtype=bool)
+        for g in groups:
+            fd |= np.all(self.S[:, list(g)] == 0, axis=1)
+        return int(dist.allreduce_scalar(int(fd.sum())) if dist.world()[1] > 1 else fd.sum())
+
     def pair_counts(self):
         Si = self.S.astype(np.int64)
         return dist.allreduce_counts(Si.T @ Si)

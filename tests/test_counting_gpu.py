@@ -137,3 +137,22 @@ def test_pair_counts_and_device_correlation_path(gpu, monkeypatch):
             cnt, N = ind[:, cols].any(axis=1).sum(), ind.shape[0]
             # hierarchical groups: 1 - mean(any) (:459); sequential groups: mean(all zero) (:329-332)
             assert g.pep in (1 - cnt / N, (N - cnt) / N)
+
+
+def test_selection_fwer_equals_the_reference_row_scan(gpu):
+    """blip.py:270-276: false_disc |= all(samples[:, group] == 0, axis=1); fwer = mean -- exact."""
+    from pyblip_b200 import create_groups as cg
+    rng = np.random.default_rng(4)
+    for N, p in [(1, 3), (77, 40), (30011, 333)]:
+        S = rng.random((N, p)) < 0.2
+        for ng in (0, 1, 5, 40):
+            groups = [sorted(rng.choice(p, size=int(rng.integers(1, min(p, 6) + 1)), replace=False).tolist())
+                      for _ in range(ng)]
+            fd = np.zeros(N, dtype=bool)
+            for g in groups:
+                fd = fd | np.all(S[:, g] == 0, axis=1)
+            assert cg.selection_fwer(S, groups) == fd.mean(), (N, p, ng)
+    groups = [cg.CandidateGroup(group={1, 2}, pep=0.1), cg.CandidateGroup(group={5}, pep=0.2)]
+    S = rng.random((500, 8)) < 0.5
+    want = (np.all(S[:, [1, 2]] == 0, axis=1) | np.all(S[:, [5]] == 0, axis=1)).mean()
+    assert cg.selection_fwer(S, groups) == want
