@@ -123,19 +123,54 @@ class ClockSampler:
 _REF_DATA = {}
 
 
+_HP = dict(tau2=1.0, update_tau2=1, tau2_a0=2.0, tau2_b0=1.0, sigma2=1.0, update_sigma2=1, sigma2_a0=2.0,
+           sigma2_b0=1.0, p0=0.9, update_p0=1, min_p0=0.0, p0_a0=1.0, p0_b0=1.0)
+
+
 def _ref_worker(nsweeps):
-    """One chain of `_sample_spikeslab` (pyblip/linear/_linear.pyx:34) for nsweeps sweeps."""
-    from pyblip.linear._linear import _sample_spikeslab
-    X, y = _REF_DATA["X"], _REF_DATA["y"]
+    """One chain of the reference's compiled kernel for nsweeps sweeps.  kind "linear" / "probit":
+    `_sample_spikeslab` (pyblip/linear/_linear.pyx:34); "block": `_sample_spikeslab_multi`
+    (pyblip/linear/_linear_multi.pyx:271); "nprior": `_nprior_sample` (pyblip/nprior/_nprior.pyx:56)."""
+    X, y, kind, kw = _REF_DATA["X"], _REF_DATA["y"], _REF_DATA.get("kind", "linear"), _REF_DATA.get("kw", {})
+    if kind == "nprior" and "blas" not in _REF_DATA:
+        # one chain per core: the nprior kernel's level-3 BLAS / LAPACK calls must stay single-threaded
+        # (16 workers x 16 BLAS threads ran 34x slower); the other kernels only make level-1 calls
+        try:
+            import threadpoolctl
+            _REF_DATA["blas"] = threadpoolctl.threadpool_limits(limits=1)
+        except Exception:
+            _REF_DATA["blas"] = None
     t0 = time.perf_counter()
-    _sample_spikeslab(N=nsweeps, X=X, y=y, z=np.zeros(1, dtype=np.int64), probit=0,
-                      tau2=1.0, update_tau2=1, tau2_a0=2.0, tau2_b0=1.0,
-                      sigma2=1.0, update_sigma2=1, sigma2_a0=2.0, sigma2_b0=1.0,
-                      p0=0.9, update_p0=1, min_p0=0.0, p0_a0=1.0, p0_b0=1.0)
+    if kind == "linear":
+        from pyblip.linear._linear import _sample_spikeslab
+        _sample_spikeslab(N=nsweeps, X=X, y=y, z=np.zeros(1, dtype=np.int64), probit=0, **_HP)
+    elif kind == "probit":
+        from pyblip.linear._linear import _sample_spikeslab
+        _sample_spikeslab(N=nsweeps, X=X, y=np.zeros(X.shape[0]), z=y.astype(np.int64), probit=1,
+                          **dict(_HP, update_sigma2=0))
+    elif kind == "block":
+        from pyblip.linear._linear_multi import _sample_spikeslab_multi
+        _sample_spikeslab_multi(N=nsweeps, bsize=kw.get("bsize", 3), X=X, y=y.copy(), z=np.zeros(1, dtype=np.int64),
+                                probit=0, max_signals_per_block=0, **_HP)
+    elif kind == "nprior":
+        from pyblip.nprior._nprior import _nprior_sample
+        import scipy.linalg
+        if not getattr(scipy.linalg.cholesky, "_f_ordered", False):
+            # scipy >= 1.18 returns a C-ordered factor; the reference (_nprior.pyx:352) takes `.T` of it into
+            # a C-contiguous memoryview, which only works with the Fortran-ordered factor of older scipy
+            chol = scipy.linalg.cholesky
+            scipy.linalg.cholesky = lambda a, *args, **kw: np.asfortranarray(chol(a, *args, **kw))
+            scipy.linalg.cholesky._f_ordered = True
+        p = X.shape[1]
+        _nprior_sample(N=nsweeps, X=X, y=y, tauw2=1.0, p0_init=1 - min(0.01, 1 / p), min_p0=1e-10, update_p0=1,
+                       sigma_a0=5.0, sigma_b0=1.0, alpha0_a0=1.0, alpha0_b0=1.0, sigma_prior_type=0,
+                       joint_sample_W=1, group_alpha_update=1, log_interval=nsweeps + 1, time0=0.0)
+    else:
+        raise ValueError(kind)
     return time.perf_counter() - t0
 
 
-def reference_throughput(X, y, sweeps, workers=None):
+def reference_throughput(X, y, sweeps, workers=None, kind="linear", **kw):
     """Coordinate-updates/s of the reference kernel with one chain per host core.
     Setup cost (XT copy etc.) is removed by differencing a short and a long run."""
     import multiprocessing as mp
@@ -143,9 +178,8 @@ def reference_throughput(X, y, sweeps, workers=None):
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     from oracle import ref_loader
     ref_loader.load()
-    kind = "reference"
     workers = workers or len(os.sched_getaffinity(0))
-    _REF_DATA["X"], _REF_DATA["y"] = X, y
+    _REF_DATA.update(X=X, y=y, kind=kind, kw=kw)
     short = max(2, sweeps // 10)
     ctx = mp.get_context("fork")
     with ctx.Pool(workers) as pool:
@@ -158,7 +192,7 @@ def reference_throughput(X, y, sweeps, workers=None):
         t_long = time.perf_counter() - t0
     dt = max(t_long - t_short, 1e-9)
     p = X.shape[1]
-    return dict(value=workers * p * sweeps / dt, seconds=dt, cores=workers, kind=kind,
+    return dict(value=workers * p * sweeps / dt, seconds=dt, cores=workers, kind="reference",
                 sample=f"{workers} chains (one per host core) x {sweeps} sweeps of the "
                        f"n={X.shape[0]}, p={p} workload; setup removed by differencing")
 
