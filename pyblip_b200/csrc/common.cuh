@@ -190,8 +190,10 @@ __device__ inline double rng_beta(const RngKey& key, uint32_t proposal, uint32_t
 // rejection otherwise: the algorithm of the reference's truncated-normal
 // primitive (/root/reference/pyblip/cython_utils/_truncnorm.pyx:42-86), attempts
 // drawn from the keyed sub-stream (kind, c0, c1).
+// `first_normal`, when given, is box_muller(rng_words(key, kind, c0, c1, 0)) computed ahead of
+// time by the caller (the first attempt of the normal-rejection branch does not depend on a).
 __device__ inline double truncnorm_std(const RngKey& key, uint32_t kind, uint32_t c0, uint32_t c1,
-                                       double a)
+                                       double a, const double* first_normal = nullptr)
 {
     // attempts are capped so that a NaN argument (upstream bug) cannot hang the GPU
     const uint32_t kMaxAttempts = 1u << 14;
@@ -206,6 +208,12 @@ __device__ inline double truncnorm_std(const RngKey& key, uint32_t kind, uint32_
             if (u2 <= rho) return y + a;
         }
     } else {
+        if (first_normal) {
+            double z = *first_normal;
+            attempt = 1;
+            if (a >= 0) z = fabs(z);
+            if (z >= a) return z;
+        }
         while (attempt < kMaxAttempts) {
             double z = box_muller(rng_words(key, kind, c0, c1, attempt++));
             if (a >= 0) z = fabs(z);
@@ -217,13 +225,14 @@ __device__ inline double truncnorm_std(const RngKey& key, uint32_t kind, uint32_
 
 // sample_truncnorm(mean, var, b, lower_interval)  (_truncnorm.pyx:88-107)
 __device__ inline double truncnorm(const RngKey& key, uint32_t kind, uint32_t c0, uint32_t c1,
-                                   double mean, double var, double b, int lower_interval)
+                                   double mean, double var, double b, int lower_interval,
+                                   const double* first_normal = nullptr)
 {
     double scale = sqrt(var);
     double a = (b - mean) / scale;
     double z;
-    if (lower_interval == 0) z = truncnorm_std(key, kind, c0, c1, a);
-    else z = -1 * truncnorm_std(key, kind, c0, c1, -1 * a);
+    if (lower_interval == 0) z = truncnorm_std(key, kind, c0, c1, a, first_normal);
+    else z = -1 * truncnorm_std(key, kind, c0, c1, -1 * a, first_normal);
     return mean + scale * z;
 }
 

@@ -34,7 +34,12 @@ struct blipgpu_nprior {
 namespace {
 
 constexpr int NP_BLOCK = 256;
+constexpr int NP_QT = 8;         // coordinates of q a thread keeps in registers while q is rebuilt
 constexpr int NP_AMAX_MIN = 512;   // the joint-W Cholesky workspace holds at least this many active coordinates
+
+// variates of one coordinate visit that do not depend on the state: spike uniform, normal of the w
+// draw, first normal of the truncated-normal rejection loop (sub-stream NP_TN, attempt 0)
+struct __align__(32) NPDraws { double u, z, tn0, pad; };
 
 struct NPParams {
     const double* G; int64_t ldg; const double* Xl2; const double* q0; double yy;
@@ -44,7 +49,9 @@ struct NPParams {
     // chain state
     double *alpha, *w, *beta;      // [chains][p]
     double* q;                     // [chains][p2]
+    NPDraws* uz;                   // [chains][p]: this sweep's state-independent variates by visiting position
     double* hs;                    // [chains][4]: sigma2, alpha0, p0, rr
+    int state_smem;                // alpha, w, q and ||X_j||^2 live in dynamic shared memory during the launch
     int amax;                      // capacity of the active-set workspace (<= p, sized from free memory)
     double* chol;                  // [chains][amax*amax]
     double* vec;                   // [chains][3*amax]
@@ -81,7 +88,8 @@ __device__ __forceinline__ double normcdf_d(double z) { return 0.5 * erfc(-z * s
 // Inputs: state of the coordinate BEFORE its visit; qj, rr of the current residual.
 struct NPVisit { double alpha_new, w_new, beta_new, qj_back, rr_back; bool stays_inactive; };
 
-__device__ inline NPVisit np_visit(const NPParams& P, const RngKey& key, int pos, int sweep, int64_t soff,
+__device__ inline NPVisit np_visit(const NPParams& P, const RngKey& key, int pos, int sweep, double u, double z,
+                                   double tn0, double log_p0,
                                    double alpha_old, double w_old, double xl2, double qj, double rr,
                                    double sigma2, double alpha0, double p0)
 {
@@ -100,22 +108,20 @@ __device__ inline NPVisit np_visit(const NPParams& P, const RngKey& key, int pos
     double t_alphaj = qb + r_scale * xl2;                       // X_j . (r' + r_scale X_j)
     t_alphaj = wj * t_alphaj / t_denom;
     const double rplus2 = rrb + 2.0 * r_scale * qb + r_scale * r_scale * xl2;
-    double log_kappa_num = log(p0);
+    double log_kappa_num = log_p0;
     log_kappa_num -= r2 / (2 * sigma2);
     double log_kappa_denom = log(1 - normcdf_d((alpha0 - t_alphaj) / sqrt(t_sigma2)));
     log_kappa_denom += log(t_sigma2) / 2 + (t_alphaj * t_alphaj / (2 * t_sigma2) - rplus2 / (2 * sigma2));
     const double ratio = exp(log_kappa_num - log_kappa_denom);
     const double kappa = ratio / (1.0 + ratio);
-    const double u = P.u ? P.u[soff + pos] : rng_uniform(key, NP_U, pos, sweep, 0);
-    if (u < kappa) v.alpha_new = truncnorm(key, NP_TN, pos, sweep, 0.0, 1.0, alpha0, 1);
-    else v.alpha_new = truncnorm(key, NP_TN, pos, sweep, t_alphaj, t_sigma2, alpha0, 0);
+    if (u < kappa) v.alpha_new = truncnorm(key, NP_TN, pos, sweep, 0.0, 1.0, alpha0, 1, &tn0);
+    else v.alpha_new = truncnorm(key, NP_TN, pos, sweep, t_alphaj, t_sigma2, alpha0, 0, &tn0);
     // _update_wj (:543-586)
     const double Tj = fmax(v.alpha_new - alpha0, 0.0);
     const double sigma02 = P.cfg.sigma_prior_type == 0 ? 1.0 : sigma2;
     const double vj = xl2 * Tj * Tj + (sigma02 / P.cfg.tauw2);
     double mj = 0.0;
     if (Tj > 0) mj = qb * Tj / vj;
-    const double z = P.wz ? P.wz[soff + pos] : rng_normal(key, NP_WZ, pos, sweep, 0);
     v.w_new = sqrt(sigma2 / vj) * z + mj;
     v.beta_new = v.w_new * Tj;
     v.stays_inactive = (b_old == 0.0) && (v.beta_new == 0.0);
@@ -130,6 +136,12 @@ __device__ inline NPVisit np_visit(const NPParams& P, const RngKey& key, int pos
 // the column-by-column version streams A^3/6 elements through L2.
 constexpr int NPC_NB = 32, NPC_T = 64;
 struct NpCholSmem { double D[NPC_NB][NPC_NB + 1]; double Pr[NPC_T][NPC_NB + 1]; double Pc[NPC_T][NPC_NB + 1]; };
+
+// Active sets of at most NPS_A coordinates (the steady state of a sparse posterior) are factored
+// and solved entirely in shared memory; the storage is shared with the blocked factorisation.
+constexpr int NPS_A = 64;
+struct NpSmallSmem { double L[NPS_A][NPS_A + 1]; double tmu[NPS_A]; double wt[NPS_A]; };
+union NpSmem { NpCholSmem blocked; NpSmallSmem small; };
 
 __device__ inline void np_cholesky_blocked(double* L, int A, int* err, NpCholSmem* sm)
 {
@@ -227,22 +239,50 @@ __device__ inline void np_cholesky_blocked(double* L, int A, int* err, NpCholSme
     }
 }
 
+#ifdef NP_PHASE_CLOCKS
+#define NPH_DECL long long ph_t[12] = {0,0,0,0,0,0,0,0,0,0,0,0}; long long ph_last = clock64(); int ph_iter = 0;
+#define NPH(i) do { if (threadIdx.x == 0) { long long _n = clock64(); ph_t[i] += _n - ph_last; ph_last = _n; } } while (0)
+#define NPH_ITER (++ph_iter)
+#define NPH_PRINT do { if (threadIdx.x == 0 && blockIdx.x == 0 && (sweep < 6 || sweep % 50 == 0)) \
+    printf("sweep %d A %d iters %d | draws %lld ptp %lld chol %lld solve %lld qbuild %lld | eval %lld find %lld commit %lld qupd %lld rest %lld | tail %lld\n", sweep, A, ph_iter, \
+           ph_t[0], ph_t[1], ph_t[2], ph_t[3], ph_t[4], ph_t[5], ph_t[6], ph_t[7], ph_t[8], ph_t[9], ph_t[10]); printf("   fwd(incl. 2 div) %lld\n", ph_t[11]); } while (0)
+#else
+#define NPH_DECL
+#define NPH(i) do {} while (0)
+#define NPH_ITER do {} while (0)
+#define NPH_PRINT do {} while (0)
+#endif
+
 __global__ void __launch_bounds__(NP_BLOCK) nprior_kernel(NPParams P)
 {
     __shared__ double scratch[40];
     __shared__ double s_sigma2, s_alpha0, s_p0, s_rr, s_delta, s_w;
     __shared__ int s_j, s_A;
     __shared__ unsigned s_flags[NP_BLOCK / 32];
-    __shared__ NpCholSmem s_chol;
+    __shared__ NpSmem s_mem;
+    NpCholSmem& s_chol = s_mem.blocked;
     __shared__ int s_scan[NP_BLOCK / 32 + 2];
 
     const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int p = P.p, p2 = P.p2;
     const RngKey key = { P.k0, P.k1, P.chain_offset + (uint32_t)c };
-    double* alpha = P.alpha + (int64_t)c * p;
-    double* w = P.w + (int64_t)c * p;
+    // chain state: in dynamic shared memory for the whole launch when it fits (4 p doubles), else in
+    // the chain's global arrays; the code below only sees the pointers
+    extern __shared__ double np_dyn[];
+    double* const g_alpha = P.alpha + (int64_t)c * p;
+    double* const g_w = P.w + (int64_t)c * p;
+    double* const g_q = P.q + (int64_t)c * p2;
+    double* alpha = g_alpha; double* w = g_w; double* q = g_q;
+    const double* Xl2 = P.Xl2;
+    if (P.state_smem) {
+        alpha = np_dyn; w = np_dyn + p2; q = np_dyn + 2 * p2;
+        double* xs = np_dyn + 3 * p2;
+        for (int k = tid; k < p; k += NP_BLOCK) { alpha[k] = g_alpha[k]; w[k] = g_w[k]; q[k] = g_q[k]; xs[k] = P.Xl2[k]; }
+        for (int k = p + tid; k < p2; k += NP_BLOCK) q[k] = 0.0;
+        Xl2 = xs;
+    }
     double* beta = P.beta + (int64_t)c * p;
-    double* q = P.q + (int64_t)c * p2;
+    NPDraws* uz = P.uz + (int64_t)c * p;
     const int NP_AMAX = P.amax;
     double* L = P.chol + (int64_t)c * NP_AMAX * NP_AMAX;
     double* vec = P.vec + (int64_t)c * 3 * NP_AMAX;
@@ -254,11 +294,22 @@ __global__ void __launch_bounds__(NP_BLOCK) nprior_kernel(NPParams P)
 
     for (int s = 0; s < P.S; ++s) {
         const int sweep = P.sweep0 + s;
+        NPH_DECL
         const int64_t soff = ((int64_t)c * P.n_total + sweep) * p;      // injected arrays: full length
         const PermView perm_s = { P.perm, ((int64_t)c * P.perm_S + P.perm_s0 + s) * p, P.perm16 };
         const double sigma2 = s_sigma2, alpha0 = s_alpha0, p0 = s_p0;
-        if (*reinterpret_cast<volatile int*>(P.err) == 1) return;   // another chain outgrew the workspace: this launch is replayed
 
+        // the state-independent variates of the coordinate visits (spike uniform, normal of the w
+        // draw) are keyed by position: drawn once per sweep here, not at each re-evaluation
+        for (int pos = tid; pos < p; pos += NP_BLOCK) {
+            NPDraws d;
+            d.u = P.u ? P.u[soff + pos] : rng_uniform(key, NP_U, pos, sweep, 0);
+            d.z = P.wz ? P.wz[soff + pos] : rng_normal(key, NP_WZ, pos, sweep, 0);
+            d.tn0 = rng_normal(key, NP_TN, pos, sweep, 0);
+            d.pad = 0.0;
+            uz[pos] = d;
+        }
+        const double log_p0 = log(p0);
         // ---- step 1: w of this sweep (:132-140 joint draw, or the fresh 0.1*N(0,1) row :100)
         int nact = 0;
         for (int j0 = 0; j0 < p; j0 += NP_BLOCK) {                     // ordered compaction of the active set
@@ -282,52 +333,108 @@ __global__ void __launch_bounds__(NP_BLOCK) nprior_kernel(NPParams P)
         if (tid == 0) s_A = nact;
         __syncthreads();
         const int A = nact;
+        // another chain outgrew the workspace: this launch is replayed.  Report this chain's own
+        // active-set size first, so that one replay sizes the workspace for all chains.
+        if (*reinterpret_cast<volatile int*>(P.err) == 1) { if (tid == 0) atomicMax(P.err + 1, A); return; }
+        NPH(0);
         if (cf.joint_sample_W == 1 && A > 0) {
             if (A > NP_AMAX) { if (tid == 0) { atomicMax(P.err + 1, A); *P.err = 1; } return; }
-            // precision PTP = T G_AA T + I / tauw2  (:307-337), lower triangle
-            for (int e = tid; e < A * A; e += NP_BLOCK) {
-                const int r = e / A, cc = e % A;
-                if (cc <= r) {
-                    const int jr = act[r], jc = act[cc];
-                    double v = fmax(alpha[jr] - alpha0, 0.0) * fmax(alpha[jc] - alpha0, 0.0) * P.G[(int64_t)jr * P.ldg + jc];
-                    if (r == cc) v += 1 / cf.tauw2;
-                    L[r * A + cc] = v;
+            if (A <= NPS_A) {
+                // small active set: precision, factor and both solves in shared memory.  Same
+                // operation order per element as the global-memory path below.
+                NpSmallSmem& S = s_mem.small;
+                for (int e = tid; e < A * A; e += NP_BLOCK) {
+                    const int r = e / A, cc = e % A;
+                    if (cc <= r) {
+                        const int jr = act[r], jc = act[cc];
+                        double v = fmax(alpha[jr] - alpha0, 0.0) * fmax(alpha[jc] - alpha0, 0.0) * P.G[(int64_t)jr * P.ldg + jc];
+                        if (r == cc) v += 1 / cf.tauw2;
+                        S.L[r][cc] = v;
+                    }
                 }
-            }
-            __syncthreads();
-            // right-looking Cholesky in place.  Column k is scaled into a contiguous scratch vector
-            // first; the trailing update then walks the rows with the threads along a row
-            // (contiguous, coalesced) and two warps' worth of rows in flight per pass.
-            double* colk = vec + 2 * NP_AMAX;
-            if (A > 64) np_cholesky_blocked(L, A, P.err, &s_chol);
-            else for (int k = 0; k < A; ++k) {
-                if (tid == 0) {
-                    const double d = L[k * A + k];
-                    if (!(d > 0)) *P.err = 2;
-                    L[k * A + k] = sqrt(d);
+                for (int a = tid; a < A; a += NP_BLOCK) {
+                    const int j = act[a];
+                    S.tmu[a] = fmax(alpha[j] - alpha0, 0.0) * P.q0[j];                  // Phi y
+                    S.wt[a] = P.joint_act ? P.joint_act[soff + a] : rng_normal(key, NP_JOINT_ACT, a, sweep, 0);
                 }
                 __syncthreads();
-                const double d = L[k * A + k];
-                for (int r = k + 1 + tid; r < A; r += NP_BLOCK) { const double v = L[r * A + k] / d; L[r * A + k] = v; colk[r] = v; }
-                __syncthreads();
-                // rows are dealt to the warps, lanes run along the row (cc <= r)
-                for (int r = k + 1 + warp; r < A; r += NP_BLOCK / 32) {
-                    const double lrk = colk[r];
-                    double* row = L + (int64_t)r * A;
-                    for (int cc = k + 1 + lane; cc <= r; cc += 32) row[cc] -= lrk * colk[cc];
+                NPH(1);
+                // right-looking factorisation with ONE barrier per column: column k stays unscaled
+                // (L[r][k] sqrt(d_k)) while the trailing update uses L[r][k] L[c][k] / d_k, and all
+                // columns are scaled by 1 / sqrt(d_k) in one pass at the end
+                for (int k = 0; k < A; ++k) {
+                    const double d = S.L[k][k];
+                    if (tid == 0 && !(d > 0)) *P.err = 2;
+                    const double dinv = 1.0 / d;
+                    for (int r = k + 1 + warp; r < A; r += NP_BLOCK / 32) {
+                        const double lrk = S.L[r][k] * dinv;
+                        for (int cc = k + 1 + lane; cc <= r; cc += 32) S.L[r][cc] = fma(-lrk, S.L[cc][k], S.L[r][cc]);
+                    }
+                    __syncthreads();
+                }
+                for (int e = tid; e < A * A; e += NP_BLOCK) {
+                    const int r = e / A, cc = e % A;
+                    if (cc < r) S.L[r][cc] *= rsqrt(S.L[cc][cc]);
                 }
                 __syncthreads();
-            }
-            // mean and draw by triangular solves (:371-432); warp 0, lanes split the inner sums
-            double* tmu = vec; double* wt = vec + NP_AMAX;
-            for (int a = tid; a < A; a += NP_BLOCK) {
-                const int j = act[a];
-                tmu[a] = fmax(alpha[j] - alpha0, 0.0) * P.q0[j];                    // Phi y
-                wt[a] = P.joint_act ? P.joint_act[soff + a] : rng_normal(key, NP_JOINT_ACT, a, sweep, 0);
-            }
-            __syncthreads();
-            if (A > 64) {
-                // large systems: the whole block works on one row of L at a time (contiguous loads).
+                if (tid < A) S.L[tid][tid] = sqrt(S.L[tid][tid]);
+                __syncthreads();
+                NPH(2);
+                if (warp == 0) {
+                    // triangular solves in column (axpy) form, lane = row (rows lane and lane + 32):
+                    // forward L v = tmu, then backward L^T m = v and L^T s = z together
+                    const unsigned full = 0xffffffffu;
+                    const int r0 = lane, r1 = lane + 32;
+                    const double id0 = r0 < A ? 1.0 / S.L[r0][r0] : 0.0, id1 = r1 < A ? 1.0 / S.L[r1][r1] : 0.0;
+                    double t0 = r0 < A ? S.tmu[r0] : 0.0, t1 = r1 < A ? S.tmu[r1] : 0.0;
+                    for (int k = 0; k < A; ++k) {
+                        const double xk = __shfl_sync(full, k < 32 ? t0 * id0 : t1 * id1, k & 31);
+                        if (r0 == k) t0 = xk;
+                        if (r1 == k) t1 = xk;
+                        if (r0 > k && r0 < A) t0 = fma(-S.L[r0][k], xk, t0);
+                        if (r1 > k && r1 < A) t1 = fma(-S.L[r1][k], xk, t1);
+                    }
+                    NPH(11);
+                    double z0 = r0 < A ? S.wt[r0] : 0.0, z1 = r1 < A ? S.wt[r1] : 0.0;
+                    for (int k = A - 1; k >= 0; --k) {
+                        const double mk = __shfl_sync(full, k < 32 ? t0 * id0 : t1 * id1, k & 31);
+                        const double sk = __shfl_sync(full, k < 32 ? z0 * id0 : z1 * id1, k & 31);
+                        if (r0 == k) { t0 = mk; z0 = sk; }
+                        if (r1 == k) { t1 = mk; z1 = sk; }
+                        if (r0 < k) { const double l = S.L[k][r0]; t0 = fma(-l, mk, t0); z0 = fma(-l, sk, z0); }
+                        if (r1 < k) { const double l = S.L[k][r1]; t1 = fma(-l, mk, t1); z1 = fma(-l, sk, z1); }
+                    }
+                    if (r0 < A) { S.tmu[r0] = t0; S.wt[r0] = z0; }
+                    if (r1 < A) { S.tmu[r1] = t1; S.wt[r1] = z1; }
+                }
+                __syncthreads();
+                for (int a = tid; a < A; a += NP_BLOCK) w[act[a]] = S.wt[a] + S.tmu[a];
+                __syncthreads();
+            } else {
+                // large active set (early sweeps): precision PTP = T G_AA T + I / tauw2 (:307-337),
+                // lower triangle, in the chain's global workspace; blocked factorisation
+                for (int e = tid; e < A * A; e += NP_BLOCK) {
+                    const int r = e / A, cc = e % A;
+                    if (cc <= r) {
+                        const int jr = act[r], jc = act[cc];
+                        double v = fmax(alpha[jr] - alpha0, 0.0) * fmax(alpha[jc] - alpha0, 0.0) * P.G[(int64_t)jr * P.ldg + jc];
+                        if (r == cc) v += 1 / cf.tauw2;
+                        L[(int64_t)r * A + cc] = v;
+                    }
+                }
+                __syncthreads();
+                NPH(1);
+                np_cholesky_blocked(L, A, P.err, &s_chol);
+                NPH(2);
+                // mean and draw by triangular solves (:371-432)
+                double* tmu = vec; double* wt = vec + NP_AMAX;
+                for (int a = tid; a < A; a += NP_BLOCK) {
+                    const int j = act[a];
+                    tmu[a] = fmax(alpha[j] - alpha0, 0.0) * P.q0[j];                    // Phi y
+                    wt[a] = P.joint_act ? P.joint_act[soff + a] : rng_normal(key, NP_JOINT_ACT, a, sweep, 0);
+                }
+                __syncthreads();
+                // the whole block works on one row of L at a time (contiguous loads).
                 // forward  L v = tmu  by rows, with the partial sums reduced over the block;
                 // backward L^T m = v, L^T s = z  in axpy form: once x_r is known, row r of L updates
                 // the right-hand sides of all m < r.
@@ -349,44 +456,36 @@ __global__ void __launch_bounds__(NP_BLOCK) nprior_kernel(NPParams P)
                     }
                     __syncthreads();
                 }
-            } else if (warp == 0) {
-                for (int r = 0; r < A; ++r) {               // L v = tmu
-                    double acc = 0.0;
-                    for (int m = lane; m < r; m += 32) acc = fma(L[r * A + m], tmu[m], acc);
-                    acc = warp_sum(acc);
-                    if (lane == 0) tmu[r] = (tmu[r] - acc) / L[r * A + r];
-                    __syncwarp();
-                }
-                for (int r = A - 1; r >= 0; --r) {          // L^T m = v ; L^T s = z
-                    double acc = 0.0, acc2 = 0.0;
-                    for (int m = r + 1 + lane; m < A; m += 32) {
-                        const double l = L[m * A + r];
-                        acc = fma(l, tmu[m], acc); acc2 = fma(l, wt[m], acc2);
-                    }
-                    acc = warp_sum(acc); acc2 = warp_sum(acc2);
-                    if (lane == 0) {
-                        tmu[r] = (tmu[r] - acc) / L[r * A + r];
-                        wt[r] = (wt[r] - acc2) / L[r * A + r];
-                    }
-                    __syncwarp();
-                }
+                for (int a = tid; a < A; a += NP_BLOCK) w[act[a]] = wt[a] + tmu[a];
+                __syncthreads();
             }
-            __syncthreads();
-            for (int a = tid; a < A; a += NP_BLOCK) w[act[a]] = wt[a] + tmu[a];
-            __syncthreads();
         }
 
+        NPH(3);
         // ---- beta, q = X^T(y - X beta), rr  (:143-160)
         for (int j = tid; j < p; j += NP_BLOCK) beta[j] = w[j] * fmax(alpha[j] - alpha0, 0.0);
-        for (int k = tid; k < p2; k += NP_BLOCK) q[k] = k < p ? P.q0[k] : 0.0;
         __syncthreads();
         if (A <= NP_AMAX) {
-            for (int a = 0; a < A; ++a) {
-                const int j = act[a];
-                const double bj = beta[j];
-                for (int k = tid; k < p; k += NP_BLOCK) q[k] = fma(-bj, P.G[(int64_t)j * P.ldg + k], q[k]);
+            // each thread carries NP_QT of its coordinates in registers through the active columns
+            // (ascending, the order of the column-by-column form), so the loads are independent
+            for (int kt = 0; kt < p2; kt += NP_QT * NP_BLOCK) {
+                double acc[NP_QT];
+#pragma unroll
+                for (int i = 0; i < NP_QT; ++i) { const int k = kt + tid + i * NP_BLOCK; acc[i] = k < p ? P.q0[k] : 0.0; }
+#pragma unroll 2
+                for (int a = 0; a < A; ++a) {
+                    const int j = act[a];
+                    const double bj = beta[j];
+                    const double* g = P.G + (int64_t)j * P.ldg + kt + tid;
+#pragma unroll
+                    for (int i = 0; i < NP_QT; ++i) if (kt + tid + i * NP_BLOCK < p) acc[i] = fma(-bj, g[i * NP_BLOCK], acc[i]);
+                }
+#pragma unroll
+                for (int i = 0; i < NP_QT; ++i) { const int k = kt + tid + i * NP_BLOCK; if (k < p2) q[k] = acc[i]; }
             }
         } else {                                    // joint draw off and a large active set: scan all
+            for (int k = tid; k < p2; k += NP_BLOCK) q[k] = k < p ? P.q0[k] : 0.0;
+            __syncthreads();
             for (int j = 0; j < p; ++j) {
                 const double bj = beta[j];
                 if (bj != 0) for (int k = tid; k < p; k += NP_BLOCK) q[k] = fma(-bj, P.G[(int64_t)j * P.ldg + k], q[k]);
@@ -404,45 +503,60 @@ __global__ void __launch_bounds__(NP_BLOCK) nprior_kernel(NPParams P)
         // ---- coordinate loop (:163-198): a window of NP_BLOCK upcoming positions, one per thread, is
         // evaluated against the current state; the leading visits that stay inactive are committed
         // (they redraw alpha_j and w_j but leave r alone) and the first one that touches r is applied
+        NPH(4);
         int pos0 = 0;
         while (pos0 < p) {
+            NPH_ITER;
             const int T = min(NP_BLOCK, p - pos0);
             NPVisit v; v.stays_inactive = false;
             int j = 0; double a_old = 0, w_old = 0, xl2 = 0, qj = 0;
             bool change = false;
             if (tid < T) {
                 j = perm_s[pos0 + tid];
-                a_old = alpha[j]; w_old = w[j]; xl2 = P.Xl2[j]; qj = q[j];
-                if (w_old * fmax(a_old - alpha0, 0.0) != 0.0) change = true;     // active before: certain change
-                else {
-                    v = np_visit(P, key, pos0 + tid, sweep, soff, a_old, w_old, xl2, qj, s_rr, sigma2, alpha0, p0);
-                    change = !v.stays_inactive;
-                }
+                a_old = alpha[j]; w_old = w[j]; xl2 = Xl2[j]; qj = q[j];
+                // every visit is evaluated against the current state, active coordinates included: the
+                // first one that touches r is then applied as evaluated (active before => never inactive)
+                const NPDraws d = uz[pos0 + tid];
+                v = np_visit(P, key, pos0 + tid, sweep, d.u, d.z, d.tn0, log_p0, a_old, w_old, xl2, qj, s_rr, sigma2, alpha0, p0);
+                change = !v.stays_inactive;
             }
+            NPH(5);
             const unsigned m = __ballot_sync(0xffffffffu, change);
             if (lane == 0) s_flags[warp] = m;
             __syncthreads();
             int first = -1;
 #pragma unroll
             for (int wv = NP_BLOCK / 32 - 1; wv >= 0; --wv) if (s_flags[wv]) first = 32 * wv + __ffs(s_flags[wv]) - 1;
+            NPH(6);
             if (tid < T && (first < 0 || tid < first)) { alpha[j] = v.alpha_new; w[j] = v.w_new; }
             if (first >= 0 && tid == first) {
-                // an active coordinate was not evaluated speculatively; a flipping one was evaluated
-                // against the same state, re-evaluating is identical (keyed draws) and keeps one path
-                v = np_visit(P, key, pos0 + tid, sweep, soff, a_old, w_old, xl2, qj, s_rr, sigma2, alpha0, p0);
                 const double b_old = w_old * fmax(a_old - alpha0, 0.0);
                 alpha[j] = v.alpha_new; w[j] = v.w_new; beta[j] = v.beta_new;
                 s_rr = v.rr_back - 2.0 * v.beta_new * v.qj_back + v.beta_new * v.beta_new * xl2;
                 s_delta = v.beta_new - b_old; s_j = j;
             }
             __syncthreads();
+            NPH(7);
             if (first < 0) { pos0 += T; continue; }
             const double delta = s_delta; const int jstar = s_j;
-            if (delta != 0) for (int k = tid; k < p; k += NP_BLOCK) q[k] = fma(-delta, P.G[(int64_t)jstar * P.ldg + k], q[k]);
+            if (delta != 0) {
+                // the column is loaded into registers first: a store to q between two loads of G would
+                // serialise the round trips (q and G may alias as far as the compiler knows)
+                const double* gcol = P.G + (int64_t)jstar * P.ldg;
+                for (int kt = 0; kt < p; kt += NP_QT * NP_BLOCK) {
+                    double g[NP_QT];
+#pragma unroll
+                    for (int i = 0; i < NP_QT; ++i) { const int k = kt + tid + i * NP_BLOCK; g[i] = k < p ? __ldg(gcol + k) : 0.0; }
+#pragma unroll
+                    for (int i = 0; i < NP_QT; ++i) { const int k = kt + tid + i * NP_BLOCK; if (k < p) q[k] = fma(-delta, g[i], q[k]); }
+                }
+            }
             __syncthreads();
+            NPH(8);
             pos0 += first + 1;
         }
 
+        NPH(9);
         // ---- sigma2 (:510-537)
         {
             double w2 = 0.0;
@@ -506,8 +620,12 @@ __global__ void __launch_bounds__(NP_BLOCK) nprior_kernel(NPParams P)
             }
         }
         __syncthreads();
+        NPH(10);
+        NPH_PRINT;
     }
     if (tid == 0) { P.hs[4 * c] = s_sigma2; P.hs[4 * c + 1] = s_alpha0; P.hs[4 * c + 2] = s_p0; P.hs[4 * c + 3] = s_rr; }
+    if (P.state_smem)
+        for (int k = tid; k < p; k += NP_BLOCK) { g_alpha[k] = alpha[k]; g_w[k] = w[k]; g_q[k] = q[k]; }
 }
 
 __global__ void nprior_init_kernel(NPParams P)
@@ -590,19 +708,20 @@ extern "C" int blipgpu_sample_nprior(blipgpu_ctx* ctx, blipgpu_design* design, c
     }
     CUDA_TRY(cudaMalloc(&res->scal, sizeof(double) * 3 * res->rows));
 
-    DBuf d_alpha, d_w, d_beta, d_q, d_hs, d_chol, d_vec, d_act, d_err, d_q0, d_y, d_perm;
+    DBuf d_alpha, d_w, d_beta, d_q, d_uz, d_hs, d_chol, d_vec, d_act, d_err, d_q0, d_y, d_perm;
     DBuf i_u, i_wz, i_ai, i_wf, i_si, i_ja, i_jc, i_dz, i_ig, i_p0;
     BLIP_TRY(d_alpha.alloc(sizeof(double) * chains * p)); BLIP_TRY(d_w.alloc(sizeof(double) * chains * p));
     BLIP_TRY(d_beta.alloc(sizeof(double) * chains * p)); BLIP_TRY(d_q.alloc(sizeof(double) * chains * p2));
+    BLIP_TRY(d_uz.alloc(sizeof(NPDraws) * chains * p));
     BLIP_TRY(d_hs.alloc(sizeof(double) * chains * 4));
     // active-set workspace of the joint W draw: starts small and is doubled (with a replay of the
-    // launch, see below) when a chain's active set outgrows it; the limit is what a quarter of the
-    // free memory (at most 16 GB) can hold
+    // launch, see below) when a chain's active set outgrows it; the limit is what half of the
+    // free memory can hold
     int64_t amax_limit = p;
     {
         size_t free_b = 0, total_b = 0;
         CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-        const double budget = std::min(0.25 * (double)free_b, 16.0e9);
+        const double budget = 0.5 * (double)free_b;
         const int64_t fit = (int64_t)std::sqrt(budget / (8.0 * (double)chains));
         amax_limit = std::max<int64_t>(std::min<int64_t>(p, NP_AMAX_MIN), std::min<int64_t>(p, fit));
     }
@@ -630,9 +749,23 @@ extern "C" int blipgpu_sample_nprior(blipgpu_ctx* ctx, blipgpu_design* design, c
     memset(&P, 0, sizeof(P));
     P.G = design->G; P.ldg = design->ldg; P.Xl2 = design->Xl2; P.q0 = d_q0.as<double>(); P.yy = yy;
     P.n = (int)n; P.p = (int)p; P.p2 = (int)p2; P.cfg = *cfg;
+    // chain state in shared memory when 4 p doubles fit next to the kernel's static shared memory
+    size_t dyn_smem = 0;
+    {
+        cudaFuncAttributes fa;
+        CUDA_TRY(cudaFuncGetAttributes(&fa, nprior_kernel));
+        const size_t want = sizeof(double) * 4 * (size_t)p2;
+        const size_t room = (size_t)ctx->smem_optin > fa.sharedSizeBytes + 1024 ? (size_t)ctx->smem_optin - fa.sharedSizeBytes - 1024 : 0;
+        if (want <= room) {
+            dyn_smem = want;
+            CUDA_TRY(cudaFuncSetAttribute(nprior_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+        }
+        P.state_smem = dyn_smem ? 1 : 0;
+    }
     P.min_alpha0 = norm_quantile_apprx_hd(cfg->min_p0);
     P.sigma_a = n / 2.0 + cfg->sigma_a0 + (cfg->sigma_prior_type != 0 ? p / 2.0 : 0.0);
     P.alpha = d_alpha.as<double>(); P.w = d_w.as<double>(); P.beta = d_beta.as<double>(); P.q = d_q.as<double>();
+    P.uz = d_uz.as<NPDraws>();
     P.amax = (int)NP_AMAX;
     P.hs = d_hs.as<double>(); P.chol = d_chol.as<double>(); P.vec = d_vec.as<double>(); P.act = d_act.as<int>();
     P.err = d_err.as<int>();
@@ -686,7 +819,7 @@ extern "C" int blipgpu_sample_nprior(blipgpu_ctx* ctx, blipgpu_design* design, c
         for (;;) {
             P.amax = (int)NP_AMAX; P.chol = d_chol.as<double>(); P.vec = d_vec.as<double>(); P.act = d_act.as<int>();
             ScopedTimer timer(ctx, true);
-            nprior_kernel<<<(unsigned)chains, NP_BLOCK, 0, st>>>(P);
+            nprior_kernel<<<(unsigned)chains, NP_BLOCK, dyn_smem, st>>>(P);
             CUDA_TRY(cudaGetLastError());
             res->sweep_ms += timer.stop(1);
             int errv[2] = { 0, 0 };
@@ -718,7 +851,7 @@ extern "C" int blipgpu_nprior_get(blipgpu_nprior* r, int32_t which, double* out)
     if (!r || !out || which < 0 || which > 5) { blip_set_error("nprior_get: bad arguments"); return BLIP_ERR_ARG; }
     BLIP_TRY(blip_ctx_activate(r->ctx));
     if (which < 3) {
-        CUDA_TRY(cudaMemcpy(out, r->dense[which], sizeof(double) * r->rows * r->p, cudaMemcpyDeviceToHost));
+        BLIP_TRY(blip_d2h(r->ctx, out, r->dense[which], sizeof(double) * r->rows * r->p));
         r->ctx->d2h_bytes += (int64_t)sizeof(double) * r->rows * r->p;
     } else {
         CUDA_TRY(cudaMemcpy(out, r->scal + (which - 3) * r->rows, sizeof(double) * r->rows, cudaMemcpyDeviceToHost));
