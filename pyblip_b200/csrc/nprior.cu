@@ -195,47 +195,69 @@ __device__ inline void np_cholesky_blocked(double* L, int A, int* err, NpCholSme
             for (int j = 0; j < NPC_NB; ++j) if (j < nb) row[j] = x[j];
         }
         __syncthreads();
-        // (3) trailing update L[r][c] -= sum_j P[r][j] P[c][j], r >= c >= r0, 64 x 64 tiles
-        const int tr = (tid >> 4) * 4, tc = (tid & 15) * 4;          // this thread's 4 x 4 outputs in a tile
+        // (3) trailing update L[r][c] -= sum_j P[r][j] P[c][j], r >= c >= r0, 64 x 64 tiles.
+        // A thread owns the 4 x 4 outputs (tr + 16 a, tc + 16 b): the 16 lanes of a half-warp read 16
+        // different panel rows (row stride 33 doubles: conflict-free) and write 128-byte row segments.
+        // The outputs are loaded into the accumulators before the panel strip is staged, and the next
+        // strip is fetched into registers while this one is multiplied, so global latency is covered.
+        const int tr = tid >> 4, tc = tid & 15;
+        constexpr int NPF = NPC_T * NPC_NB / NP_BLOCK;                 // strip elements a thread stages
         for (int rb = r0; rb < A; rb += NPC_T) {
+            __syncthreads();
             for (int e = tid; e < NPC_T * NPC_NB; e += NP_BLOCK) {    // panel strip of the row block
                 const int r = e / NPC_NB, j = e % NPC_NB;
                 sm->Pr[r][j] = (rb + r < A && j < nb) ? L[(int64_t)(rb + r) * A + kb + j] : 0.0;
             }
+            double nxt[NPF];
+#pragma unroll
+            for (int i = 0; i < NPF; ++i) {
+                const int e = tid + i * NP_BLOCK, r = e / NPC_NB, j = e % NPC_NB;
+                nxt[i] = (r0 + r < A && j < nb) ? L[(int64_t)(r0 + r) * A + kb + j] : 0.0;
+            }
             for (int cb = r0; cb <= rb; cb += NPC_T) {
-                __syncthreads();
-                for (int e = tid; e < NPC_T * NPC_NB; e += NP_BLOCK) {
-                    const int r = e / NPC_NB, j = e % NPC_NB;
-                    sm->Pc[r][j] = (cb + r < A && j < nb) ? L[(int64_t)(cb + r) * A + kb + j] : 0.0;
-                }
-                __syncthreads();
                 double acc[4][4];
 #pragma unroll
-                for (int a = 0; a < 4; ++a)
+                for (int a = 0; a < 4; ++a) {
+                    const int r = rb + tr + 16 * a;
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+                    for (int b = 0; b < 4; ++b) {
+                        const int c2 = cb + tc + 16 * b;
+                        acc[a][b] = (r < A && c2 <= r) ? L[(int64_t)r * A + c2] : 0.0;
+                    }
+                }
+                __syncthreads();                                      // previous tile done with Pc
+#pragma unroll
+                for (int i = 0; i < NPF; ++i) { const int e = tid + i * NP_BLOCK; sm->Pc[e / NPC_NB][e % NPC_NB] = nxt[i]; }
+                __syncthreads();
+                if (cb + NPC_T <= rb) {
+#pragma unroll
+                    for (int i = 0; i < NPF; ++i) {
+                        const int e = tid + i * NP_BLOCK, r = e / NPC_NB, j = e % NPC_NB;
+                        nxt[i] = (cb + NPC_T + r < A && j < nb) ? L[(int64_t)(cb + NPC_T + r) * A + kb + j] : 0.0;
+                    }
+                }
 #pragma unroll 8
                 for (int j = 0; j < NPC_NB; ++j) {
                     double pr[4], pc[4];
 #pragma unroll
-                    for (int a = 0; a < 4; ++a) { pr[a] = sm->Pr[tr + a][j]; pc[a] = sm->Pc[tc + a][j]; }
+                    for (int a = 0; a < 4; ++a) { pr[a] = sm->Pr[tr + 16 * a][j]; pc[a] = sm->Pc[tc + 16 * a][j]; }
 #pragma unroll
                     for (int a = 0; a < 4; ++a)
 #pragma unroll
-                        for (int b = 0; b < 4; ++b) acc[a][b] = fma(pr[a], pc[b], acc[a][b]);
+                        for (int b = 0; b < 4; ++b) acc[a][b] = fma(-pr[a], pc[b], acc[a][b]);
                 }
 #pragma unroll
                 for (int a = 0; a < 4; ++a) {
-                    const int r = rb + tr + a;
+                    const int r = rb + tr + 16 * a;
 #pragma unroll
                     for (int b = 0; b < 4; ++b) {
-                        const int c2 = cb + tc + b;
-                        if (r < A && c2 <= r) L[(int64_t)r * A + c2] -= acc[a][b];
+                        const int c2 = cb + tc + 16 * b;
+                        if (r < A && c2 <= r) L[(int64_t)r * A + c2] = acc[a][b];
                     }
                 }
             }
-            __syncthreads();
         }
+        __syncthreads();
     }
 }
 
@@ -243,8 +265,8 @@ __device__ inline void np_cholesky_blocked(double* L, int A, int* err, NpCholSme
 #define NPH_DECL long long ph_t[12] = {0,0,0,0,0,0,0,0,0,0,0,0}; long long ph_last = clock64(); int ph_iter = 0;
 #define NPH(i) do { if (threadIdx.x == 0) { long long _n = clock64(); ph_t[i] += _n - ph_last; ph_last = _n; } } while (0)
 #define NPH_ITER (++ph_iter)
-#define NPH_PRINT do { if (threadIdx.x == 0 && blockIdx.x == 0 && (sweep < 6 || sweep % 50 == 0)) \
-    printf("sweep %d A %d iters %d | draws %lld ptp %lld chol %lld solve %lld qbuild %lld | eval %lld find %lld commit %lld qupd %lld rest %lld | tail %lld\n", sweep, A, ph_iter, \
+#define NPH_PRINT do { if (threadIdx.x == 0 && ((blockIdx.x == 0 && (sweep < 6 || sweep % 50 == 0)) || A > 300 || ph_iter > 400)) \
+    printf("chain %d sweep %d A %d iters %d | draws %lld ptp %lld chol %lld solve %lld qbuild %lld | eval %lld find %lld commit %lld qupd %lld rest %lld | tail %lld\n", (int)blockIdx.x, sweep, A, ph_iter, \
            ph_t[0], ph_t[1], ph_t[2], ph_t[3], ph_t[4], ph_t[5], ph_t[6], ph_t[7], ph_t[8], ph_t[9], ph_t[10]); printf("   fwd(incl. 2 div) %lld\n", ph_t[11]); } while (0)
 #else
 #define NPH_DECL
@@ -253,7 +275,7 @@ __device__ inline void np_cholesky_blocked(double* L, int A, int* err, NpCholSme
 #define NPH_PRINT do {} while (0)
 #endif
 
-__global__ void __launch_bounds__(NP_BLOCK) nprior_kernel(NPParams P)
+__global__ void __launch_bounds__(NP_BLOCK, 2) nprior_kernel(NPParams P)
 {
     __shared__ double scratch[40];
     __shared__ double s_sigma2, s_alpha0, s_p0, s_rr, s_delta, s_w;
