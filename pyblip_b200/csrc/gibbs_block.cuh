@@ -97,7 +97,11 @@ __device__ __forceinline__ double block_model_lp_t(uint32_t mask, const double* 
             double sacc = Q[i][j];
 #pragma unroll
             for (int k = 0; k < j; ++k) sacc -= Q[i][k] * Q[j][k];
-            Q[i][j] = sacc / d;
+            // an entry outside the model is an exact 0 / d; dividing 1.0 instead and discarding the
+            // quotient keeps the whole warp out of the division's zero-numerator slow path
+            const bool in = ((mask >> i) & 1u) && ((mask >> j) & 1u);
+            const double qt = (in ? sacc : 1.0) / d;
+            Q[i][j] = in ? qt : 0.0;
         }
     }
     if (!ok) return nan("");
@@ -107,8 +111,10 @@ __device__ __forceinline__ double block_model_lp_t(uint32_t mask, const double* 
         double sacc = ((mask >> a) & 1u) ? x[a] : 0.0;
 #pragma unroll
         for (int k = 0; k < a; ++k) sacc -= Q[a][k] * yv[k];
-        yv[a] = sacc / Q[a][a];
-        if ((mask >> a) & 1u) nrm2 += yv[a] * yv[a];
+        const bool in = (mask >> a) & 1u;
+        const double qt = (in ? sacc : 1.0) / Q[a][a];
+        yv[a] = in ? qt : 0.0;
+        if (in) nrm2 += yv[a] * yv[a];
     }
     const int m = __popc(mask);
     double nrm = sqrt(nrm2);
@@ -168,6 +174,27 @@ __device__ inline bool block_draw(uint32_t mask, int bsize, const double* A, con
     int m = 0;
     for (int jj = 0; jj < bsize; ++jj) { out[jj] = 0.0; if (mask & (1u << jj)) mem[m++] = jj; }
     const double cm = tau2 / sigma2;
+    if (m == 1) {
+        // one member (the usual draw in the stationary regime): the operations of the general path
+        // below on 1 x 1 matrices, in the same order, without the local-memory matrices
+        const double a11 = A[mem[0] * bsize + mem[0]], x1 = x[mem[0]];
+        double l = 1.0 + cm * a11;
+        if (!(l > 0.0)) return false;
+        l = sqrt(l);
+        double mu1 = x1 / l; mu1 = mu1 / l;
+        double s1 = 0.0; s1 += a11 * mu1;
+        const double t1 = cm * s1;
+        mu1 = t1 - x1; mu1 *= -1 * tau2 / sigma2;
+        double w1 = a11 / l; w1 = w1 / l;
+        const double c2s = -1 * tau2 * tau2 / sigma2, c3s = tau2 * tau2 * tau2 / (sigma2 * sigma2);
+        double vs = 0.0; vs += a11 * w1;
+        double v = tau2; v += c2s * a11; v += c3s * vs;
+        if (!(v > 0.0)) return false;
+        v = sqrt(v);
+        double o = 0.0; o += v * zn[0];
+        out[mem[0]] = o + mu1;
+        return true;
+    }
     double Am[BK_MAXB * BK_MAXB], L[BK_MAXB * BK_MAXB], W[BK_MAXB * BK_MAXB], V[BK_MAXB * BK_MAXB];
     double xm[BK_MAXB], mu[BK_MAXB], t[BK_MAXB];
     for (int a = 0; a < m; ++a) {
@@ -242,7 +269,21 @@ struct BlockShared {
     int mem[BK_MAXB];
     double bold[BK_MAXB], bnew[BK_MAXB], xatr[BK_MAXB], A[BK_MAXB * BK_MAXB];
     unsigned flags[GB_NWARP];
+    unsigned failb[GB_NWARP];          // lanes of each warp whose window score hit a failed factorisation
+    double zn[BK_MAXB];                // normals of the coefficient draw
 };
+
+#ifdef BK_PHASE_CLOCKS
+#define BPH_DECL long long bph[10] = {0,0,0,0,0,0,0,0,0,0}; long long bph_last = clock64();
+#define BPH(i) do { if (threadIdx.x == 0) { long long _n = clock64(); bph[i] += _n - bph_last; bph_last = _n; } } while (0)
+#define BPH_PRINT do { if (threadIdx.x == 0 && blockIdx.x == 0 && (sweep % 16 == 0)) \
+    printf("sweep %d windows %lld applied %lld | start %lld score %lld find %lld | stats %lld rescore+draw %lld writeback %lld | epilogue %lld\n", sweep, \
+           n_windows, n_changes, bph[0], bph[1], bph[2], bph[3], bph[4], bph[5], bph[6]); } while (0)
+#else
+#define BPH_DECL
+#define BPH(i) do {} while (0)
+#define BPH_PRINT do {} while (0)
+#endif
 
 template <bool GRAM, bool PROBIT>
 __global__ void __launch_bounds__(GB_BLOCK, 2) gibbs_block_kernel(SweepParams P)
@@ -317,6 +358,7 @@ __global__ void __launch_bounds__(GB_BLOCK, 2) gibbs_block_kernel(SweepParams P)
 
     for (int s = 0; s < P.S; ++s) {
         const int sweep = P.sweep0 + s;
+        BPH_DECL
         const double* u_s = P.u ? P.u + ((int64_t)c * P.S + s) * nblock : nullptr;
         const double* z_s = P.z ? P.z + ((int64_t)c * P.S + s) * nblock * bsize : nullptr;
         if (GRAM && P.gram_refresh > 0 && sweep > 0 && sweep % P.gram_refresh == 0) {
@@ -349,6 +391,7 @@ __global__ void __launch_bounds__(GB_BLOCK, 2) gibbs_block_kernel(SweepParams P)
         const double tau2 = sh.tau2, sigma2 = sh.sigma2;
         const double logp0 = log(sh.p0), log1p0 = log(1 - sh.p0);       // :339-340, :912-913
 
+        BPH(0);
         int pos0 = 0;
         while (pos0 < nblock) {
             ++n_windows;
@@ -369,15 +412,29 @@ __global__ void __launch_bounds__(GB_BLOCK, 2) gibbs_block_kernel(SweepParams P)
                 const bool act = valid && gl < bsize && ((mask_s[j >> 5] >> (j & 31)) & 1u);
                 const unsigned actb = __ballot_sync(0xffffffffu, act);
                 const bool certain = (actb & gmask) != 0u;             // must be zeroed: a certain change
-                const bool score = valid && !certain;
+                // gram form: a block that holds coefficients is scored as well, on the statistics of
+                // the zeroed block (q_m + sum_k beta_k G[m][k], the chain of the apply step), so that
+                // the apply step below never scores again
+                const bool score = valid && (GRAM || !certain);
                 const unsigned scoreb = __ballot_sync(0xffffffffu, score && gl == 0);
                 double* gx = w_x[warp] + grp * bsize;
                 double* gA = w_A[warp] + grp * bsize * bsize;
+                const int j0 = __shfl_sync(0xffffffffu, j, grp * npad);
+                const double* gb = P.gb + (int64_t)(j0 / bsize) * bsize * bsize;
+                double xg = 0.0;
+                if (GRAM) {
+                    const double bold = act ? __ldcg(beta_g + j) : 0.0;
+                    if (score && gl < bsize) xg = q[j];
+                    if (__any_sync(0xffffffffu, certain && valid)) {
+                        for (int k = 0; k < bsize; ++k) {
+                            const double bk = __shfl_sync(0xffffffffu, bold, grp * npad + k);
+                            if (score && gl < bsize && bk != 0) xg = fma(bk, gb[gl * bsize + k], xg);
+                        }
+                    }
+                }
                 if (score) {
-                    const int j0 = __shfl_sync(gmask, j, grp * npad);
-                    const double* gb = P.gb + (int64_t)(j0 / bsize) * bsize * bsize;
                     for (int e = gl; e < bsize * bsize; e += npad) gA[e] = gb[e];
-                    if (GRAM && gl < bsize) gx[gl] = q[j];
+                    if (GRAM && gl < bsize) gx[gl] = xg;
                 }
                 if (!GRAM) {                                            // dots need the whole warp
                     for (int g = 0; g < G; ++g) {
@@ -402,6 +459,7 @@ __global__ void __launch_bounds__(GB_BLOCK, 2) gibbs_block_kernel(SweepParams P)
                 double* gp = probs + grp * npad;                        // 32 doubles per warp
                 if (score && gl < P.nmodel) gp[gl] = exp(lp - mx);
                 const unsigned failb = __ballot_sync(0xffffffffu, fail);
+                if (lane == 0) bs.failb[warp] = failb;
                 __syncwarp();
                 bool chg = false;
                 if (valid && gl == 0) {
@@ -439,12 +497,14 @@ __global__ void __launch_bounds__(GB_BLOCK, 2) gibbs_block_kernel(SweepParams P)
                 }
                 changed = change ? 1u : 0u;
             }
+            BPH(1);
             if (lane == 0) bs.flags[warp] = changed;
             __syncthreads();
             int first = -1;
 #pragma unroll
             for (int w = GB_NWARP - 1; w >= 0; --w) if (bs.flags[w]) first = w * G + __ffs(bs.flags[w]) - 1;
             __syncthreads();
+            BPH(2);
             if (first < 0) { pos0 += WB; continue; }
 
             // ---- apply block bi exactly like the reference
@@ -485,29 +545,42 @@ __global__ void __launch_bounds__(GB_BLOCK, 2) gibbs_block_kernel(SweepParams P)
                 }
                 __syncthreads();
             }
+            BPH(3);
             if (warp == 0) {
                 bool bad2 = false;
-                const double denom = block_score(P, bs.A, bs.xatr, tau2, sigma2, logp0, log1p0, probs, &bad2);
+                double denom = 0.0;
+                const double* pr = probs;
+                if (GRAM && P.npad <= 32) {
+                    // the window scored this block on the same (zeroed) statistics: take its model
+                    // probabilities and accumulate the normaliser in the order of _weighted_choice
+                    const int wf = first / G, gf = first - wf * G;
+                    pr = probs_all + wf * nmodel_pad + gf * P.npad;
+                    const unsigned gm = (P.npad == 32 ? 0xffffffffu : ((1u << P.npad) - 1u)) << (gf * P.npad);
+                    bad2 = (bs.failb[wf] & gm) != 0u;
+                    if (lane == 0) for (int ii = 0; ii < P.nmodel; ++ii) denom += pr[ii];
+                } else {
+                    denom = block_score(P, bs.A, bs.xatr, tau2, sigma2, logp0, log1p0, probs, &bad2);
+                }
+                if (lane < bsize) bs.zn[lane] = z_s ? z_s[bi * bsize + lane] : rng_normal(key, KIND_BLOCK, bi, sweep, 1 + lane);
+                __syncwarp();
                 if (lane == 0) {
                     const double u = u_s ? u_s[bi] : rng_uniform(key, KIND_BLOCK, bi, sweep, 0);
                     int mj = 0;
                     double cumsum = 0.0;
                     for (int ii = 0; ii < P.nmodel; ++ii) {            // _weighted_choice :72-77
-                        cumsum += probs[ii] / denom;
+                        cumsum += pr[ii] / denom;
                         if (cumsum >= u) { mj = ii; break; }
                     }
                     for (int k = 0; k < bsize; ++k) bs.bnew[k] = 0.0;
                     if (mj > 0 && !bad2) {
-                        double zn[BK_MAXB];
-                        for (int k = 0; k < bsize; ++k)
-                            zn[k] = z_s ? z_s[bi * bsize + k] : rng_normal(key, KIND_BLOCK, bi, sweep, 1 + k);
-                        if (!block_draw(P.model_masks[mj - 1], bsize, bs.A, bs.xatr, tau2, sigma2, zn, bs.bnew)) bad2 = true;
+                        if (!block_draw(P.model_masks[mj - 1], bsize, bs.A, bs.xatr, tau2, sigma2, bs.zn, bs.bnew)) bad2 = true;
                     }
                     if (bad2) { *P.numeric_err = 1; mj = 0; for (int k = 0; k < bsize; ++k) bs.bnew[k] = 0.0; }
                     bs.mj = mj;
                 }
             }
             __syncthreads();
+            BPH(4);
             const int mj = bs.mj;
             if (GRAM) {                                                // zeroing and write-back in one update
                 const uint32_t msk = mj > 0 ? P.model_masks[mj - 1] : 0u;
@@ -551,6 +624,7 @@ __global__ void __launch_bounds__(GB_BLOCK, 2) gibbs_block_kernel(SweepParams P)
                 }
             }
             __syncthreads();
+            BPH(5);
             pos0 = bi + 1;
         }
 
@@ -563,6 +637,8 @@ __global__ void __launch_bounds__(GB_BLOCK, 2) gibbs_block_kernel(SweepParams P)
         sweep_epilogue(P, &sh, mask_s, beta_g, scratch, key, c, s, ssr, y_s, dirty);
         dirty = false;
         __syncthreads();
+        BPH(6);
+        BPH_PRINT;
     }
 
     if (GRAM) for (int k = tid; k < p2; k += GB_BLOCK) P.q[(int64_t)c * p2 + k] = q[k];
