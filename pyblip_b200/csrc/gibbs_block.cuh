@@ -100,7 +100,9 @@ __device__ __forceinline__ double block_model_lp_t(uint32_t mask, const double* 
             // an entry outside the model is an exact 0 / d; dividing 1.0 instead and discarding the
             // quotient keeps the whole warp out of the division's zero-numerator slow path
             const bool in = ((mask >> i) & 1u) && ((mask >> j) & 1u);
-            const double qt = (in ? sacc : 1.0) / d;
+            double num = in ? sacc : 1.0;
+            asm volatile("" : "+d"(num));          // keeps the compiler from dividing the zero after all
+            const double qt = num / d;
             Q[i][j] = in ? qt : 0.0;
         }
     }
@@ -112,7 +114,9 @@ __device__ __forceinline__ double block_model_lp_t(uint32_t mask, const double* 
 #pragma unroll
         for (int k = 0; k < a; ++k) sacc -= Q[a][k] * yv[k];
         const bool in = (mask >> a) & 1u;
-        const double qt = (in ? sacc : 1.0) / Q[a][a];
+        double num = in ? sacc : 1.0;
+        asm volatile("" : "+d"(num));
+        const double qt = num / Q[a][a];
         yv[a] = in ? qt : 0.0;
         if (in) nrm2 += yv[a] * yv[a];
     }
