@@ -275,6 +275,8 @@ struct BlockShared {
     unsigned flags[GB_NWARP];
     unsigned failb[GB_NWARP];          // lanes of each warp whose window score hit a failed factorisation
     double zn[BK_MAXB];                // normals of the coefficient draw
+    double u[GB_NWARP][8];             // choice uniforms of the blocks of the window (drawn while their loads fly)
+    double cq[32];                     // model probabilities of the applied block, normalised
 };
 
 #ifdef BK_PHASE_CLOCKS
@@ -413,6 +415,12 @@ __global__ void __launch_bounds__(GB_BLOCK, 2) gibbs_block_kernel(SweepParams P)
                 const bool valid = grp < G && bi_g < nblock;
                 const unsigned gmask = (npad == 32 ? 0xffffffffu : ((1u << npad) - 1u)) << (grp * npad);
                 const int j = (valid && gl < bsize) ? blocks[bi_g * bsize + gl] : 0;
+                // the choice uniform does not depend on the state: drawn here, under the loads
+                double u_blk = 0.0;
+                if (valid && gl == 0) {
+                    u_blk = u_s ? u_s[bi_g] : rng_uniform(key, KIND_BLOCK, bi_g, sweep, 0);
+                    bs.u[warp][grp] = u_blk;
+                }
                 const bool act = valid && gl < bsize && ((mask_s[j >> 5] >> (j & 31)) & 1u);
                 const unsigned actb = __ballot_sync(0xffffffffu, act);
                 const bool certain = (actb & gmask) != 0u;             // must be zeroed: a certain change
@@ -471,8 +479,7 @@ __global__ void __launch_bounds__(GB_BLOCK, 2) gibbs_block_kernel(SweepParams P)
                     else {
                         double denom = 0.0;
                         for (int mj = 0; mj < P.nmodel; ++mj) denom += gp[mj];
-                        const double u = u_s ? u_s[bi_g] : rng_uniform(key, KIND_BLOCK, bi_g, sweep, 0);
-                        chg = !(0.0 + gp[0] / denom >= u);              // model 0 is drawn iff its share reaches u
+                        chg = !(0.0 + gp[0] / denom >= u_blk);          // model 0 is drawn iff its share reaches u
                     }
                 }
                 const unsigned chgb = __ballot_sync(0xffffffffu, chg);
@@ -566,13 +573,19 @@ __global__ void __launch_bounds__(GB_BLOCK, 2) gibbs_block_kernel(SweepParams P)
                     denom = block_score(P, bs.A, bs.xatr, tau2, sigma2, logp0, log1p0, probs, &bad2);
                 }
                 if (lane < bsize) bs.zn[lane] = z_s ? z_s[bi * bsize + lane] : rng_normal(key, KIND_BLOCK, bi, sweep, 1 + lane);
+                const bool par = GRAM && P.npad <= 32;                  // one quotient per lane, summed in order below
+                if (par) {
+                    denom = __shfl_sync(0xffffffffu, denom, 0);
+                    if (lane < P.nmodel) bs.cq[lane] = pr[lane] / denom;
+                }
                 __syncwarp();
                 if (lane == 0) {
-                    const double u = u_s ? u_s[bi] : rng_uniform(key, KIND_BLOCK, bi, sweep, 0);
+                    const double u = par ? bs.u[first / G][first % G]
+                                         : (u_s ? u_s[bi] : rng_uniform(key, KIND_BLOCK, bi, sweep, 0));
                     int mj = 0;
                     double cumsum = 0.0;
                     for (int ii = 0; ii < P.nmodel; ++ii) {            // _weighted_choice :72-77
-                        cumsum += pr[ii] / denom;
+                        cumsum += par ? bs.cq[ii] : pr[ii] / denom;
                         if (cumsum >= u) { mj = ii; break; }
                     }
                     for (int k = 0; k < bsize; ++k) bs.bnew[k] = 0.0;
