@@ -15,6 +15,7 @@
 // :100,132-140), so q and rr are rebuilt from X^T y at every sweep and never drift.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -51,6 +52,7 @@ struct NPParams {
     double* q;                     // [chains][p2]
     NPDraws* uz;                   // [chains][p]: this sweep's state-independent variates by visiting position
     double* hs;                    // [chains][4]: sigma2, alpha0, p0, rr
+    int chain_base;                // first chain of this launch (waves)
     int state_smem;                // alpha, w, q and ||X_j||^2 live in dynamic shared memory during the launch
     int amax;                      // capacity of the active-set workspace (<= p, sized from free memory)
     double* chol;                  // [chains][amax*amax]
@@ -285,7 +287,9 @@ __global__ void __launch_bounds__(NP_BLOCK, 2) nprior_kernel(NPParams P)
     NpCholSmem& s_chol = s_mem.blocked;
     __shared__ int s_scan[NP_BLOCK / 32 + 2];
 
-    const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // chain c of this rank; the joint-draw workspace is indexed by the slot within the launch, because
+    // the chains run in waves when the workspace of all of them does not fit in memory
+    const int slot = blockIdx.x, c = P.chain_base + slot, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int p = P.p, p2 = P.p2;
     const RngKey key = { P.k0, P.k1, P.chain_offset + (uint32_t)c };
     // chain state: in dynamic shared memory for the whole launch when it fits (4 p doubles), else in
@@ -306,9 +310,9 @@ __global__ void __launch_bounds__(NP_BLOCK, 2) nprior_kernel(NPParams P)
     double* beta = P.beta + (int64_t)c * p;
     NPDraws* uz = P.uz + (int64_t)c * p;
     const int NP_AMAX = P.amax;
-    double* L = P.chol + (int64_t)c * NP_AMAX * NP_AMAX;
-    double* vec = P.vec + (int64_t)c * 3 * NP_AMAX;
-    int* act = P.act + (int64_t)c * NP_AMAX;
+    double* L = P.chol + (int64_t)slot * NP_AMAX * NP_AMAX;
+    double* vec = P.vec + (int64_t)slot * 3 * NP_AMAX;
+    int* act = P.act + (int64_t)slot * NP_AMAX;
     const blipgpu_nprior_config& cf = P.cfg;
 
     if (tid == 0) { s_sigma2 = P.hs[4 * c]; s_alpha0 = P.hs[4 * c + 1]; s_p0 = P.hs[4 * c + 2]; s_rr = P.hs[4 * c + 3]; }
@@ -739,21 +743,25 @@ extern "C" int blipgpu_sample_nprior(blipgpu_ctx* ctx, blipgpu_design* design, c
     // active-set workspace of the joint W draw: starts small and is doubled (with a replay of the
     // launch, see below) when a chain's active set outgrows it; the limit is what half of the
     // free memory can hold
-    int64_t amax_limit = p;
+    // (BLIPGPU_NPRIOR_WORKSPACE_MB overrides the budget; the tests use it to force waves).  When the
+    // workspace of all chains does not fit, the chains of a launch run in waves of `wave` chains.
+    double budget = 0.0;
     {
         size_t free_b = 0, total_b = 0;
         CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-        const double budget = 0.5 * (double)free_b;
-        const int64_t fit = (int64_t)std::sqrt(budget / (8.0 * (double)chains));
-        amax_limit = std::max<int64_t>(std::min<int64_t>(p, NP_AMAX_MIN), std::min<int64_t>(p, fit));
+        budget = 0.5 * (double)free_b;
+        if (const char* e = getenv("BLIPGPU_NPRIOR_WORKSPACE_MB")) budget = std::max(1e-3, atof(e)) * 1048576.0;
     }
+    const int64_t amax_limit = std::min<int64_t>(p, std::max<int64_t>(NP_AMAX_MIN, (int64_t)std::sqrt(budget / 8.0)));
     int64_t NP_AMAX = std::min<int64_t>(amax_limit, 256);
+    int64_t wave = chains;
     auto alloc_workspace = [&]() -> int {
         if (d_chol.ptr) { cudaFree(d_chol.ptr); d_chol.ptr = nullptr; }
         if (d_vec.ptr) { cudaFree(d_vec.ptr); d_vec.ptr = nullptr; }
         if (d_act.ptr) { cudaFree(d_act.ptr); d_act.ptr = nullptr; }
-        BLIP_TRY(d_chol.alloc(sizeof(double) * chains * NP_AMAX * NP_AMAX));
-        BLIP_TRY(d_vec.alloc(sizeof(double) * chains * 3 * NP_AMAX)); BLIP_TRY(d_act.alloc(sizeof(int) * chains * NP_AMAX));
+        wave = std::max<int64_t>(1, std::min<int64_t>(chains, (int64_t)(budget / (8.0 * (double)NP_AMAX * (double)NP_AMAX))));
+        BLIP_TRY(d_chol.alloc(sizeof(double) * wave * NP_AMAX * NP_AMAX));
+        BLIP_TRY(d_vec.alloc(sizeof(double) * wave * 3 * NP_AMAX)); BLIP_TRY(d_act.alloc(sizeof(int) * wave * NP_AMAX));
         return BLIP_OK;
     };
     BLIP_TRY(alloc_workspace());
@@ -841,8 +849,11 @@ extern "C" int blipgpu_sample_nprior(blipgpu_ctx* ctx, blipgpu_design* design, c
         for (;;) {
             P.amax = (int)NP_AMAX; P.chol = d_chol.as<double>(); P.vec = d_vec.as<double>(); P.act = d_act.as<int>();
             ScopedTimer timer(ctx, true);
-            nprior_kernel<<<(unsigned)chains, NP_BLOCK, dyn_smem, st>>>(P);
-            CUDA_TRY(cudaGetLastError());
+            for (int64_t base = 0; base < chains; base += wave) {
+                P.chain_base = (int)base;
+                nprior_kernel<<<(unsigned)std::min<int64_t>(wave, chains - base), NP_BLOCK, dyn_smem, st>>>(P);
+                CUDA_TRY(cudaGetLastError());
+            }
             res->sweep_ms += timer.stop(1);
             int errv[2] = { 0, 0 };
             CUDA_TRY(cudaMemcpyAsync(errv, d_err.ptr, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -853,7 +864,7 @@ extern "C" int blipgpu_sample_nprior(blipgpu_ctx* ctx, blipgpu_design* design, c
             // a chain's active set outgrew the workspace: enlarge it and replay the launch from the
             // snapshot (keyed draws make the replay identical)
             if (NP_AMAX >= amax_limit) {
-                blip_set_error("sample_nprior: more than %lld active coordinates in the joint W draw (workspace limited by free memory)", (long long)NP_AMAX);
+                blip_set_error("sample_nprior: more than %lld active coordinates in the joint W draw (one chain's workspace exceeds half of the free memory)", (long long)NP_AMAX);
                 return BLIP_ERR_UNSUPPORTED;
             }
             NP_AMAX = std::min<int64_t>(amax_limit, std::max<int64_t>(2 * NP_AMAX, (int64_t)errv[1] + errv[1] / 4 + 32));

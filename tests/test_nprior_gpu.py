@@ -122,3 +122,29 @@ def test_nprior_workspace_grows_and_replays(gpu):
         assert np.array_equal(out["betas"][sl] != 0, orc["betas"] != 0)
         for k in ("alphas", "ws", "sigma2s"):
             assert util.rel_err(out[k][sl], orc[k]) <= 1e-7, k    # 300x300 Cholesky: conditioning, not logic
+
+
+def test_nprior_waves_when_the_workspace_does_not_fit(gpu, monkeypatch):
+    """A workspace budget that holds one chain at a time (BLIPGPU_NPRIOR_WORKSPACE_MB): the chains of a
+    launch run in waves, with results identical to the single-launch run."""
+    from pyblip_b200 import _lib
+    rng = np.random.default_rng(33)
+    n, p, N, chains = 100, 300, 6, 5
+    X = rng.standard_normal((n, p))
+    y = X @ rng.standard_normal(p) + 0.1 * rng.standard_normal(n)
+    cfg = _lib.NPriorConfig(1.0, 0.3, 1e-10, 1, 5.0, 1.0, 0, 1, 1, 0)
+    design = _lib.Design.upload(X)
+
+    def run():
+        smp = _lib.sample_nprior(design, cfg, y, chains=chains, n_keep=N, burn=2, seed=9)
+        out = {k: smp.get(k) for k in ("alphas", "ws", "betas", "sigma2s", "alpha0s", "p0s")}
+        smp.close()
+        return out
+
+    ref = run()
+    assert ((ref["betas"] != 0).sum(1) > 64).any(), "the case must use the global-memory workspace"
+    monkeypatch.setenv("BLIPGPU_NPRIOR_WORKSPACE_MB", "1.0")      # 300 x 300 doubles = 0.69 MB per chain
+    out = run()
+    design.close()
+    for k in ref:
+        assert np.array_equal(out[k], ref[k]), k
