@@ -182,13 +182,14 @@ def reference_throughput(X, y, sweeps, workers=None, kind="linear", **kw):
     _REF_DATA.update(X=X, y=y, kind=kind, kw=kw)
     short = max(2, sweeps // 10)
     ctx = mp.get_context("fork")
+    limit = 900                                           # seconds; a stuck worker must not hang the bench
     with ctx.Pool(workers) as pool:
-        pool.map(_ref_worker, [1] * workers)             # page in, import
+        pool.map_async(_ref_worker, [1] * workers).get(timeout=limit)             # page in, import
         t0 = time.perf_counter()
-        pool.map(_ref_worker, [short] * workers)
+        pool.map_async(_ref_worker, [short] * workers).get(timeout=limit)
         t_short = time.perf_counter() - t0
         t0 = time.perf_counter()
-        pool.map(_ref_worker, [short + sweeps] * workers)
+        pool.map_async(_ref_worker, [short + sweeps] * workers).get(timeout=limit)
         t_long = time.perf_counter() - t0
     dt = max(t_long - t_short, 1e-9)
     p = X.shape[1]
