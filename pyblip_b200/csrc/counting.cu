@@ -183,13 +183,46 @@ __global__ void __launch_bounds__(CT_BLOCK) count_sequential_kernel(
     for (int m = 0; m < MAXM; ++m) cnt[m] = 0;
     int zero_rows = 0;  // rows of tiles in which every window of this word is trivially zero
 
-    for (int64_t r0 = r_begin + 32 * warp; r0 < r_end; r0 += 32 * CT_NWARP) {
+    auto fetch = [&](int64_t r0, uint32_t& lo, uint32_t& mid, uint32_t& hi) {
         const int64_t r = r0 + lane;
         const bool live = r < r_end;
-        const uint32_t lo = live ? c0[r] : 0xffffffffu;   // dead rows count for nothing
-        const uint32_t mid = (live && c1) ? c1[r] : 0u;
-        const uint32_t hi = (live && c2) ? c2[r] : 0u;
-        if (!__any_sync(0xffffffffu, (lo | mid | hi) != 0u)) { zero_rows += 32; continue; }
+        lo = live ? c0[r] : 0xffffffffu;                   // dead rows count for nothing
+        mid = (live && c1) ? c1[r] : 0u;
+        hi = (live && c2) ? c2[r] : 0u;
+    };
+    // Sparse tiles (posterior samples: a handful of non-zero columns among the 64 a word's windows can
+    // reach) skip the transposes: each non-zero column c is gathered with one ballot, in increasing
+    // order, and lane j adds the rows it newly covers to E[c - j]; with E[m] = #rows first covered at
+    // width m, the zero count of window (j, m) is 32 T - sum_{k <= m} E[k] over the T sparse tiles.
+    constexpr bool SPARSE = MAXM <= 32;
+    constexpr int SPARSE_MAX_COLS = 10;
+    __shared__ int s_E[SPARSE ? CT_NWARP : 1][SPARSE ? 32 : 1][32];
+    if (SPARSE) {
+        for (int m = 0; m < 32; ++m) s_E[warp][m][lane] = 0;
+        __syncwarp();
+    }
+    int sparse_tiles = 0;
+    auto process = [&](const uint32_t lo, const uint32_t mid, const uint32_t hi) {
+        if (!__any_sync(0xffffffffu, (lo | mid | hi) != 0u)) { zero_rows += 32; return; }
+        if (SPARSE) {
+            const uint32_t nz_lo = __reduce_or_sync(0xffffffffu, lo), nz_mid = __reduce_or_sync(0xffffffffu, mid);
+            if (__popc(nz_lo) + __popc(nz_mid) <= SPARSE_MAX_COLS) {
+                unsigned long long nz = (unsigned long long)nz_lo | ((unsigned long long)nz_mid << 32);
+                uint32_t acc = 0u;                          // rows covered by the non-zero columns in [j, c)
+                while (nz) {                                // warp-uniform
+                    const int c = __ffsll((long long)nz) - 1;
+                    nz &= nz - 1;
+                    const uint32_t colc = __ballot_sync(0xffffffffu, (((c < 32) ? lo : mid) >> (c & 31)) & 1u);
+                    const int m = c - lane;
+                    if (m >= 0 && m < max_size) {
+                        s_E[warp][m][lane] += __popc(colc & ~acc);
+                        acc |= colc;
+                    }
+                }
+                ++sparse_tiles;
+                return;
+            }
+        }
         __syncwarp();
         uint32_t acc = warp_transpose32(lo);                // OR of columns j..j+m, one bit per row
         s_cw[warp][32 + lane] = warp_transpose32(mid);
@@ -202,6 +235,35 @@ __global__ void __launch_bounds__(CT_BLOCK) count_sequential_kernel(
             if (m < max_size) {
                 acc |= s_cw[warp][lane + m];
                 cnt[m] += __popc(~acc);
+            }
+        }
+    };
+    // CS_PF tiles are requested ahead of the one being processed: the kernel is bound by the bytes a
+    // warp keeps in flight, not by its instructions
+    constexpr int CS_PF = 4;
+    const int64_t step = 32 * CT_NWARP;
+    uint32_t lo_n[CS_PF], mid_n[CS_PF], hi_n[CS_PF];
+#pragma unroll
+    for (int i = 0; i < CS_PF; ++i) fetch(r_begin + 32 * warp + i * step, lo_n[i], mid_n[i], hi_n[i]);
+    for (int64_t rb = r_begin + 32 * warp; rb < r_end; rb += CS_PF * step) {
+        uint32_t lo_c[CS_PF], mid_c[CS_PF], hi_c[CS_PF];
+#pragma unroll
+        for (int i = 0; i < CS_PF; ++i) { lo_c[i] = lo_n[i]; mid_c[i] = mid_n[i]; hi_c[i] = hi_n[i]; }
+        if (rb + CS_PF * step < r_end) {
+#pragma unroll
+            for (int i = 0; i < CS_PF; ++i) fetch(rb + (CS_PF + i) * step, lo_n[i], mid_n[i], hi_n[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < CS_PF; ++i)
+            if (rb + i * step < r_end) process(lo_c[i], mid_c[i], hi_c[i]);      // warp-uniform
+    }
+    if (SPARSE) {
+        int covered = 0;
+#pragma unroll
+        for (int m = 0; m < MAXM; ++m) {
+            if (m < max_size) {
+                covered += s_E[warp][m][lane];
+                cnt[m] += 32 * sparse_tiles - covered;
             }
         }
     }
