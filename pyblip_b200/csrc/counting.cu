@@ -205,16 +205,27 @@ __global__ void __launch_bounds__(CT_BLOCK) count_sequential_kernel(
     auto process = [&](const uint32_t lo, const uint32_t mid, const uint32_t hi) {
         if (!__any_sync(0xffffffffu, (lo | mid | hi) != 0u)) { zero_rows += 32; return; }
         if (SPARSE) {
-            const uint32_t nz_lo = __reduce_or_sync(0xffffffffu, lo), nz_mid = __reduce_or_sync(0xffffffffu, mid);
-            if (__popc(nz_lo) + __popc(nz_mid) <= SPARSE_MAX_COLS) {
-                unsigned long long nz = (unsigned long long)nz_lo | ((unsigned long long)nz_mid << 32);
+            // only the first max_size - 1 columns of the next word are within reach of this word's windows
+            const uint32_t reach = max_size >= 33 ? 0xffffffffu : ((1u << (max_size - 1)) - 1u);
+            uint32_t nzl = __reduce_or_sync(0xffffffffu, lo), nzm = __reduce_or_sync(0xffffffffu, mid) & reach;
+            if (__popc(nzl) + __popc(nzm) <= SPARSE_MAX_COLS) {
                 uint32_t acc = 0u;                          // rows covered by the non-zero columns in [j, c)
-                while (nz) {                                // warp-uniform
-                    const int c = __ffsll((long long)nz) - 1;
-                    nz &= nz - 1;
-                    const uint32_t colc = __ballot_sync(0xffffffffu, (((c < 32) ? lo : mid) >> (c & 31)) & 1u);
+                while (nzl) {                               // warp-uniform
+                    const int c = __ffs(nzl) - 1;
+                    nzl &= nzl - 1;
+                    const uint32_t colc = __ballot_sync(0xffffffffu, (lo >> c) & 1u);
                     const int m = c - lane;
                     if (m >= 0 && m < max_size) {
+                        s_E[warp][m][lane] += __popc(colc & ~acc);
+                        acc |= colc;
+                    }
+                }
+                while (nzm) {
+                    const int c = __ffs(nzm) - 1;
+                    nzm &= nzm - 1;
+                    const uint32_t colc = __ballot_sync(0xffffffffu, (mid >> c) & 1u);
+                    const int m = 32 + c - lane;            // >= 1
+                    if (m < max_size) {
                         s_E[warp][m][lane] += __popc(colc & ~acc);
                         acc |= colc;
                     }
