@@ -296,6 +296,58 @@ __global__ void __launch_bounds__(CT_BLOCK) count_sequential_kernel(
     }
 }
 
+// ---- column-major copy of the bit matrix -----------------------------------
+// One warp transposes 8 consecutive 32 x 32 tiles of word w (256 rows) and lane c writes the 8 row
+// words of column 32 w + c as two 16-byte stores (one full 32-byte sector).
+__global__ void __launch_bounds__(CT_BLOCK) transpose_bits_kernel(
+    const uint32_t* __restrict__ bits, int64_t N, int64_t N_pad, int64_t NW, uint32_t* __restrict__ colbits)
+{
+    const int w = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t t0 = 8 * ((int64_t)blockIdx.y * CT_NWARP + warp);           // first row word of this warp
+    if (t0 >= NW) return;
+    uint32_t v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int64_t r = 32 * (t0 + i) + lane;
+        v[i] = r < N ? bits[(int64_t)w * N_pad + r] : 0u;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = warp_transpose32(v[i]);
+    uint4* dst = reinterpret_cast<uint4*>(colbits + ((int64_t)32 * w + lane) * NW + t0);
+    dst[0] = make_uint4(v[0], v[1], v[2], v[3]);
+    dst[1] = make_uint4(v[4], v[5], v[6], v[7]);
+}
+
+// any-counts from the column-major copy: a group costs |group| N / 8 bytes instead of 4 N |group|.
+// grid (groups, chunks); a thread ORs the members' row words four at a time.
+__global__ void __launch_bounds__(CT_BLOCK) count_groups_colmajor_kernel(
+    const uint32_t* __restrict__ colbits, int64_t NW, const int64_t* __restrict__ offsets,
+    const int32_t* __restrict__ members, int64_t quads_per_block, unsigned long long* __restrict__ any_counts)
+{
+    __shared__ int s_cnt[CT_NWARP];
+    const int g = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t m0 = offsets[g], m1 = offsets[g + 1];
+    const int64_t nquad = NW / 4;
+    const int64_t q_begin = (int64_t)blockIdx.y * quads_per_block, q_end = min(nquad, q_begin + quads_per_block);
+    int cnt = 0;
+    for (int64_t qd = q_begin + threadIdx.x; qd < q_end; qd += CT_BLOCK) {
+        uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+        for (int64_t k = m0; k < m1; ++k) {
+            const uint4 x = __ldg(reinterpret_cast<const uint4*>(colbits + (int64_t)members[k] * NW) + qd);
+            acc.x |= x.x; acc.y |= x.y; acc.z |= x.z; acc.w |= x.w;
+        }
+        cnt += __popc(acc.x) + __popc(acc.y) + __popc(acc.z) + __popc(acc.w);
+    }
+    cnt = warp_sum_int(cnt);
+    if (lane == 0) s_cnt[warp] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int i = 0; i < CT_NWARP; ++i) t += s_cnt[i];
+        if (t) atomicAdd(any_counts + g, (unsigned long long)t);
+    }
+}
+
 // ---- arbitrary groups: any(samples[:, group]) ---------------------------
 // grid (groups, chunks); lane = row.
 __global__ void __launch_bounds__(CT_BLOCK) count_groups_kernel(
@@ -413,7 +465,7 @@ int alloc_bits(blipgpu_ctx* ctx, int64_t N, int64_t p, blipgpu_bits** out)
     blipgpu_bits* b = new (std::nothrow) blipgpu_bits();
     if (!b) { blip_set_error("host allocation failed"); return BLIP_ERR_NOMEM; }
     b->ctx = ctx; b->N = N; b->N_pad = round_up(std::max<int64_t>(N, 1), 32); b->p = p;
-    b->words = (p + 31) / 32; b->owns = true; b->bits = nullptr;
+    b->words = (p + 31) / 32; b->owns = true; b->bits = nullptr; b->colbits = nullptr; b->NW = 0;
     const size_t bytes = sizeof(uint32_t) * std::max<int64_t>(b->words, 1) * b->N_pad;
     cudaError_t e = cudaMalloc(&b->bits, bytes);
     if (e != cudaSuccess) { delete b; blip_set_error("bits allocation (%zu bytes) failed: %s", bytes, cudaGetErrorString(e)); return BLIP_ERR_NOMEM; }
@@ -635,10 +687,33 @@ extern "C" int blipgpu_count_groups(blipgpu_bits* b, const int64_t* offsets, con
     if (e != cudaSuccess) { cudaFree(d_off); cudaFree(d_mem); blip_set_error("count_groups: %s", cudaGetErrorString(e)); return BLIP_ERR_CUDA; }
     const int64_t rpb = pick_rows_per_block(b->N, n_groups, b->ctx->sm_count);
     const unsigned chunks = (unsigned)std::max<int64_t>(1, (b->N + rpb - 1) / rpb);
+    // With enough members to pay for it (the transposition moves 2 N p / 8 bytes once per handle) the
+    // counts come from a column-major copy of the bit matrix: |group| N / 8 bytes per group instead
+    // of one 32-bit word per (row, member).
+    if (!b->colbits && b->N > 0 && total > b->p / 8) {
+        const int64_t NW = round_up((b->N + 31) / 32, 8);
+        uint32_t* cb = nullptr;
+        if (cudaMalloc(&cb, sizeof(uint32_t) * 32 * b->words * NW) == cudaSuccess) {
+            const unsigned ty = (unsigned)((NW / 8 + CT_NWARP - 1) / CT_NWARP);
+            transpose_bits_kernel<<<dim3((unsigned)b->words, ty), CT_BLOCK, 0, st>>>(b->bits, b->N, b->N_pad, NW, cb);
+            b->ctx->kernel_launches += 1;
+            b->colbits = cb; b->NW = NW;
+        } else {
+            cudaGetLastError();                     // no room for the copy: stay on the row-major kernel
+        }
+    }
     int rc = with_output(b->ctx, n_groups, any_counts, out_is_device, [&](unsigned long long* dev) {
         if (b->N == 0) return;
         // grid.x is limited to 2^31-1 groups; grid.y to 65535 chunks
-        count_groups_kernel<<<dim3((unsigned)n_groups, chunks), CT_BLOCK, 0, st>>>(b->bits, b->N, b->N_pad, d_off, d_mem, rpb, dev);
+        if (b->colbits) {
+            const int64_t nquad = b->NW / 4;
+            const int64_t want = std::max<int64_t>(1, 8LL * b->ctx->sm_count / std::max<int64_t>(1, n_groups));
+            const int64_t qpb = std::max<int64_t>(CT_BLOCK, round_up((nquad + want - 1) / want, CT_BLOCK));
+            const unsigned cy = (unsigned)std::max<int64_t>(1, (nquad + qpb - 1) / qpb);
+            count_groups_colmajor_kernel<<<dim3((unsigned)n_groups, cy), CT_BLOCK, 0, st>>>(b->colbits, b->NW, d_off, d_mem, qpb, dev);
+        } else {
+            count_groups_kernel<<<dim3((unsigned)n_groups, chunks), CT_BLOCK, 0, st>>>(b->bits, b->N, b->N_pad, d_off, d_mem, rpb, dev);
+        }
     });
     cudaFree(d_off); cudaFree(d_mem);
     return rc;
@@ -677,6 +752,7 @@ extern "C" int blipgpu_bits_free(blipgpu_bits* b)
     if (!b) return BLIP_OK;
     cudaSetDevice(b->ctx->device);
     if (b->owns) cudaFree(b->bits);
+    if (b->colbits) cudaFree(b->colbits);
     delete b;
     return BLIP_OK;
 }

@@ -53,6 +53,10 @@ struct blipgpu_bits {
     int64_t N, N_pad, p, words;
     uint32_t* bits;        // [words][N_pad]
     bool owns;
+    // column-major copy, built on the first count_groups call that can use it:
+    // colbits[c * NW + t] = bit r of column c for the rows r = 32 t .. 32 t + 31 (rows >= N are zero)
+    uint32_t* colbits;     // [32 * words][NW]
+    int64_t NW;            // row words per column, a multiple of 8
 };
 
 // helpers implemented in api.cu
