@@ -460,6 +460,47 @@ __global__ void __launch_bounds__(CT_BLOCK) count_false_rows_kernel(
     }
 }
 
+// The same scan on the column-major copy, 128 rows per thread step: a row is a false discovery as
+// soon as one selected group has no member set in it.
+__global__ void __launch_bounds__(CT_BLOCK) count_false_rows_colmajor_kernel(
+    const uint32_t* __restrict__ colbits, int64_t N, int64_t NW, const int64_t* __restrict__ offsets,
+    const int32_t* __restrict__ members, int n_groups, unsigned long long* __restrict__ out)
+{
+    __shared__ int s_cnt[CT_NWARP];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t nquad = NW / 4;
+    int cnt = 0;
+    for (int64_t qd = (int64_t)blockIdx.x * CT_BLOCK + threadIdx.x; qd < nquad; qd += (int64_t)gridDim.x * CT_BLOCK) {
+        uint4 fd = make_uint4(0u, 0u, 0u, 0u);
+        for (int g = 0; g < n_groups; ++g) {
+            uint4 any = make_uint4(0u, 0u, 0u, 0u);
+            for (int64_t k = offsets[g]; k < offsets[g + 1]; ++k) {
+                const uint4 x = __ldg(reinterpret_cast<const uint4*>(colbits + (int64_t)members[k] * NW) + qd);
+                any.x |= x.x; any.y |= x.y; any.z |= x.z; any.w |= x.w;
+            }
+            fd.x |= ~any.x; fd.y |= ~any.y; fd.z |= ~any.z; fd.w |= ~any.w;
+            if ((fd.x & fd.y & fd.z & fd.w) == 0xffffffffu) break;
+        }
+        // rows >= N do not exist
+        const int64_t r0 = 128 * qd;
+        uint32_t w4[4] = { fd.x, fd.y, fd.z, fd.w };
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int64_t left = N - (r0 + 32 * i);
+            if (left <= 0) w4[i] = 0u; else if (left < 32) w4[i] &= (1u << left) - 1u;
+            cnt += __popc(w4[i]);
+        }
+    }
+    cnt = warp_sum_int(cnt);
+    if (lane == 0) s_cnt[warp] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int i = 0; i < CT_NWARP; ++i) t += s_cnt[i];
+        if (t) atomicAdd(out, (unsigned long long)t);
+    }
+}
+
 int alloc_bits(blipgpu_ctx* ctx, int64_t N, int64_t p, blipgpu_bits** out)
 {
     blipgpu_bits* b = new (std::nothrow) blipgpu_bits();
@@ -666,6 +707,20 @@ extern "C" int blipgpu_count_pairs(blipgpu_bits* b, int64_t* pair_counts, int32_
     });
 }
 
+// Builds the column-major copy of the bit matrix once per handle (no-op if it exists or if there is
+// no room for it: the callers then stay on their row-major kernels).
+static void ensure_colbits(blipgpu_bits* b, cudaStream_t st)
+{
+    if (b->colbits || b->N <= 0) return;
+    const int64_t NW = round_up((b->N + 31) / 32, 8);
+    uint32_t* cb = nullptr;
+    if (cudaMalloc(&cb, sizeof(uint32_t) * 32 * b->words * NW) != cudaSuccess) { cudaGetLastError(); return; }
+    const unsigned ty = (unsigned)((NW / 8 + CT_NWARP - 1) / CT_NWARP);
+    transpose_bits_kernel<<<dim3((unsigned)b->words, ty), CT_BLOCK, 0, st>>>(b->bits, b->N, b->N_pad, NW, cb);
+    b->ctx->kernel_launches += 1;
+    b->colbits = cb; b->NW = NW;
+}
+
 extern "C" int blipgpu_count_groups(blipgpu_bits* b, const int64_t* offsets, const int64_t* members,
                                     int64_t n_groups, int64_t* any_counts, int32_t out_is_device)
 {
@@ -690,18 +745,7 @@ extern "C" int blipgpu_count_groups(blipgpu_bits* b, const int64_t* offsets, con
     // With enough members to pay for it (the transposition moves 2 N p / 8 bytes once per handle) the
     // counts come from a column-major copy of the bit matrix: |group| N / 8 bytes per group instead
     // of one 32-bit word per (row, member).
-    if (!b->colbits && b->N > 0 && total > b->p / 8) {
-        const int64_t NW = round_up((b->N + 31) / 32, 8);
-        uint32_t* cb = nullptr;
-        if (cudaMalloc(&cb, sizeof(uint32_t) * 32 * b->words * NW) == cudaSuccess) {
-            const unsigned ty = (unsigned)((NW / 8 + CT_NWARP - 1) / CT_NWARP);
-            transpose_bits_kernel<<<dim3((unsigned)b->words, ty), CT_BLOCK, 0, st>>>(b->bits, b->N, b->N_pad, NW, cb);
-            b->ctx->kernel_launches += 1;
-            b->colbits = cb; b->NW = NW;
-        } else {
-            cudaGetLastError();                     // no room for the copy: stay on the row-major kernel
-        }
-    }
+    if (total > b->p / 8) ensure_colbits(b, st);
     int rc = with_output(b->ctx, n_groups, any_counts, out_is_device, [&](unsigned long long* dev) {
         if (b->N == 0) return;
         // grid.x is limited to 2^31-1 groups; grid.y to 65535 chunks
@@ -741,7 +785,12 @@ extern "C" int blipgpu_count_false_rows(blipgpu_bits* b, const int64_t* offsets,
     const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((b->N + CT_BLOCK - 1) / CT_BLOCK, 8LL * b->ctx->sm_count));
     int rc = with_output(b->ctx, 1, count, out_is_device, [&](unsigned long long* dev) {
         if (b->N == 0 || n_groups == 0) return;
-        count_false_rows_kernel<<<grid, CT_BLOCK, 0, st>>>(b->bits, b->N, b->N_pad, d_off, d_mem, (int)n_groups, dev);
+        if (b->colbits) {
+            const unsigned gq = (unsigned)std::max<int64_t>(1, std::min<int64_t>((b->NW / 4 + CT_BLOCK - 1) / CT_BLOCK, 8LL * b->ctx->sm_count));
+            count_false_rows_colmajor_kernel<<<gq, CT_BLOCK, 0, st>>>(b->colbits, b->N, b->NW, d_off, d_mem, (int)n_groups, dev);
+        } else {
+            count_false_rows_kernel<<<grid, CT_BLOCK, 0, st>>>(b->bits, b->N, b->N_pad, d_off, d_mem, (int)n_groups, dev);
+        }
     });
     cudaFree(d_off); cudaFree(d_mem);
     return rc;

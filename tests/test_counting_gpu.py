@@ -156,3 +156,36 @@ def test_selection_fwer_equals_the_reference_row_scan(gpu):
     S = rng.random((500, 8)) < 0.5
     want = (np.all(S[:, [1, 2]] == 0, axis=1) | np.all(S[:, [5]] == 0, axis=1)).mean()
     assert cg.selection_fwer(S, groups) == want
+
+
+def test_column_major_copy_gives_the_same_counts(gpu):
+    """count_groups switches to a column-major copy of the bit matrix when the groups hold more than
+    p/8 members in total, and count_false_rows uses that copy once it exists: both must equal the
+    row-major kernels and NumPy on ragged shapes (N not a multiple of 32 / 128 / 256)."""
+    from pyblip_b200 import _lib
+    rng = np.random.default_rng(12)
+    for N, p in [(1, 5), (33, 70), (4097, 130), (50021, 203)]:
+        S = rng.random((N, p)) < 0.05
+        S[:, p // 2] = False
+        few = [[0], [p - 1, 1]] if p > 2 else [[0]]
+        many = [sorted(rng.choice(p, size=int(rng.integers(1, min(p, 9) + 1)), replace=False).tolist())
+                for _ in range(max(8, p // 4))]
+        sel = many[:7]
+
+        def want_any(groups):
+            return np.array([np.any(S[:, g], axis=1).sum() for g in groups], dtype=np.int64)
+
+        def want_false(groups):
+            fd = np.zeros(N, dtype=bool)
+            for g in groups:
+                fd |= np.all(S[:, g] == 0, axis=1)
+            return int(fd.sum())
+
+        bits = _lib.Bits.from_dense(S)
+        assert np.array_equal(bits.count_groups(few), want_any(few))              # row-major (few members)
+        assert bits.count_false_rows(sel) == want_false(sel)                      # row-major scan
+        assert np.array_equal(bits.count_groups(many), want_any(many))            # builds the copy
+        assert np.array_equal(bits.count_groups(few), want_any(few))              # now served by the copy
+        assert bits.count_false_rows(sel) == want_false(sel)                      # column-major scan
+        assert bits.count_false_rows([[p // 2]]) == N                             # an all-zero column
+        bits.close()
