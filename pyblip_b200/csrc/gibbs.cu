@@ -456,6 +456,35 @@ static int sample_impl(blipgpu_ctx* ctx, blipgpu_design* design,
         resident = std::max(1, per_sm) * ctx->sm_count;
     }
     const int sub_sweeps_opt = qsmem ? 8 : 0;
+    // q in global memory (p too large for shared memory): every flush reads and writes a chain's q, so
+    // q is pinned in L2 as far as the persisting carve-out goes and the rest of the traffic (Gram
+    // columns) is left to stream past it
+    struct L2Guard {
+        cudaStream_t st; bool on;
+        ~L2Guard() {
+            if (!on) return;
+            cudaStreamAttrValue a; memset(&a, 0, sizeof(a));
+            cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &a);
+            cudaCtxResetPersistingL2Cache();
+        }
+    } l2g{ st, false };
+    if (gram && !block && !qsmem) {
+        int max_persist = 0, max_window = 0;
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
+        const size_t window = std::min<size_t>(d_q.bytes, (size_t)std::max(0, max_window));
+        const size_t persist = std::min<size_t>(window, (size_t)std::max(0, max_persist));
+        if (persist > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist) == cudaSuccess) {
+            cudaStreamAttrValue a; memset(&a, 0, sizeof(a));
+            a.accessPolicyWindow.base_ptr = d_q.ptr;
+            a.accessPolicyWindow.num_bytes = window;
+            a.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)persist / (double)window);
+            a.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            a.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &a) == cudaSuccess) l2g.on = true;
+        }
+        cudaGetLastError();
+    }
 
     cudaEvent_t ev_perm[2], ev_done[2];
     for (int i = 0; i < 2; ++i) {
