@@ -468,15 +468,19 @@ static int sample_impl(blipgpu_ctx* ctx, blipgpu_design* design,
             cudaCtxResetPersistingL2Cache();
         }
     } l2g{ st, false };
-    if (gram && !block && !qsmem) {
+    // residual form: all chains stream the same X every sweep, so X is what is pinned
+    const void* l2_ptr = nullptr; size_t l2_bytes = 0;
+    if (gram && !block && !qsmem) { l2_ptr = d_q.ptr; l2_bytes = d_q.bytes; }
+    else if (!gram && design->XT && getenv("BLIPGPU_NO_L2_PIN") == nullptr) { l2_ptr = design->XT; l2_bytes = sizeof(double) * (size_t)design->ldx * (size_t)p; }
+    if (l2_ptr) {
         int max_persist = 0, max_window = 0;
         cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
         cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
-        const size_t window = std::min<size_t>(d_q.bytes, (size_t)std::max(0, max_window));
+        const size_t window = std::min<size_t>(l2_bytes, (size_t)std::max(0, max_window));
         const size_t persist = std::min<size_t>(window, (size_t)std::max(0, max_persist));
         if (persist > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist) == cudaSuccess) {
             cudaStreamAttrValue a; memset(&a, 0, sizeof(a));
-            a.accessPolicyWindow.base_ptr = d_q.ptr;
+            a.accessPolicyWindow.base_ptr = const_cast<void*>(l2_ptr);
             a.accessPolicyWindow.num_bytes = window;
             a.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)persist / (double)window);
             a.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
