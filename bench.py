@@ -37,6 +37,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# rank 0's stdout carries exactly one JSON line: NCCL's own banner / debug output (NCCL_DEBUG=VERSION
+# or INFO in the environment) goes to stderr instead
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 CONFIG = dict(n=1000, p=10000, rho=0.95, k=50, chains=512, seed=1002)
 METRIC = "gibbs_coordinate_updates_per_sec"
