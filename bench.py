@@ -37,9 +37,28 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# rank 0's stdout carries exactly one JSON line: NCCL's own banner / debug output (NCCL_DEBUG=VERSION
-# or INFO in the environment) goes to stderr instead
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
+# stdout carries exactly one JSON line: file descriptor 1 is pointed at stderr for the duration of the
+# run (NCCL prints its banner / debug lines to stdout when NCCL_DEBUG is set in the environment) and
+# the result line is written to the original stdout at the end
+_REAL_STDOUT = None
+
+
+def _capture_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
 
 CONFIG = dict(n=1000, p=10000, rho=0.95, k=50, chains=512, seed=1002)
 METRIC = "gibbs_coordinate_updates_per_sec"
@@ -268,7 +287,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, impl="b200", chains=None):
@@ -306,6 +325,7 @@ def main():
                          "chains (global chain ids rank*512 ..), no data-path collective; strong: the same 512 "
                          "chains are split over the ranks (64 per GPU at N=8: fewer chains than SMs)")
     args = ap.parse_args()
+    _capture_stdout()
     if args.impl == "reference":
         return run_reference_arm(args)
 
@@ -438,7 +458,7 @@ def main():
             "gpu_launches": int(counters["kernel_launches"]),
             "roofline": roofline, "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     design.close()
     if dist is not None:
         dist.destroy_process_group()
