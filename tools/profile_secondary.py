@@ -67,6 +67,17 @@ for name, fn, nbytes, what in (
     line(f"{name} rows={rows}", t["other_ms"], what, gbs, "GB/s", gbs / HBM)
     if name.startswith("count_groups"):
         print(f"    first call {first_ms:.2f} ms wall (includes the transposition of the {bits_bytes / 1e9:.2f} GB bit matrix and the H2D of the group lists)")
+# pair (co-occurrence) counts on the 1024 columns with the largest marginal counts, as all_cand_groups selects them
+cc = bits.count_columns()
+sub = bits.select_columns(np.sort(np.argsort(-cc)[:1024]))
+sub.count_pairs()
+ctx.timing(reset=True)
+sub.count_pairs()
+ctx.synchronize()
+t = ctx.timing()
+line(f"count_pairs 1024 columns rows={rows}", t["other_ms"], "N*1024/8 bytes read once, 1024^2/2 pair counts",
+     rows * 1024 / 8 / (t["other_ms"] * 1e-3) / 1e9, "GB/s")
+sub.close()
 bits.close()
 smp.close()
 
