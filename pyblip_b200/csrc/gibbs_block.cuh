@@ -8,9 +8,11 @@
 //
 // Exact speculation carries over from the single-site kernels: a block that holds no non-zero
 // coefficient and whose draw is the empty model leaves the chain state untouched, so a window
-// of GB_NWARP upcoming blocks is scored in parallel -- one warp per block, one lane per
-// sub-model -- against the current state, the first block that changes anything is applied by
-// the whole CTA, and the window restarts right after it.
+// of upcoming blocks is scored in parallel against the current state -- one lane per sub-model,
+// 32 / npad blocks per warp (npad = models per block rounded up to a power of two) -- the first
+// block that changes anything is applied by the whole CTA, and the window restarts right after
+// it.  In the gram form a block that holds coefficients is scored in the window as well, on the
+// statistics of the zeroed block, and the apply step reuses those model probabilities.
 //
 // Two formulations (template GRAM):
 //   residual  state r = y - X beta in shared memory; X_A^T r costs bsize dots of length n per

@@ -8,11 +8,15 @@
 // q = X^T r and rr = ||r||^2:
 //     X_j.(r + s X_j) = q_j + s G_jj,        ||r + s X_j||^2 = rr + 2 s q_j + s^2 G_jj.
 // A visit that leaves the coordinate inactive (alpha_j <= alpha0 before and after) does not
-// touch r, so warp 0 evaluates a window of 32 upcoming coordinates in parallel (exact
-// speculation, as in gibbs_kernels.cuh), commits the leading inactive ones and applies the
-// first coordinate whose beta changes with one Gram-column axpy by the whole block.
+// touch r, so the block evaluates a window of NP_BLOCK upcoming visits in parallel, one per
+// thread and active coordinates included (exact speculation, as in gibbs_kernels.cuh), commits
+// the leading visits that stay inactive and applies the first one that touches r as evaluated,
+// with one Gram-column axpy by the whole block.  alpha, w, q and ||X_j||^2 live in dynamic shared
+// memory when 4 p doubles fit; the state-independent variates of a visit are drawn once per sweep.
 // Every sweep starts from fresh w (joint draw or the reference's fresh 0.1*N(0,1) row,
-// :100,132-140), so q and rr are rebuilt from X^T y at every sweep and never drift.
+// :100,132-140), so q and rr are rebuilt from X^T y at every sweep and never drift.  The joint
+// draw factors the active-set precision in shared memory (<= 64 active coordinates) or with a
+// blocked Cholesky in a per-chain global workspace that grows on demand (launch replayed).
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
