@@ -15,6 +15,13 @@
  *   - host pointers are borrowed for the duration of the call only;
  *   - handles are opaque and freed by the matching *_free;
  *   - "device pointer" arguments must belong to the context's device.
+ *
+ * Environment (diagnostics; none changes a result)
+ *   BLIPGPU_LAUNCH_LOG=1             every sweep-kernel launch with its CUDA-event time on stderr
+ *   BLIPGPU_NO_L2_PIN=1              residual-form sweeps: do not pin the design matrix in L2
+ *   BLIPGPU_NPRIOR_WORKSPACE_MB=x    budget of the neuronized prior's joint-draw workspace
+ *                                    (default: half of the free device memory; chains run in
+ *                                    waves when all of them do not fit)
  */
 #ifndef BLIPGPU_H
 #define BLIPGPU_H
