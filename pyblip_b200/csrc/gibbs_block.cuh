@@ -358,7 +358,8 @@ __global__ void __launch_bounds__(GB_BLOCK, 2) gibbs_block_kernel(SweepParams P)
             for (int k = tid; k < n; k += GB_BLOCK) {
                 const double x = __ldg(xcol + k);
                 r_s[k] = fma(coef, x, r_s[k]);
-                if (PROBIT) mu_s[k] = fma(-coef, x, mu_s[k]);
+                if (PROBIT) mu_s[k] = __dadd_rn(__dmul_rn(-coef, x), mu_s[k]);   // rounded product: exact cancellation
+                                                                                 // to 0.0 (see gibbs_residual_kernel)
             }
         }
         __syncthreads();

@@ -399,7 +399,11 @@ __global__ void __launch_bounds__(GB_BLOCK, 2) gibbs_residual_kernel(SweepParams
                 const double delta = bnew - beta_old; // :172-190
                 if (delta != 0) {
                     for (int k = tid; k < n; k += GB_BLOCK) {
-                        double m = fma(delta, __ldg(xcol + k), mu_s[k]);
+                        // mu += delta * X_j with a rounded product, not an fma: when a coefficient goes
+                        // back to zero its share of mu then cancels to exactly 0.0 (an fma would leave the
+                        // rounding residual of the product, of either sign), and truncnorm_std branches on
+                        // the sign of a = -mu/scale at a == 0 (_truncnorm.pyx:57-69)
+                        double m = __dadd_rn(__dmul_rn(delta, __ldg(xcol + k)), mu_s[k]);
                         mu_s[k] = m;
                         double yv = truncnorm(key, KIND_TRUNCNORM, (uint32_t)k, event, m, P.cfg.sigma2,
                                               0.0, P.zlab[k]);

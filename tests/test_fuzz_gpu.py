@@ -43,10 +43,9 @@ def test_block_sampler_on_random_problems(gpu):
     """Keyed stream, both forms, block sizes 2..6 with and without a cap on the signals per block."""
     from oracle import gibbs_oracle as go
     from pyblip_b200 import _lib
-    from pyblip_b200.linear import LinearSpikeSlab
     rng = np.random.default_rng(77)
-    for case in range(8):
-        n = int(rng.integers(20, 90))
+    for case in range(12):
+        n = int(rng.integers(4, 90))
         p = int(rng.integers(7, 60))
         bsize = int(rng.integers(2, 7))
         cap = int(rng.integers(0, bsize + 1))
@@ -56,19 +55,111 @@ def test_block_sampler_on_random_problems(gpu):
         beta[rng.choice(p, size=min(4, p), replace=False)] = 2.0 * rng.standard_normal(min(4, p))
         y = X @ beta + rng.standard_normal(n)
         N, seed = 12, int(rng.integers(1, 1 << 30))
-        cfg = LinearSpikeSlab(X, y)._config()
-        hp = go.hparams()
+        probit = case % 2 == 1                                    # probit: residual form only, sigma2 fixed at 1
+        hp = go.hparams(update_sigma2=False) if probit else go.hparams()
+        cfg = _lib.SpikeSlabConfig(*[getattr(hp, f) for f, _ in hp._fields_])
+        data = dict(z=(y < 0).astype(np.int64), probit=True) if probit else dict(y=y, probit=False)
         design = _lib.Design.upload(X)
-        for mode in (_lib.MODE_RESIDUAL, _lib.MODE_GRAM):
-            smp = _lib.sample_spikeslab(design, cfg, y=y, chains=2, n_keep=N, burn=0, seed=seed, mode=mode,
-                                        bsize=bsize, max_signals_per_block=cap)
+        for mode in ((_lib.MODE_RESIDUAL,) if probit else (_lib.MODE_RESIDUAL, _lib.MODE_GRAM)):
+            smp = _lib.sample_spikeslab(design, cfg, chains=2, n_keep=N, burn=0, seed=seed, mode=mode,
+                                        bsize=bsize, max_signals_per_block=cap, **data)
             betas = smp.dense().reshape(2, N, p)
             p0s, tau2s, sigma2s = (a.reshape(2, N) for a in smp.hyper())
             smp.close()
             for c in range(2):
-                ref = go.sample_spikeslab_multi(N, bsize, X, y=y, probit=False, hp=hp, max_signals_per_block=cap,
-                                                seed=seed, chain=c)
-                assert np.array_equal(betas[c] != 0, ref["betas"] != 0), (case, mode, c, n, p, bsize, cap)
+                ref = go.sample_spikeslab_multi(N, bsize, X, hp=hp, max_signals_per_block=cap, seed=seed, chain=c,
+                                                **data)
+                assert np.array_equal(betas[c] != 0, ref["betas"] != 0), (case, mode, c, n, p, bsize, cap, probit)
                 for got, key in ((betas[c], "betas"), (p0s[c], "p0s"), (tau2s[c], "tau2s"), (sigma2s[c], "sigma2s")):
-                    assert util.rel_err(got, ref[key]) <= 1e-9, (case, mode, c, key)
+                    assert util.rel_err(got, ref[key]) <= 1e-9, (case, mode, c, key, probit)
         design.close()
+
+
+def test_single_site_sampler_on_random_problems(gpu):
+    """Keyed stream, linear (both forms) and probit, ragged n and p down to 1, random hyper-parameter switches,
+    several chains per launch and relaunches every few sweeps."""
+    from oracle import gibbs_oracle as go
+    from pyblip_b200 import _lib
+    rng = np.random.default_rng(4242)
+    shapes = [(1, 1), (2, 1), (1, 3), (5, 33), (33, 5), (64, 64), (3, 70)]
+    shapes += [(int(rng.integers(2, 150)), int(rng.integers(1, 200))) for _ in range(9)]
+    for case, (n, p) in enumerate(shapes):
+        probit = case % 4 == 3
+        X = rng.standard_normal((n, p))
+        if p > 1:
+            X[:, 1:] += 0.8 * X[:, :-1]
+        beta = np.zeros(p)
+        k = min(3, p)
+        beta[rng.choice(p, size=k, replace=False)] = 1.5 * rng.standard_normal(k)
+        mu = X @ beta
+        hp_kw = dict(update_tau2=bool(rng.integers(2)), update_sigma2=bool(rng.integers(2)),
+                     update_p0=bool(rng.integers(2)), min_p0=float(rng.choice([0.0, 0.5, 0.95])),
+                     p0=float(rng.choice([0.5, 0.9, 0.99])), tau2=float(rng.choice([0.3, 1.0, 4.0])))
+        if probit:
+            hp_kw.update(update_sigma2=False, sigma2=1.0)         # probit/probit.py:27: the noise variance is fixed at 1
+        hp = go.hparams(**hp_kw)
+        cfg = _lib.SpikeSlabConfig(*[getattr(hp, f) for f, _ in hp._fields_])
+        N, chains, seed = 14, 3, int(rng.integers(1, 1 << 30))
+        design = _lib.Design.upload(X)
+        if probit:
+            z = (mu + rng.standard_normal(n) < 0).astype(np.int64)
+            data, modes = dict(z=z, probit=True), [_lib.MODE_RESIDUAL]
+        else:
+            y = mu + rng.standard_normal(n)
+            data, modes = dict(y=y, probit=False), [_lib.MODE_RESIDUAL, _lib.MODE_GRAM]
+        refs = [go.sample_spikeslab(N, X, hp=hp, seed=seed, chain=c, **data) for c in range(chains)]
+        for mode in modes:
+            smp = _lib.sample_spikeslab(design, cfg, chains=chains, n_keep=N, burn=0, seed=seed, mode=mode,
+                                        chunk_sweeps=int(rng.choice([0, 1, 5])), **data)
+            betas = smp.dense().reshape(chains, N, p)
+            hyper = dict(zip(("p0s", "tau2s", "sigma2s"), (a.reshape(chains, N) for a in smp.hyper())))
+            lat = smp.latents().reshape(chains, N, n) if probit else None
+            smp.close()
+            for c, ref in enumerate(refs):
+                tag = (case, n, p, probit, mode, c, hp_kw)
+                assert np.array_equal(betas[c] != 0, ref["betas"] != 0), tag
+                assert util.rel_err(betas[c], ref["betas"]) <= 1e-9, tag
+                for key, got in hyper.items():
+                    assert util.rel_err(got[c], ref[key]) <= 1e-9, tag + (key,)
+                if probit:
+                    assert util.rel_err(lat[c], ref["y_latent"]) <= 1e-9, tag
+        design.close()
+
+
+def test_nprior_on_random_problems(gpu):
+    """Keyed stream, every combination of the joint-W / grouped-alpha switches and both noise priors."""
+    from oracle import gibbs_oracle as go
+    from pyblip_b200 import _lib
+    rng = np.random.default_rng(909)
+    for case in range(8):
+        n = int(rng.integers(8, 120))
+        p = int(rng.integers(1, 90))
+        X = rng.standard_normal((n, p))
+        if p > 1:
+            X[:, 1:] += 0.6 * X[:, :-1]
+        beta = np.zeros(p)
+        k = min(3, p)
+        beta[rng.choice(p, size=k, replace=False)] = 2.0 * rng.standard_normal(k)
+        y = X @ beta + rng.standard_normal(n)
+        kw = dict(tauw2=float(rng.choice([0.5, 1.0, 3.0])), p0_init=float(rng.choice([0.7, 0.9])),
+                  min_p0=float(rng.choice([0.0, 0.6])), update_p0=int(rng.integers(2)),
+                  sigma_a0=2.0, sigma_b0=1.0, sigma_prior_type=int(case % 2),
+                  joint_sample_W=int((case >> 1) % 2), group_alpha_update=int((case >> 2) % 2))
+        cfg = _lib.NPriorConfig(kw["tauw2"], kw["p0_init"], kw["min_p0"], kw["update_p0"], kw["sigma_a0"],
+                                kw["sigma_b0"], kw["sigma_prior_type"], kw["joint_sample_W"],
+                                kw["group_alpha_update"], 0)
+        N, seed = 12, int(rng.integers(1, 1 << 30))
+        design = _lib.Design.upload(X)
+        smp = _lib.sample_nprior(design, cfg, y, chains=2, n_keep=N, burn=0, seed=seed)
+        out = {key: smp.get(key).reshape(2, N, -1) for key in ("alphas", "ws", "betas", "sigma2s", "alpha0s", "p0s")}
+        smp.close()
+        design.close()
+        for c in range(2):
+            orc = go.nprior_sample(N, X, y, seed=seed, chain=c, **kw)
+            tag = (case, n, p, c, kw)
+            assert np.array_equal(out["betas"][c] != 0, orc["betas"] != 0), tag
+            for key in ("alphas", "ws", "sigma2s", "alpha0s", "p0s"):
+                assert util.rel_err(out[key][c].reshape(orc[key].shape), orc[key]) <= 1e-9, tag + (key,)
+            scale = np.abs(orc["ws"]) * (np.abs(orc["alphas"]) + np.abs(orc["alpha0s"])[:, None])
+            excess = np.abs(out["betas"][c] - orc["betas"]) - 1e-9 * np.maximum(scale, np.abs(orc["betas"]))
+            assert excess.max() <= 0, tag                         # beta = w * max(alpha - alpha0, 0) cancels (test_nprior_gpu)
