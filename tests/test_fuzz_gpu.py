@@ -199,3 +199,77 @@ def test_probit_mean_cancels_to_exact_zero(gpu):
         assert np.array_equal(betas[c] != 0, ref["betas"] != 0), c
         assert util.rel_err(betas[c], ref["betas"]) <= 1e-9, c
         assert util.rel_err(lat[c], ref["y_latent"]) <= 1e-9, c
+
+
+def test_grid_peps_on_random_point_clouds(gpu):
+    """Dimensions 1-3, points on cell borders and on the ends of [0,1], clustered and scattered clouds, every
+    combination of shape / count_signals / extra centres: the output dict must equal the oracle's."""
+    from oracle import cts_oracle as co
+    from pyblip_b200 import create_groups_cts as cts
+    rng = np.random.default_rng(31)
+    for case in range(24):
+        d = int(rng.integers(1, 4))
+        N = int(rng.integers(1, 260))
+        n_src = int(rng.integers(1, 7))
+        grid = np.unique(rng.choice([1.0, 2.0, 3.0, 4.0, 7.0, 10.0, 16.0, 33.0, 100.0, 1000.0],
+                                    size=int(rng.integers(1, 6))))
+        true = rng.random((4, d))
+        locs = np.full((N, n_src, d), np.nan)
+        for i in range(N):
+            for k in range(n_src):
+                u = rng.random()
+                if u < 0.45:
+                    locs[i, k] = np.clip(true[rng.integers(4)] + 0.01 * rng.standard_normal(d), 0, 1)
+                elif u < 0.55:
+                    locs[i, k] = rng.integers(0, 11, size=d) / 10.0          # cell borders of the 10-grid, 0.0 and 1.0
+                elif u < 0.65:
+                    locs[i, k] = rng.random(d)
+        extra = rng.random((int(rng.integers(1, 6)), d)) if case % 3 else None
+        shape = "circle" if (d == 2 and case % 2) else "square"
+        cs = bool(rng.integers(2))
+        max_pep = float(rng.choice([0.25, 0.9, 1.0]))
+        kw = dict(count_signals=cs, extra_centers=extra, max_pep=max_pep, shape=shape)
+        if np.all(np.isnan(locs)):
+            continue
+        got = cts.grid_peps(locs, grid, **kw)
+        want = co.grid_peps(locs, grid, **kw)
+        assert got == want, (case, d, N, n_src, grid.tolist(), shape, cs, extra is not None, len(got), len(want))
+
+
+def test_changepoint_implicit_design_on_random_lengths(gpu):
+    """ChangepointSpikeSlab (closed-form Gram of the step design) against LinearSpikeSlab on the dense design,
+    same keyed stream, lengths around the 32/64-column tile borders and down to 2."""
+    from pyblip_b200 import LinearSpikeSlab, changepoint
+    rng = np.random.default_rng(58)
+    for T in (2, 3, 31, 32, 33, 64, 65, 97, int(rng.integers(100, 400))):
+        beta = np.zeros(T)
+        beta[rng.choice(T, size=min(3, T), replace=False)] = 4.0 * rng.standard_normal(min(3, T))
+        Y = np.cumsum(beta) + rng.standard_normal(T)
+        cp = changepoint.ChangepointSpikeSlab(Y)
+        cp.sample(N=15, burn=3, chains=2, seed=T)
+        for mode in ("gram", "residual"):
+            lm = LinearSpikeSlab(np.tril(np.ones((T, T))), Y)
+            lm.sample(N=15, burn=3, chains=2, seed=T, mode=mode)
+            assert np.array_equal(cp.betas != 0, lm.betas != 0), (T, mode)
+            assert util.rel_err(cp.betas, lm.betas) <= 1e-9, (T, mode)
+            for a, b in ((cp.sigma2s, lm.sigma2s), (cp.tau2s, lm.tau2s), (cp.p0s, lm.p0s)):
+                assert util.rel_err(a, b) <= 1e-9, (T, mode)
+
+
+def test_gram_build_on_ragged_shapes(gpu):
+    """X'X from the tensor-pipe kernel on shapes that do not fill its tiles, including one row / one column."""
+    from pyblip_b200 import _lib
+    rng = np.random.default_rng(66)
+    shapes = [(1, 1), (1, 40), (40, 1), (7, 129), (129, 7), (65, 64), (64, 65), (255, 257)]
+    shapes += [(int(rng.integers(1, 500)), int(rng.integers(1, 500))) for _ in range(6)]
+    for n, p in shapes:
+        X = rng.standard_normal((n, p)) * np.exp(rng.standard_normal(p))       # columns of very different scales
+        d = _lib.Design.upload(X)
+        d.build_gram()
+        G = d.gram()
+        ref = X.T @ X
+        scale = np.sqrt(np.outer(np.diag(ref), np.diag(ref)))
+        assert np.max(np.abs(G - ref) / scale) <= 1e-12, (n, p)
+        assert np.array_equal(G, G.T), (n, p)
+        assert util.rel_err(d.xl2(), (X ** 2).sum(0)) <= 1e-13, (n, p)
+        d.close()
