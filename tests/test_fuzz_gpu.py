@@ -273,3 +273,41 @@ def test_gram_build_on_ragged_shapes(gpu):
         assert np.array_equal(G, G.T), (n, p)
         assert util.rel_err(d.xl2(), (X ** 2).sum(0)) <= 1e-13, (n, p)
         d.close()
+
+
+def test_value_arena_overflow_replays_the_chunk(gpu):
+    """A posterior with most coordinates active needs far more room per kept sweep than the first guess
+    (max(64, p/16) values per row): the launch overflows the value arena, the chain state is restored and the
+    chunk replayed into a larger arena.  Results must equal the oracle's, for every sampler form."""
+    from oracle import gibbs_oracle as go
+    from pyblip_b200 import _lib
+    rng = np.random.default_rng(404)
+    n, p, N, chains, seed = 700, 420, 8, 48, 77     # 48 chains x 4 sweeps x ~400 values > the 65536-value floor
+    X = rng.standard_normal((n, p))
+    beta = 0.5 * rng.standard_normal(p)
+    y = X @ beta + rng.standard_normal(n)
+    legs = [("linear", _lib.MODE_RESIDUAL, 1), ("linear", _lib.MODE_GRAM, 1), ("probit", _lib.MODE_RESIDUAL, 1),
+            ("linear", _lib.MODE_GRAM, 3)]
+    design = _lib.Design.upload(X)
+    for kind, mode, bsize in legs:
+        probit = kind == "probit"
+        hp = go.hparams(p0=0.05, update_p0=False, update_sigma2=not probit)
+        cfg = _lib.SpikeSlabConfig(*[getattr(hp, f) for f, _ in hp._fields_])
+        data = dict(z=(y < 0).astype(np.int64), probit=True) if probit else dict(y=y, probit=False)
+        smp = _lib.sample_spikeslab(design, cfg, chains=chains, n_keep=N, burn=0, seed=seed, mode=mode,
+                                    bsize=bsize, chunk_sweeps=4, **data)
+        assert smp.info.sweep_launches > 2, (kind, mode, bsize, "no replay happened: the test no longer covers it")
+        betas = smp.dense().reshape(chains, N, p)
+        assert (betas != 0).mean() > 0.5
+        smp.close()
+        for c in (0, 17, chains - 1):
+            if bsize > 1:
+                ref = go.sample_spikeslab_multi(N, bsize, X, hp=hp, seed=seed, chain=c, **data)
+            else:
+                ref = go.sample_spikeslab(N, X, hp=hp, seed=seed, chain=c, **data)
+            assert np.array_equal(betas[c] != 0, ref["betas"] != 0), (kind, mode, bsize, c)
+            # ~400 draws per row, some within 1e-6 of zero by cancellation of mean and noise: bound the error
+            # by the scale of the row, not of the entry
+            err = np.max(np.abs(betas[c] - ref["betas"])) / np.max(np.abs(ref["betas"]))
+            assert err <= 1e-9, (kind, mode, bsize, c, err)
+    design.close()
