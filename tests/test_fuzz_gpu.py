@@ -311,3 +311,25 @@ def test_value_arena_overflow_replays_the_chunk(gpu):
             err = np.max(np.abs(betas[c] - ref["betas"])) / np.max(np.abs(ref["betas"]))
             assert err <= 1e-9, (kind, mode, bsize, c, err)
     design.close()
+
+
+def test_sequential_groups_on_random_samples(gpu):
+    """create_groups.sequential_groups (samples branch, create_groups.py:321-353) on random indicator matrices:
+    every max_size (also wider than p), prenarrowing with several q, PEP thresholds up to 1."""
+    from oracle import counting_oracle as co
+    from pyblip_b200 import create_groups as cg
+    rng = np.random.default_rng(88)
+    for case in range(40):
+        N = int(rng.integers(1, 900))
+        p = int(rng.integers(1, 120))
+        S = np.zeros((N, p), dtype=bool)
+        for j in rng.choice(p, size=min(p, int(rng.integers(0, 6))), replace=False):   # a few signals, each smeared
+            pos = np.clip(j + rng.integers(-2, 3, size=N), 0, p - 1)                    # over neighbouring columns
+            hit = rng.random(N) < rng.random()
+            S[np.nonzero(hit)[0], pos[hit]] = True
+        S |= rng.random((N, p)) < float(rng.choice([0.0, 0.01, 0.2]))
+        kw = dict(q=float(rng.choice([0.0, 0.05, 0.2, 0.5])), max_pep=float(rng.choice([0.1, 0.25, 0.7, 1.0])),
+                  max_size=int(rng.integers(1, 41)), prenarrow=bool(rng.integers(2)))
+        got = util.cg_list(cg.sequential_groups(S.astype(np.float64), **kw))
+        want = [(tuple(g), float(pep)) for g, pep in co.sequential_groups(S, **kw)]
+        assert got == want, (case, N, p, kw, len(got), len(want))
