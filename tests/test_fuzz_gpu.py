@@ -333,3 +333,52 @@ def test_sequential_groups_on_random_samples(gpu):
         got = util.cg_list(cg.sequential_groups(S.astype(np.float64), **kw))
         want = [(tuple(g), float(pep)) for g, pep in co.sequential_groups(S, **kw)]
         assert got == want, (case, N, p, kw, len(got), len(want))
+
+
+def test_launch_geometry_does_not_change_any_chain(gpu):
+    """Chains sharded over launches (the multi-GPU split), relaunches every few sweeps and a burn-in boundary inside a
+    chunk must give bit-identical output for every sampler: probit, block (both forms), neuronized prior."""
+    from pyblip_b200 import _lib
+    rng = np.random.default_rng(1234)
+    n, p, N, burn, seed = 130, 57, 11, 4, 99
+    X = rng.standard_normal((n, p))
+    X[:, 1:] += 0.5 * X[:, :-1]
+    beta = np.zeros(p)
+    beta[[3, 20, 41]] = [2.5, -3.0, 2.0]
+    y = X @ beta + rng.standard_normal(n)
+    z = (y < 0).astype(np.int64)
+    design = _lib.Design.upload(X)
+    from oracle import gibbs_oracle as go
+    legs = [dict(probit=True, mode=_lib.MODE_RESIDUAL, bsize=1), dict(probit=True, mode=_lib.MODE_RESIDUAL, bsize=3),
+            dict(probit=False, mode=_lib.MODE_RESIDUAL, bsize=4), dict(probit=False, mode=_lib.MODE_GRAM, bsize=2),
+            dict(probit=False, mode=_lib.MODE_RESIDUAL, bsize=1)]
+    for leg in legs:
+        hp = go.hparams(update_sigma2=not leg["probit"])
+        cfg = _lib.SpikeSlabConfig(*[getattr(hp, f) for f, _ in hp._fields_])
+        data = dict(z=z, probit=True) if leg["probit"] else dict(y=y, probit=False)
+
+        def run(chains, offset, chunk):
+            smp = _lib.sample_spikeslab(design, cfg, chains=chains, chain_offset=offset, n_keep=N, burn=burn,
+                                        seed=seed, mode=leg["mode"], bsize=leg["bsize"], chunk_sweeps=chunk, **data)
+            out = [smp.dense(), np.stack(smp.hyper(), axis=1)]
+            if leg["probit"]:
+                out.append(smp.latents())
+            smp.close()
+            return out
+        full = run(5, 0, 0)
+        for chunk in (1, 3, 7):
+            parts = [run(2, 0, chunk), run(3, 2, chunk)]
+            for k, whole in enumerate(full):
+                assert np.array_equal(whole, np.concatenate([parts[0][k], parts[1][k]])), (leg, chunk, k)
+    cfgn = _lib.NPriorConfig(1.0, 0.9, 0.0, 1, 2.0, 1.0, 0, 1, 1, 0)
+    keys = ("alphas", "ws", "betas", "sigma2s", "alpha0s", "p0s")
+
+    def run_np(chains, offset):
+        smp = _lib.sample_nprior(design, cfgn, y, chains=chains, chain_offset=offset, n_keep=N, burn=burn, seed=seed)
+        out = [smp.get(k) for k in keys]
+        smp.close()
+        return out
+    full, a, b = run_np(5, 0), run_np(2, 0), run_np(3, 2)
+    for k in range(len(keys)):
+        assert np.array_equal(full[k], np.concatenate([a[k], b[k]])), keys[k]
+    design.close()
