@@ -297,48 +297,48 @@ __global__ void __launch_bounds__(GB_BLOCK, 2) gibbs_residual_kernel(SweepParams
             ++n_windows;
             // ---- speculative dots of the next T columns against the current residual
             const int jl = perm_s[min(pos0 + lane, p - 1)];
-            double acc[GB_ROUND];
-#pragma unroll
-            for (int cc = 0; cc < GB_ROUND; ++cc) acc[cc] = 0.0;
-            for (int kb = 0; kb < n2; kb += 2 * GB_BLOCK) {   // warp-uniform trip count (shuffles inside)
-                const int k = kb + 2 * tid;
-                const bool ok = k < n2;
-                const double2 rk = ok ? *reinterpret_cast<const double2*>(r_s + k) : make_double2(0.0, 0.0);
-                const double* xrow = P.XT + (ok ? k : 0);
-#pragma unroll
-                for (int cc = 0; cc < GB_ROUND; ++cc) {
-                    const int jc = __shfl_sync(0xffffffffu, jl, cc);
-                    const double2 x = __ldg(reinterpret_cast<const double2*>(xrow + (int64_t)jc * P.ldx));
-                    acc[cc] = fma(x.x, rk.x, acc[cc]);
-                    acc[cc] = fma(x.y, rk.y, acc[cc]);
+            // warp 0 scores the window after the dots: what does not depend on them (indicator, uniform, ||X_j||^2)
+            // is fetched now, under the latency of the column loads
+            bool act = false;
+            double u_spec = 0.0, xl2_spec = 0.0;
+            if (warp == 0 && lane < T) {
+                act = (mask_s[jl >> 5] >> (jl & 31)) & 1u;
+                if (!act) {
+                    u_spec = u_s ? u_s[pos0 + lane] : rng_uniform(key, KIND_SPIKE_U, pos0 + lane, sweep, 0);
+                    xl2_spec = P.Xl2[jl];
                 }
             }
-            // ---- transpose-reduce: lane l ends with the warp's partial dot of column l
+            // each warp owns GB_ROUND / GB_NWARP whole columns: few accumulators, so many loads stay in flight
+            constexpr int CPW = GB_ROUND / GB_NWARP;
+            const double* xc[CPW];
+            double acc[CPW];
 #pragma unroll
-            for (int o = 16, cnt = 16; o >= 1; o >>= 1, cnt >>= 1) {
-                const bool upper = (lane & o) != 0;
+            for (int i = 0; i < CPW; ++i) {
+                xc[i] = P.XT + (int64_t)__shfl_sync(0xffffffffu, jl, warp * CPW + i) * P.ldx;
+                acc[i] = 0.0;
+            }
+#pragma unroll 4
+            for (int k = 2 * lane; k < n2; k += 64) {
+                const double2 rk = *reinterpret_cast<const double2*>(r_s + k);
 #pragma unroll
-                for (int i = 0; i < cnt; ++i) {
-                    double send = upper ? acc[i] : acc[i + cnt];
-                    double keep = upper ? acc[i + cnt] : acc[i];
-                    acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                for (int i = 0; i < CPW; ++i) {
+                    const double2 x = __ldg(reinterpret_cast<const double2*>(xc[i] + k));
+                    acc[i] = fma(x.x, rk.x, acc[i]);
+                    acc[i] = fma(x.y, rk.y, acc[i]);
                 }
             }
-            part[warp * 32 + lane] = acc[0];
+#pragma unroll
+            for (int i = 0; i < CPW; ++i) {
+                const double t = warp_sum(acc[i]);
+                if (lane == i) part[warp * CPW + i] = t;         // part[column of the window]
+            }
             __syncthreads();
             if (warp == 0) {
-                double d = 0.0;
-#pragma unroll
-                for (int w = 0; w < GB_NWARP; ++w) d += part[w * 32 + lane];
-                bool change = false, act = false;
+                const double d = part[lane];
+                bool change = false;
                 if (lane < T) {
-                    act = (mask_s[jl >> 5] >> (jl & 31)) & 1u;
                     if (act) change = true;
-                    else {
-                        double u = u_s ? u_s[pos0 + lane] : rng_uniform(key, KIND_SPIKE_U, pos0 + lane, sweep, 0);
-                        double kappa = kappa_of(d, P.Xl2[jl], h);
-                        change = !(u <= kappa);      // NaN kappa -> slab, like the reference
-                    }
+                    else change = !(u_spec <= kappa_of(d, xl2_spec, h));   // NaN kappa -> slab, like the reference
                 }
                 const unsigned m = __ballot_sync(0xffffffffu, change);
                 const int tstar = m ? __ffs(m) - 1 : -1;
