@@ -22,7 +22,8 @@
 
 constexpr int GB_BLOCK = 256;
 constexpr int GB_NWARP = GB_BLOCK / 32;
-constexpr int GB_ROUND = 32;      // residual mode: columns speculated per window
+constexpr int GB_ROUND = 32;      // residual mode: columns speculated per window (64 with two scoring warps was
+                                  // measured: no gain on probit C3, -20 % on linear C2 -- more columns redone after a change)
 constexpr int GB_HS = 6;          // doubles of per-chain scalar state: sigma2 tau2 p0 rr n_changes n_windows
 
 struct SweepParams {
