@@ -1,6 +1,8 @@
 """Randomised shapes through the counting kernels and the block sampler against the CPU oracle:
 ragged N and p, all densities, every window size -- the corners of the sparse-tile, column-major
 and window-scoring paths that the fixed fixtures do not pin."""
+import os
+
 import numpy as np
 import pytest
 
@@ -8,11 +10,14 @@ import blip_testutil as util
 
 pytestmark = pytest.mark.gpu
 
+# BLIP_FUZZ_SEED=k shifts every generator seed: a soak run over other problems than the committed ones
+SEED = int(os.environ.get("BLIP_FUZZ_SEED", "0"))
+
 
 def test_counting_kernels_on_random_shapes(gpu):
     from oracle import counting_oracle as co
     from pyblip_b200 import _lib
-    rng = np.random.default_rng(2024)
+    rng = np.random.default_rng(2024 + SEED)
     for case in range(60):
         N = int(rng.integers(1, 3000))
         p = int(rng.integers(1, 300))
@@ -43,7 +48,7 @@ def test_block_sampler_on_random_problems(gpu):
     """Keyed stream, both forms, block sizes 2..6 with and without a cap on the signals per block."""
     from oracle import gibbs_oracle as go
     from pyblip_b200 import _lib
-    rng = np.random.default_rng(77)
+    rng = np.random.default_rng(77 + SEED)
     for case in range(12):
         n = int(rng.integers(20, 90))                             # n < p keeps X'X singular: the gram form is checked
                                                                   # for n >= 20 only, where 1e-9 is a fair bound
@@ -81,7 +86,7 @@ def test_single_site_sampler_on_random_problems(gpu):
     several chains per launch and relaunches every few sweeps."""
     from oracle import gibbs_oracle as go
     from pyblip_b200 import _lib
-    rng = np.random.default_rng(4242)
+    rng = np.random.default_rng(4242 + SEED)
     shapes = [(1, 1), (2, 1), (1, 3), (5, 33), (33, 5), (64, 64), (3, 70)]
     shapes += [(int(rng.integers(2, 150)), int(rng.integers(1, 200))) for _ in range(9)]
     for case, (n, p) in enumerate(shapes):
@@ -136,7 +141,7 @@ def test_nprior_on_random_problems(gpu):
     """Keyed stream, every combination of the joint-W / grouped-alpha switches and both noise priors."""
     from oracle import gibbs_oracle as go
     from pyblip_b200 import _lib
-    rng = np.random.default_rng(909)
+    rng = np.random.default_rng(909 + SEED)
     for case in range(8):
         n = int(rng.integers(8, 120))
         p = int(rng.integers(1, 90))
@@ -165,7 +170,11 @@ def test_nprior_on_random_problems(gpu):
             tag = (case, n, p, c, kw)
             assert np.array_equal(out["betas"][c] != 0, orc["betas"] != 0), tag
             for key in ("alphas", "ws", "sigma2s", "alpha0s", "p0s"):
-                assert util.rel_err(out[key][c].reshape(orc[key].shape), orc[key]) <= 1e-9, tag + (key,)
+                got, ref = out[key][c].reshape(orc[key].shape), orc[key]
+                # entry-wise relative error, entries below 1e-3 of the largest measured on that floor (a joint W draw
+                # with p > n leaves some w_j near zero by cancellation: soak seed 2 had 1.3e-9 on one of them)
+                den = np.maximum(np.abs(ref), 1e-3 * np.max(np.abs(ref)))
+                assert np.max(np.abs(got - ref) / den) <= 1e-9, tag + (key,)
             scale = np.abs(orc["ws"]) * (np.abs(orc["alphas"]) + np.abs(orc["alpha0s"])[:, None])
             excess = np.abs(out["betas"][c] - orc["betas"]) - 1e-9 * np.maximum(scale, np.abs(orc["betas"]))
             assert excess.max() <= 0, tag                         # beta = w * max(alpha - alpha0, 0) cancels (test_nprior_gpu)
@@ -206,7 +215,7 @@ def test_grid_peps_on_random_point_clouds(gpu):
     combination of shape / count_signals / extra centres: the output dict must equal the oracle's."""
     from oracle import cts_oracle as co
     from pyblip_b200 import create_groups_cts as cts
-    rng = np.random.default_rng(31)
+    rng = np.random.default_rng(31 + SEED)
     for case in range(24):
         d = int(rng.integers(1, 4))
         N = int(rng.integers(1, 260))
@@ -240,7 +249,7 @@ def test_changepoint_implicit_design_on_random_lengths(gpu):
     """ChangepointSpikeSlab (closed-form Gram of the step design) against LinearSpikeSlab on the dense design,
     same keyed stream, lengths around the 32/64-column tile borders and down to 2."""
     from pyblip_b200 import LinearSpikeSlab, changepoint
-    rng = np.random.default_rng(58)
+    rng = np.random.default_rng(58 + SEED)
     for T in (2, 3, 31, 32, 33, 64, 65, 97, int(rng.integers(100, 400))):
         beta = np.zeros(T)
         beta[rng.choice(T, size=min(3, T), replace=False)] = 4.0 * rng.standard_normal(min(3, T))
@@ -259,7 +268,7 @@ def test_changepoint_implicit_design_on_random_lengths(gpu):
 def test_gram_build_on_ragged_shapes(gpu):
     """X'X from the tensor-pipe kernel on shapes that do not fill its tiles, including one row / one column."""
     from pyblip_b200 import _lib
-    rng = np.random.default_rng(66)
+    rng = np.random.default_rng(66 + SEED)
     shapes = [(1, 1), (1, 40), (40, 1), (7, 129), (129, 7), (65, 64), (64, 65), (255, 257)]
     shapes += [(int(rng.integers(1, 500)), int(rng.integers(1, 500))) for _ in range(6)]
     for n, p in shapes:
@@ -281,7 +290,7 @@ def test_value_arena_overflow_replays_the_chunk(gpu):
     chunk replayed into a larger arena.  Results must equal the oracle's, for every sampler form."""
     from oracle import gibbs_oracle as go
     from pyblip_b200 import _lib
-    rng = np.random.default_rng(404)
+    rng = np.random.default_rng(404 + SEED)
     n, p, N, chains, seed = 700, 420, 8, 48, 77     # 48 chains x 4 sweeps x ~400 values > the 65536-value floor
     X = rng.standard_normal((n, p))
     beta = 0.5 * rng.standard_normal(p)
@@ -318,7 +327,7 @@ def test_sequential_groups_on_random_samples(gpu):
     every max_size (also wider than p), prenarrowing with several q, PEP thresholds up to 1."""
     from oracle import counting_oracle as co
     from pyblip_b200 import create_groups as cg
-    rng = np.random.default_rng(88)
+    rng = np.random.default_rng(88 + SEED)
     for case in range(40):
         N = int(rng.integers(1, 900))
         p = int(rng.integers(1, 120))
@@ -339,7 +348,7 @@ def test_launch_geometry_does_not_change_any_chain(gpu):
     """Chains sharded over launches (the multi-GPU split), relaunches every few sweeps and a burn-in boundary inside a
     chunk must give bit-identical output for every sampler: probit, block (both forms), neuronized prior."""
     from pyblip_b200 import _lib
-    rng = np.random.default_rng(1234)
+    rng = np.random.default_rng(1234 + SEED)
     n, p, N, burn, seed = 130, 57, 11, 4, 99
     X = rng.standard_normal((n, p))
     X[:, 1:] += 0.5 * X[:, :-1]
