@@ -249,6 +249,8 @@ int blipgpu_bits_shape(blipgpu_bits* b, int64_t* N, int64_t* p);
 /* samples[:, cols]  (create_groups.py:117) -- compacted index space */
 int blipgpu_bits_select_columns(blipgpu_bits* b, const int64_t* cols, int64_t ncols,
                                 blipgpu_bits** out);
+/* samples[:, 0] = 0 in place (pyblip/changepoint.py:7: time 0 is never a change point). */
+int blipgpu_bits_clear_first_column(blipgpu_bits* b);
 /* Unpack to a host uint8 (N x p) matrix (tests / fallbacks). */
 int blipgpu_bits_to_dense(blipgpu_bits* b, uint8_t* out);
 
@@ -305,6 +307,19 @@ int blipgpu_gridcounts_free(blipgpu_gridcounts* r);
  * [a][b/32] set iff regions a and b overlap (the diagonal is set). */
 int blipgpu_overlap_bits(blipgpu_ctx* ctx, const float* centers, const float* radii, int64_t G,
                          int32_t d, int32_t circle, uint32_t* out_bits);
+
+/* ---- parity hooks ---------------------------------------------------------- */
+/* The device arithmetic of `sample_truncnorm` (pyblip/cython_utils/_truncnorm.pyx:42-107) on
+ * RECORDED variate sequences instead of the keyed Philox stream: call i consumes uniforms
+ * u[u_at[i]...] in the order of the reference's rand()/RAND_MAX calls (:50-53) and normals
+ * z[z_at[i]...] in the order of its np.random.randn() calls (:63); u_used[i] / z_used[i] return
+ * how many it took.  All pointers are HOST arrays.  Used by the tests to compare the device
+ * with values produced by the reference's own compiled sampler (tests/golden/
+ * truncnorm_values.npz, written by oracle/pin_truncnorm.py); the samplers never call it. */
+int blipgpu_debug_truncnorm(blipgpu_ctx* ctx, int64_t count, const double* mean, const double* var,
+                            const double* b, const int32_t* lower_interval, const double* u,
+                            int64_t nu, const int64_t* u_at, const double* z, int64_t nz,
+                            const int64_t* z_at, double* out, int64_t* u_used, int64_t* z_used);
 
 #ifdef __cplusplus
 }

@@ -185,10 +185,23 @@ void orc_permutation(uint64_t seed, uint32_t chain, uint32_t sweep, int p,
 /* ------------------------------------------------------------------ */
 typedef struct {
     uint64_t seed; uint32_t chain, obs, event, attempt;
+    /* injected variates (value-level pin against the reference, oracle/pin_truncnorm.py):
+     * when inj_u is set, uniforms are read from inj_u[iu++] in the order the reference's
+     * rand()/RAND_MAX calls consume them and normals from inj_z[iz++] in the order of its
+     * np.random.randn() calls; otherwise the keyed Philox sub-stream is used. */
+    const double *inj_u, *inj_z; int64_t iu, iz, nu, nz; int overflow;
 } tn_stream;
 
 static double tn_next_pair(tn_stream *s, double *second)
-{   /* two uniforms from one Philox call (exponential-proposal branch) */
+{   /* the two uniforms of one attempt of the exponential-proposal branch
+     * (_truncnorm.pyx:50-53: first the proposal, then the accept test) */
+    if (s->inj_u) {
+        if (s->iu + 2 > s->nu) { s->overflow = 1; *second = 0.0; return 0.5; }   /* forces acceptance */
+        double first = s->inj_u[s->iu];
+        *second = s->inj_u[s->iu + 1];
+        s->iu += 2;
+        return first;
+    }
     uint32_t w[4];
     orc_philox4x32_10((uint32_t)s->seed, (uint32_t)(s->seed >> 32), s->obs,
                       s->event, s->chain,
@@ -200,6 +213,10 @@ static double tn_next_pair(tn_stream *s, double *second)
 
 static double tn_next_normal(tn_stream *s)
 {
+    if (s->inj_z) {
+        if (s->iz + 1 > s->nz) { s->overflow = 1; return 1e300; }                /* forces acceptance */
+        return s->inj_z[s->iz++];
+    }
     uint32_t w[4];
     orc_philox4x32_10((uint32_t)s->seed, (uint32_t)(s->seed >> 32), s->obs,
                       s->event, s->chain,
@@ -228,17 +245,44 @@ static double truncnorm_std(double a, tn_stream *s)
     }
 }
 
-/* sample_truncnorm(mean, var, b, lower_interval)   (_truncnorm.pyx:88-107) */
-double orc_truncnorm(uint64_t seed, uint32_t chain, uint32_t event, uint32_t obs,
-                     double mean, double var, double b, int lower_interval)
+/* sample_truncnorm(mean, var, b, lower_interval)   (_truncnorm.pyx:88-107): the one
+ * arithmetic path behind both the keyed and the injected entry point */
+static double truncnorm_from(tn_stream *s, double mean, double var, double b, int lower_interval)
 {
-    tn_stream s = { seed, chain, obs, event, 0 };
     double scale = sqrt(var);
     double a = (b - mean) / scale;
     double z;
-    if (lower_interval == 0) z = truncnorm_std(a, &s);
-    else z = -1 * truncnorm_std(-1 * a, &s);
+    if (lower_interval == 0) z = truncnorm_std(a, s);
+    else z = -1 * truncnorm_std(-1 * a, s);
     return mean + scale * z;
+}
+
+double orc_truncnorm(uint64_t seed, uint32_t chain, uint32_t event, uint32_t obs,
+                     double mean, double var, double b, int lower_interval)
+{
+    tn_stream s = { seed, chain, obs, event, 0, NULL, NULL, 0, 0, 0, 0, 0 };
+    return truncnorm_from(&s, mean, var, b, lower_interval);
+}
+
+/* `count` consecutive sample_truncnorm calls fed from recorded variate sequences: u[] in the
+ * order of the reference's rand()/RAND_MAX calls, z[] in the order of its np.random.randn()
+ * calls.  used[0], used[1] return how many of each were consumed; u_at[i], z_at[i] (optional)
+ * the offsets at which call i started.  Returns -1 if a sequence runs out. */
+int orc_truncnorm_injected(int64_t count, const double *mean, const double *var, const double *b,
+                           const int32_t *lower_interval, const double *u, int64_t nu,
+                           const double *z, int64_t nz, double *out, int64_t *used,
+                           int64_t *u_at, int64_t *z_at)
+{
+    static const double dummy = 0.5;
+    tn_stream s = { 0, 0, 0, 0, 0, u ? u : &dummy, z ? z : &dummy, 0, 0, u ? nu : 0, z ? nz : 0, 0 };
+    for (int64_t i = 0; i < count; ++i) {
+        if (u_at) u_at[i] = s.iu;
+        if (z_at) z_at[i] = s.iz;
+        out[i] = truncnorm_from(&s, mean[i], var[i], b[i], lower_interval[i]);
+        if (s.overflow) return -1;
+    }
+    used[0] = s.iu; used[1] = s.iz;
+    return 0;
 }
 
 /* ------------------------------------------------------------------ */

@@ -174,6 +174,33 @@ CASES = [
 ]
 
 
+def reference_run(X, y, probit, hp, N, chain, np_seed, lin=None):
+    """One chain of the reference's compiled `_sample_spikeslab` (oracle/_ref) with its native RNG,
+    every variate recorded.  Returns (reference outputs, recorded streams keyed like the C ABI's
+    blipgpu_streams: perm, u, z, invgamma, p0_draw, gamma_draw).  Used by tests/test_configs_gpu.py
+    to replay BASELINE's full-size configurations through the CUDA path."""
+    if lin is None:
+        ref_loader.load()
+        from pyblip.linear import _linear as lin
+    n, p = X.shape
+    np.random.seed(np_seed)
+    zlab = np.asarray(y).astype(np.int64) if probit else np.zeros(1, dtype=np.int64)
+    ybuf = np.zeros(n) if probit else np.array(y, dtype=np.float64)
+    Xc = np.ascontiguousarray(X, dtype=np.float64)
+    with Recorder(N, n, p, chain, lin, probit) as rec:
+        ref = lin._sample_spikeslab(
+            N=N, X=Xc, y=ybuf, z=zlab, probit=int(probit),
+            tau2=hp["tau2"], update_tau2=int(hp["update_tau2"]),
+            tau2_a0=hp["tau2_a0"], tau2_b0=hp["tau2_b0"],
+            sigma2=hp["sigma2"], update_sigma2=int(hp["update_sigma2"]),
+            sigma2_a0=hp["sigma2_a0"], sigma2_b0=hp["sigma2_b0"],
+            p0=hp["p0"], update_p0=int(hp["update_p0"]), min_p0=hp["min_p0"],
+            p0_a0=hp["p0_a0"], p0_b0=hp["p0_b0"])
+    st = rec.streams(hp)
+    st["z"] = st.pop("zn")
+    return ref, st, rec
+
+
 def rel_err(a, b):
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     den = np.maximum(np.abs(b), 1e-300)

@@ -32,11 +32,12 @@ SYMBOLS = [
     "blipgpu_samples_info_get", "blipgpu_samples_hyper", "blipgpu_samples_dense",
     "blipgpu_samples_csr", "blipgpu_samples_latents", "blipgpu_samples_free",
     "blipgpu_bits_from_samples", "blipgpu_bits_from_dense", "blipgpu_bits_shape",
-    "blipgpu_bits_select_columns", "blipgpu_bits_to_dense",
+    "blipgpu_bits_select_columns", "blipgpu_bits_to_dense", "blipgpu_bits_clear_first_column",
     "blipgpu_count_columns", "blipgpu_count_sequential", "blipgpu_count_groups", "blipgpu_count_pairs", "blipgpu_count_false_rows",
     "blipgpu_bits_free",
     "blipgpu_grid_count", "blipgpu_gridcounts_sizes", "blipgpu_gridcounts_get", "blipgpu_gridcounts_free",
     "blipgpu_overlap_bits",
+    "blipgpu_debug_truncnorm",
 ]
 
 
@@ -461,6 +462,10 @@ class Bits:
                                                  C.c_int64(cols.shape[0]), C.byref(h)))
         return Bits(self.ctx, h)
 
+    def clear_first_column(self):
+        """samples[:, 0] = 0 in place (changepoint.py:7)."""
+        check(load().blipgpu_bits_clear_first_column(self._h))
+
     def to_dense(self):
         out = np.empty((self.N, self.p), dtype=np.uint8)
         check(load().blipgpu_bits_to_dense(self._h, C.c_void_p(out.ctypes.data)))
@@ -589,7 +594,10 @@ class NPriorSamples:
     def bits(self, zero_first_column=False):
         h = C.c_void_p()
         check(load().blipgpu_nprior_bits(self._h, C.byref(h)))
-        return Bits(self.ctx, h)
+        bits = Bits(self.ctx, h)
+        if zero_first_column:
+            bits.clear_first_column()
+        return bits
 
     def close(self):
         if getattr(self, "_h", None):
@@ -678,3 +686,22 @@ def overlap_bits(centers, radii, circle, ctx=None):
                                       C.c_int64(G), C.c_int32(d), C.c_int32(int(bool(circle))),
                                       C.c_void_p(out.ctypes.data)))
     return out
+
+
+def debug_truncnorm(mean, var, b, lower, u, u_at, z, z_at, ctx=None):
+    """``blipgpu_debug_truncnorm``: the device arithmetic of ``sample_truncnorm`` on recorded
+    uniform / normal sequences (parity hook; the samplers use the keyed stream)."""
+    ctx = ctx or Context.get()
+    f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)   # noqa: E731
+    i64 = lambda a: np.ascontiguousarray(a, dtype=np.int64)     # noqa: E731
+    mean, var, b, u, z = f64(mean), f64(var), f64(b), f64(u), f64(z)
+    lower = np.ascontiguousarray(lower, dtype=np.int32)
+    u_at, z_at = i64(u_at), i64(z_at)
+    m = mean.shape[0]
+    out = np.empty(m)
+    uu, zu = np.empty(m, dtype=np.int64), np.empty(m, dtype=np.int64)
+    ptr = lambda a: C.c_void_p(a.ctypes.data)   # noqa: E731
+    check(load().blipgpu_debug_truncnorm(ctx._h, C.c_int64(m), ptr(mean), ptr(var), ptr(b), ptr(lower),
+                                         ptr(u), C.c_int64(u.shape[0]), ptr(u_at), ptr(z),
+                                         C.c_int64(z.shape[0]), ptr(z_at), ptr(out), ptr(uu), ptr(zu)))
+    return out, uu, zu

@@ -249,23 +249,23 @@ extern "C" int blipgpu_design_upload(blipgpu_ctx* ctx, const double* X, int64_t 
     if (!d) { blip_set_error("host allocation failed"); return BLIP_ERR_NOMEM; }
     d->ctx = ctx; d->kind = BLIPGPU_DESIGN_DENSE; d->n = n; d->p = p;
     d->ldx = round_up(n, 4); d->G = nullptr; d->ldg = 0; d->XT = nullptr; d->Xl2 = nullptr;
-    double* Xrow = nullptr;
+    struct DesignGuard { blipgpu_design* d; ~DesignGuard() { if (d) blipgpu_design_free(d); } } guard{ d };
+    DevBuf Xrow;                                   // row-major staging copy, freed on every exit
+    BLIP_TRY(Xrow.alloc(sizeof(double) * n * p));
     cudaError_t e;
-    if ((e = cudaMalloc(&Xrow, sizeof(double) * n * p)) != cudaSuccess ||
-        (e = cudaMalloc(&d->XT, sizeof(double) * p * d->ldx)) != cudaSuccess ||
+    if ((e = cudaMalloc(&d->XT, sizeof(double) * p * d->ldx)) != cudaSuccess ||
         (e = cudaMalloc(&d->Xl2, sizeof(double) * p)) != cudaSuccess) {
         blip_set_error("design_upload: cudaMalloc failed: %s", cudaGetErrorString(e));
-        cudaFree(Xrow); cudaFree(d->XT); cudaFree(d->Xl2); delete d;
         return BLIP_ERR_NOMEM;
     }
-    CUDA_TRY(cudaMemcpyAsync(Xrow, X, sizeof(double) * n * p, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(Xrow.ptr, X, sizeof(double) * n * p, cudaMemcpyHostToDevice, ctx->stream));
     dim3 grid((unsigned)((p + 31) / 32), (unsigned)((d->ldx + 31) / 32));
-    transpose_kernel<<<grid, dim3(32, 8), 0, ctx->stream>>>(Xrow, d->XT, n, p, d->ldx);
+    transpose_kernel<<<grid, dim3(32, 8), 0, ctx->stream>>>(Xrow.as<double>(), d->XT, n, p, d->ldx);
     xl2_kernel<<<(unsigned)((p + 7) / 8), 256, 0, ctx->stream>>>(d->XT, d->Xl2, n, p, d->ldx);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     ctx->kernel_launches += 2; ctx->h2d_bytes += (int64_t)sizeof(double) * n * p;
-    CUDA_TRY(cudaFree(Xrow));
+    guard.d = nullptr;
     *out = d;
     return BLIP_OK;
 }
@@ -283,11 +283,13 @@ extern "C" int blipgpu_design_changepoint(blipgpu_ctx* ctx, int64_t T, blipgpu_d
     blipgpu_design* d = new (std::nothrow) blipgpu_design();
     if (!d) { blip_set_error("host allocation failed"); return BLIP_ERR_NOMEM; }
     d->ctx = ctx; d->kind = BLIPGPU_DESIGN_CHANGEPOINT; d->n = T; d->p = T; d->ldx = 0;
-    d->XT = nullptr; d->G = nullptr; d->ldg = 0;
+    d->XT = nullptr; d->G = nullptr; d->ldg = 0; d->Xl2 = nullptr;
+    struct DesignGuard { blipgpu_design* d; ~DesignGuard() { if (d) blipgpu_design_free(d); } } guard{ d };
     CUDA_TRY(cudaMalloc(&d->Xl2, sizeof(double) * T));
     changepoint_xl2_kernel<<<(unsigned)((T + 255) / 256), 256, 0, ctx->stream>>>(d->Xl2, T);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    guard.d = nullptr;
     *out = d;
     return BLIP_OK;
 }
@@ -327,5 +329,56 @@ extern "C" int blipgpu_design_free(blipgpu_design* d)
     cudaSetDevice(d->ctx->device);
     cudaFree(d->XT); cudaFree(d->Xl2); cudaFree(d->G);
     delete d;
+    return BLIP_OK;
+}
+
+// ---------------------------------------------------------------------------
+// value-level pin of the truncated normal: the device arithmetic of common.cuh on recorded
+// variate sequences (see include/blipgpu.h)
+// ---------------------------------------------------------------------------
+__global__ void debug_truncnorm_kernel(int64_t count, const double* mean, const double* var, const double* b,
+                                       const int32_t* lower, const double* u, int64_t nu, const int64_t* u_at,
+                                       const double* z, int64_t nz, const int64_t* z_at, double* out,
+                                       int64_t* u_used, int64_t* z_used)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    TnInjected src{ u, z, u_at[i], z_at[i], nu, nz };
+    out[i] = truncnorm_from(src, mean[i], var[i], b[i], lower[i]);
+    u_used[i] = src.iu - u_at[i];
+    z_used[i] = src.iz - z_at[i];
+}
+
+extern "C" int blipgpu_debug_truncnorm(blipgpu_ctx* ctx, int64_t count, const double* mean, const double* var,
+                                       const double* b, const int32_t* lower_interval, const double* u,
+                                       int64_t nu, const int64_t* u_at, const double* z, int64_t nz,
+                                       const int64_t* z_at, double* out, int64_t* u_used, int64_t* z_used)
+{
+    BLIP_TRY(blip_ctx_activate(ctx));
+    if (count <= 0 || !mean || !var || !b || !lower_interval || !u_at || !z_at || !out || !u_used || !z_used) {
+        blip_set_error("debug_truncnorm: bad arguments"); return BLIP_ERR_ARG;
+    }
+    DevBuf d_mean, d_var, d_b, d_lo, d_u, d_uat, d_z, d_zat, d_out, d_uu, d_zu;
+    auto up = [&](DevBuf& buf, const void* src, size_t bytes) -> int {
+        BLIP_TRY(buf.alloc(std::max<size_t>(bytes, 8)));
+        if (bytes) CUDA_TRY(cudaMemcpyAsync(buf.ptr, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        return BLIP_OK;
+    };
+    BLIP_TRY(up(d_mean, mean, sizeof(double) * count)); BLIP_TRY(up(d_var, var, sizeof(double) * count));
+    BLIP_TRY(up(d_b, b, sizeof(double) * count)); BLIP_TRY(up(d_lo, lower_interval, sizeof(int32_t) * count));
+    BLIP_TRY(up(d_u, u, sizeof(double) * nu)); BLIP_TRY(up(d_uat, u_at, sizeof(int64_t) * count));
+    BLIP_TRY(up(d_z, z, sizeof(double) * nz)); BLIP_TRY(up(d_zat, z_at, sizeof(int64_t) * count));
+    BLIP_TRY(d_out.alloc(sizeof(double) * count)); BLIP_TRY(d_uu.alloc(sizeof(int64_t) * count));
+    BLIP_TRY(d_zu.alloc(sizeof(int64_t) * count));
+    debug_truncnorm_kernel<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(
+        count, d_mean.as<double>(), d_var.as<double>(), d_b.as<double>(), d_lo.as<int32_t>(), d_u.as<double>(), nu,
+        d_uat.as<int64_t>(), d_z.as<double>(), nz, d_zat.as<int64_t>(), d_out.as<double>(), d_uu.as<int64_t>(),
+        d_zu.as<int64_t>());
+    CUDA_TRY(cudaGetLastError());
+    ctx->kernel_launches += 1;
+    CUDA_TRY(cudaMemcpyAsync(out, d_out.ptr, sizeof(double) * count, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(u_used, d_uu.ptr, sizeof(int64_t) * count, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(z_used, d_zu.ptr, sizeof(int64_t) * count, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return BLIP_OK;
 }

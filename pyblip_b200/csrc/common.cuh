@@ -188,34 +188,59 @@ __device__ inline double rng_beta(const RngKey& key, uint32_t proposal, uint32_t
 
 // Z ~ N(0,1) | Z >= a.  Exponential-proposal rejection for a >= 0.15, normal
 // rejection otherwise: the algorithm of the reference's truncated-normal
-// primitive (/root/reference/pyblip/cython_utils/_truncnorm.pyx:42-86), attempts
-// drawn from the keyed sub-stream (kind, c0, c1).
-// `first_normal`, when given, is box_muller(rng_words(key, kind, c0, c1, 0)) computed ahead of
-// time by the caller (the first attempt of the normal-rejection branch does not depend on a).
-__device__ inline double truncnorm_std(const RngKey& key, uint32_t kind, uint32_t c0, uint32_t c1,
-                                       double a, const double* first_normal = nullptr)
+// primitive (/root/reference/pyblip/cython_utils/_truncnorm.pyx:42-86).  The arithmetic is
+// written once, over a variate source:
+//   TnKeyed     attempts drawn from the keyed sub-stream (kind, c0, c1) -- the product path;
+//               `first_normal`, when given, is box_muller(rng_words(key, kind, c0, c1, 0)) computed
+//               ahead of time by the caller (the first attempt of the normal-rejection branch does
+//               not depend on a);
+//   TnInjected  uniforms / normals read from recorded sequences in consumption order -- the
+//               value-level pin against the reference's own rand() / randn() draws
+//               (blipgpu_debug_truncnorm, oracle/pin_truncnorm.py).
+// Attempts are capped so that a NaN argument (upstream bug) cannot hang the GPU.
+struct TnKeyed {
+    const RngKey& key; uint32_t kind, c0, c1; const double* first_normal; uint32_t attempt;
+    static constexpr uint32_t kMaxAttempts = 1u << 14;
+    __device__ __forceinline__ bool pair(double& y, double& u2) {
+        if (attempt >= kMaxAttempts) return false;
+        const uint4 w = rng_words(key, kind, c0, c1, attempt++);
+        y = u52(w.x, w.y); u2 = u52(w.z, w.w);
+        return true;
+    }
+    __device__ __forceinline__ bool normal(double& z) {
+        if (attempt >= kMaxAttempts) return false;
+        if (attempt == 0 && first_normal) { z = *first_normal; attempt = 1; return true; }
+        z = box_muller(rng_words(key, kind, c0, c1, attempt++));
+        return true;
+    }
+};
+struct TnInjected {
+    const double* u; const double* z; long long iu, iz, nu, nz;
+    __device__ __forceinline__ bool pair(double& y, double& u2) {
+        if (iu + 2 > nu) return false;
+        y = u[iu]; u2 = u[iu + 1]; iu += 2;
+        return true;
+    }
+    __device__ __forceinline__ bool normal(double& zz) {
+        if (iz + 1 > nz) return false;
+        zz = z[iz++];
+        return true;
+    }
+};
+
+template <class Src>
+__device__ __forceinline__ double truncnorm_std_from(Src& src, double a)
 {
-    // attempts are capped so that a NaN argument (upstream bug) cannot hang the GPU
-    const uint32_t kMaxAttempts = 1u << 14;
-    uint32_t attempt = 0;
-    if (a >= 0.150) {
-        while (attempt < kMaxAttempts) {
-            uint4 w = rng_words(key, kind, c0, c1, attempt++);
-            double y = u52(w.x, w.y);
-            double u2 = u52(w.z, w.w);
+    if (a >= 0.150) {                        // _expo_tn_sampler :42-55
+        double y, u2;
+        while (src.pair(y, u2)) {
             y = -1 * log(y) / a;
             double rho = exp(-0.5 * y * y);
             if (u2 <= rho) return y + a;
         }
-    } else {
-        if (first_normal) {
-            double z = *first_normal;
-            attempt = 1;
-            if (a >= 0) z = fabs(z);
-            if (z >= a) return z;
-        }
-        while (attempt < kMaxAttempts) {
-            double z = box_muller(rng_words(key, kind, c0, c1, attempt++));
+    } else {                                 // _norm_tn_sampler :57-69
+        double z;
+        while (src.normal(z)) {
             if (a >= 0) z = fabs(z);
             if (z >= a) return z;
         }
@@ -224,16 +249,30 @@ __device__ inline double truncnorm_std(const RngKey& key, uint32_t kind, uint32_
 }
 
 // sample_truncnorm(mean, var, b, lower_interval)  (_truncnorm.pyx:88-107)
-__device__ inline double truncnorm(const RngKey& key, uint32_t kind, uint32_t c0, uint32_t c1,
-                                   double mean, double var, double b, int lower_interval,
-                                   const double* first_normal = nullptr)
+template <class Src>
+__device__ __forceinline__ double truncnorm_from(Src& src, double mean, double var, double b, int lower_interval)
 {
     double scale = sqrt(var);
     double a = (b - mean) / scale;
     double z;
-    if (lower_interval == 0) z = truncnorm_std(key, kind, c0, c1, a, first_normal);
-    else z = -1 * truncnorm_std(key, kind, c0, c1, -1 * a, first_normal);
+    if (lower_interval == 0) z = truncnorm_std_from(src, a);
+    else z = -1 * truncnorm_std_from(src, -1 * a);
     return mean + scale * z;
+}
+
+__device__ inline double truncnorm_std(const RngKey& key, uint32_t kind, uint32_t c0, uint32_t c1,
+                                       double a, const double* first_normal = nullptr)
+{
+    TnKeyed src{ key, kind, c0, c1, first_normal, 0u };
+    return truncnorm_std_from(src, a);
+}
+
+__device__ inline double truncnorm(const RngKey& key, uint32_t kind, uint32_t c0, uint32_t c1,
+                                   double mean, double var, double b, int lower_interval,
+                                   const double* first_normal = nullptr)
+{
+    TnKeyed src{ key, kind, c0, c1, first_normal, 0u };
+    return truncnorm_from(src, mean, var, b, lower_interval);
 }
 
 // ---------------------------------------------------------------------------

@@ -574,6 +574,22 @@ extern "C" int blipgpu_bits_from_samples(blipgpu_samples* s, int32_t zero_first_
     return BLIP_OK;
 }
 
+extern "C" int blipgpu_bits_clear_first_column(blipgpu_bits* b)
+{
+    if (!b) { blip_set_error("bits_clear_first_column: NULL handle"); return BLIP_ERR_ARG; }
+    BLIP_TRY(blip_ctx_activate(b->ctx));
+    if (b->N == 0) return BLIP_OK;
+    cudaStream_t st = b->ctx->stream;
+    clear_first_column_kernel<<<(unsigned)((b->N + 255) / 256), 256, 0, st>>>(b->bits, b->N);
+    CUDA_TRY(cudaGetLastError());
+    if (b->colbits) {                       // the column-major copy holds column 0 in its first NW words
+        CUDA_TRY(cudaMemsetAsync(b->colbits, 0, sizeof(uint32_t) * (size_t)b->NW, st));
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    b->ctx->kernel_launches += 1;
+    return BLIP_OK;
+}
+
 extern "C" int blipgpu_bits_from_dense(blipgpu_ctx* ctx, const void* samples, int32_t dtype, int64_t N,
                                        int64_t p, blipgpu_bits** out)
 {

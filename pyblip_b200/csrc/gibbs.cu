@@ -104,23 +104,6 @@ __global__ void block_gram_kernel(const double* __restrict__ XT, double* __restr
     }
 }
 
-struct DevBuf {
-    void* ptr = nullptr; size_t bytes = 0;
-    int alloc(size_t b) {
-        bytes = b;
-        if (b == 0) { ptr = nullptr; return BLIP_OK; }
-        cudaError_t e = cudaMalloc(&ptr, b);
-        if (e != cudaSuccess) {
-            ptr = nullptr;
-            blip_set_error("cudaMalloc(%zu bytes) failed: %s", b, cudaGetErrorString(e));
-            return BLIP_ERR_NOMEM;
-        }
-        return BLIP_OK;
-    }
-    ~DevBuf() { if (ptr) cudaFree(ptr); }
-    template <class T> T* as() { return reinterpret_cast<T*>(ptr); }
-};
-
 template <class T>
 int upload_chunk(T* dst, const T* src_host, int64_t chains, int64_t total_per_chain,
                  int64_t off_per_chain, int64_t count_per_chain, cudaStream_t st)
@@ -613,16 +596,20 @@ static int sample_impl(blipgpu_ctx* ctx, blipgpu_design* design,
                 if (launch_log) fprintf(stderr, "[blipgpu] launch sweeps %lld..%lld grid %u: %.3f ms\n",
                                         (long long)sweep0, (long long)(sweep0 + Sc), grid, ms);
             }
-            int ovf = 0;
+            int ovf = 0, nerr = 0;
             unsigned long long used = 0;
             CUDA_TRY(cudaMemcpyAsync(&ovf, d_ovf.ptr, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(&nerr, d_numerr.ptr, sizeof(int), cudaMemcpyDeviceToHost, st));
             CUDA_TRY(cudaMemcpyAsync(&used, smp->arena_used, sizeof(used), cudaMemcpyDeviceToHost, st));
             CUDA_TRY(cudaStreamSynchronize(st));
-            if (block) {
-                int nerr = 0;
-                CUDA_TRY(cudaMemcpy(&nerr, d_numerr.ptr, sizeof(int), cudaMemcpyDeviceToHost));
-                if (nerr) {
+            {
+                if (nerr == 1) {
                     blip_set_error("dpotrf exited with INFO != 0: a block model's matrix is not positive definite. Try setting bsize=1.");
+                    return BLIP_ERR_NUMERIC;
+                }
+                if (nerr) {
+                    blip_set_error("sample_spikeslab: a chain's sigma2 / tau2 / p0 became non-finite in sweeps %lld..%lld "
+                                   "(degenerate data or hyper-priors)", (long long)sweep0, (long long)(sweep0 + Sc));
                     return BLIP_ERR_NUMERIC;
                 }
             }

@@ -190,6 +190,10 @@ __device__ inline void sweep_epilogue(const SweepParams& P, SweepShared* sh, con
             }
         }
         if (cf.update_sigma2 == 1) {
+            // gram form tracks ||r||^2 by a recurrence (and rebuilds it as y'y - b'(q0+q)); on a
+            // near-exact fit both cancel and can land a rounding error below zero, where the
+            // reference's dnrm2(r) cannot: clamp, or sqrt would poison sigma2 and every kappa after it
+            ssr = fmax(ssr, 0.0);
             double r2 = sqrt(ssr);             // dnrm2 ...
             r2 = r2 * r2;                      // ... squared (:77-78)
             double sigma_b = r2 / 2.0 + cf.sigma2_b0;
@@ -202,6 +206,9 @@ __device__ inline void sweep_epilogue(const SweepParams& P, SweepShared* sh, con
                                     : rng_gamma(key, SLOT_TAU_GAMMA, sweep, cf.tau2_a0 + (double)k / 2.0);
             sh->tau2 = (cf.tau2_b0 + ss / 2.0) / g;
         }
+        // a non-finite hyper-parameter makes every later decision meaningless: report it (the host
+        // raises BLIPGPU_ERR_NUMERIC) instead of recording garbage.  p0 == 1 is legal (quirk 1).
+        if (!isfinite(sh->sigma2) || !isfinite(sh->tau2) || isnan(sh->p0)) atomicMax(P.numeric_err, 2);
     }
     __syncthreads();
 

@@ -136,6 +136,9 @@ int blip_gram_build(blipgpu_design* d)
                        8.0 * p * d->ldg / 1e9, (long long)p, (long long)p, cudaGetErrorString(e));
         return BLIP_ERR_NOMEM;
     }
+    // anything that fails below must not leave a half-built matrix behind: a later
+    // blipgpu_design_build_gram would take a non-NULL G for a finished one
+    struct GramGuard { blipgpu_design* d; bool ok; ~GramGuard() { if (!ok) { cudaFree(d->G); d->G = nullptr; } } } guard{ d, false };
     CUDA_TRY(cudaMemsetAsync(d->G, 0, sizeof(double) * (size_t)p * d->ldg, ctx->stream));
     const int ntile = (int)((p + TILE - 1) / TILE);
     const int64_t nblocks = (int64_t)ntile * (ntile + 1) / 2;
@@ -147,5 +150,6 @@ int blip_gram_build(blipgpu_design* d)
     CUDA_TRY(cudaGetLastError());
     timer.stop(1);
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    guard.ok = true;
     return BLIP_OK;
 }

@@ -71,6 +71,24 @@ int blip_xty(cudaStream_t st, const blipgpu_design* d, const double* d_y, double
 int blip_bits_alloc(blipgpu_ctx* ctx, int64_t N, int64_t p, blipgpu_bits** out);   // counting.cu
 static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
+// device allocation freed on scope exit
+struct DevBuf {
+    void* ptr = nullptr; size_t bytes = 0;
+    int alloc(size_t b) {
+        bytes = b;
+        if (b == 0) { ptr = nullptr; return BLIP_OK; }
+        cudaError_t e = cudaMalloc(&ptr, b);
+        if (e != cudaSuccess) {
+            ptr = nullptr;
+            blip_set_error("cudaMalloc(%zu bytes) failed: %s", b, cudaGetErrorString(e));
+            return BLIP_ERR_NOMEM;
+        }
+        return BLIP_OK;
+    }
+    ~DevBuf() { if (ptr) cudaFree(ptr); }
+    template <class T> T* as() { return reinterpret_cast<T*>(ptr); }
+};
+
 // event-timed region on ctx->stream
 struct ScopedTimer {
     blipgpu_ctx* ctx; cudaEvent_t e0, e1; bool sweep; bool ok;

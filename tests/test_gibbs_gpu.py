@@ -184,7 +184,10 @@ def test_longrun_pips_within_4_mc_standard_errors_linear(gpu):
         p0 = lm.p0s.reshape(chains, N).mean(1, keepdims=True)
         assert _mc_gate(p0, d["lin_p0"][:, None], 1e-3).all(), mode
         # the true signals are found (reference test_mcmc.py:87-134 style check)
-        assert pips.mean(0)[d["lin_beta"] != 0].min() > 0.5 or True
+        # the signals the reference finds (its own mean PIP above 0.9) are found here too
+        # (reference test_mcmc.py:87-134 style check)
+        strong = (d["lin_beta"] != 0) & (d["lin_pips"].mean(0) > 0.9)
+        assert strong.any() and pips.mean(0)[strong].min() > 0.9, mode
 
 
 def test_longrun_pips_within_4_mc_standard_errors_probit(gpu):
@@ -278,3 +281,23 @@ def test_api_surface_matches_reference(gpu):
     pm = ProbitSpikeSlab(X, (y < 0).astype(float))
     pm.sample(N=10, burn=2, chains=2)
     assert pm.betas.shape == (20, 12) and pm.Z.shape == (20, 30)
+
+
+def test_truncnorm_values_equal_the_references_own_draws(gpu):
+    """a4, value level: the device arithmetic of sample_truncnorm (_truncnorm.pyx:42-107) fed with the
+    rand()/RAND_MAX and np.random.randn() sequences the REFERENCE consumed reproduces the reference's
+    20 000 recorded values (tests/golden/truncnorm_values.npz, oracle/pin_truncnorm.py): the same
+    accept/reject decisions (identical variate consumption per call) and values within 4 ulp
+    (CUDA's log/exp/sqrt are not glibc's; the C oracle is bit-identical, tests/test_oracle.py)."""
+    import os
+    from pyblip_b200 import _lib
+    d = np.load(os.path.join(util.GOLDEN, "truncnorm_values.npz"))
+    out, uu, zu = _lib.debug_truncnorm(d["mean"], d["var"], d["b"], d["lower"], d["u"], d["u_at"], d["z"], d["z_at"])
+    nu = np.diff(np.append(d["u_at"], d["u"].shape[0]))
+    nz = np.diff(np.append(d["z_at"], d["z"].shape[0]))
+    assert np.array_equal(uu, nu) and np.array_equal(zu, nz), "accept/reject decisions differ"
+    ref = d["ref"]
+    # error scale: a value mean + scale*z is a difference of terms of that size
+    scale = np.maximum(np.abs(ref), np.abs(d["mean"]))
+    assert np.max(np.abs(out - ref) / scale) <= 4 * np.finfo(float).eps
+    assert np.mean(out == ref) > 0.5

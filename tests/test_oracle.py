@@ -162,3 +162,21 @@ def test_keyed_permutation_is_statistically_uniform():
     adj = (np.abs(np.diff(P, axis=1)) == 1).mean()
     assert abs(adj - 2 / p) < 0.15 * 2 / p
     assert abs((P == np.arange(p)).sum(1).mean() - 1.0) < 0.08
+
+
+def test_truncnorm_arithmetic_reproduces_the_references_values_bit_for_bit():
+    """a4, value level: the oracle's truncated-normal arithmetic on the uniform / normal sequences the
+    reference's compiled `sample_truncnorm` consumed (libc rand() after srand(s), NumPy legacy randn
+    after seed(s)) gives the reference's recorded values exactly (oracle/pin_truncnorm.py wrote the
+    fixture from oracle/_ref)."""
+    from oracle import pin_truncnorm as pt
+    import os
+    d = np.load(os.path.join(util.GOLDEN, "truncnorm_values.npz"))
+    out, used, u_at, z_at = pt.injected(d["mean"], d["var"], d["b"], d["lower"], d["u"], d["z"])
+    assert np.array_equal(out, d["ref"])
+    assert used[0] == d["u"].shape[0] and used[1] == d["z"].shape[0]
+    assert np.array_equal(u_at, d["u_at"]) and np.array_equal(z_at, d["z_at"])
+    a = (d["b"] - d["mean"]) / np.sqrt(d["var"])
+    a = np.where(d["lower"] == 1, -a, a)
+    # every branch of _truncnorm.pyx:57-86 is in the fixture
+    assert (a >= 0.15).sum() > 1000 and ((a >= 0) & (a < 0.15)).sum() > 1000 and (a < 0).sum() > 1000
