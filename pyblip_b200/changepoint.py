@@ -61,18 +61,11 @@ def changepoint_cand_groups(model, **kwargs):
 
 def detect_changepoints(Y, q=0.1, lm_kwargs={}, sample_kwargs={}, blip_kwargs={}):
     """
-    Changepoint detection with BLiP using the LinearSpikeSlab sampler
-    (changepoint.py:13-46).  The sampler and the PIP counting run on the GPU; the
-    final BLiP linear program is the reference's host code and needs the
-    reference package (``pyblip.blip``, which imports cvxpy) to be importable.
+    Changepoint detection with BLiP using the LinearSpikeSlab sampler (changepoint.py:13-46):
+    sampler and PIP counting on the GPU, then the BLiP programs (HiGHS, ``pyblip_b200.blip``).
     """
+    from . import blip
     lm = ChangepointSpikeSlab(Y, **lm_kwargs)
     lm.sample(**sample_kwargs)
     cand_groups = changepoint_cand_groups(lm)
-    try:
-        from pyblip import blip
-    except Exception as err:  # pragma: no cover - depends on the host environment
-        raise ImportError(
-            "detect_changepoints needs the reference's BLiP solver (pyblip.blip, cvxpy); "
-            "the candidate groups are available from changepoint_cand_groups(model)") from err
     return blip.BLiP(cand_groups=cand_groups, q=q, **blip_kwargs)

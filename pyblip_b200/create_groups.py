@@ -435,6 +435,45 @@ def _prefilter(cand_groups, max_pep):
     return [x for x in cand_groups if x.pep < max_pep]
 
 
+def _elim_redundant_features(cand_groups):
+    """Re-indexes the locations that occur in at least one group as 0..nrel-1 and stores every
+    group's re-indexed members in ``data['blip-group']`` (create_groups.py:580-613); the BLiP
+    programs then have one row per location in use.  Returns (cand_groups, nrel)."""
+    new_index = {}
+    for cg in cand_groups:
+        for j in cg.group:
+            new_index.setdefault(j, len(new_index))
+    for cg in cand_groups:
+        cg.data['blip-group'] = set(new_index[j] for j in cg.group)
+    return cand_groups, len(new_index)
+
+
+def _ecc_reduction(cand_groups, verbose=False):
+    """Replaces the locations by the cliques of an edge clique cover of the groups' intersection
+    graph (create_groups.py:616-672): two groups share a clique iff they overlap, so the
+    disjointness constraints are the same with (usually far) fewer rows.  Returns
+    (cand_groups, number of cliques)."""
+    from .create_groups_cts import _edge_clique_cover
+    for cg in cand_groups:
+        cg.data.setdefault('blip-group', cg.group)
+    m = len(cand_groups)
+    member = {}
+    for i, cg in enumerate(cand_groups):
+        for loc in cg.data['blip-group']:
+            member.setdefault(loc, []).append(i)
+    nbrs = [{i} for i in range(m)]
+    for groups_here in member.values():
+        for i in groups_here:
+            nbrs[i].update(groups_here)
+    cliques = _edge_clique_cover([sorted(x) for x in nbrs])
+    for cg in cand_groups:
+        cg.data['blip-group'] = set()
+    for k, clique in enumerate(cliques):
+        for i in clique:
+            cand_groups[i].data['blip-group'].add(k)
+    return cand_groups, len(cliques)
+
+
 def selection_fwer(samples, groups):
     """Exact family-wise error rate of a selection: the fraction of posterior samples in which
     at least one selected group contains no signal -- the quantity the reference's FWER binary

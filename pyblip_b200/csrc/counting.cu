@@ -12,6 +12,7 @@
 // walks rows with lane = row, so every load is a coalesced 128-byte line; per
 // column totals come from a 32x32 in-warp bit transpose followed by popc.
 #include <algorithm>
+#include <cstdlib>
 #include <new>
 #include <vector>
 #include "internal.cuh"
@@ -293,6 +294,108 @@ __global__ void __launch_bounds__(CT_BLOCK) count_sequential_kernel(
                 if (j + m < p && t) atomicAdd(zero_counts + (int64_t)m * p + j, (unsigned long long)t);
             }
         }
+    }
+}
+
+// ---- sequential zero counts, gap-histogram formulation ---------------------------
+// Per row, a set bit at column c with g zero columns immediately before it is the FIRST non-zero
+// column of exactly the windows starting at j = c - k, k = 0 .. g.  With
+//     H[c][g] = #rows with bit c set and a preceding zero run of length g   (g capped at max_size - 1)
+//     S[c][k] = sum_{g >= k} H[c][g]   = #rows whose first non-zero column at or after c - k is c
+// the number of rows in which columns j .. j+m are all zero is
+//     zero_counts[m][j] = N - sum_{k = 0 .. m} S[j + k][k].
+// The scan does work only where a word is non-zero -- one warp-aggregated shared-memory increment
+// per set bit -- instead of evaluating every (column, width) pair of every 32 x 32 tile, and any
+// max_size is allowed (create_groups.py:321-332 accepts any).
+template <bool SMEM_HIST>
+__global__ void __launch_bounds__(CT_BLOCK) gap_hist_kernel(
+    const uint32_t* __restrict__ bits, int64_t N, int64_t N_pad, int max_size, int64_t rows_per_block,
+    unsigned long long* __restrict__ H /* [32 * words][max_size] */)
+{
+    extern __shared__ int s_h[];                        // [32][max_size]
+    const int w = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t r_begin = (int64_t)blockIdx.y * rows_per_block;
+    const int64_t r_end = min(N, r_begin + rows_per_block);
+    const uint32_t* c0 = bits + (int64_t)w * N_pad;
+    const int nh = 32 * max_size;
+    if (SMEM_HIST) {
+        for (int i = threadIdx.x; i < nh; i += CT_BLOCK) s_h[i] = 0;
+        __syncthreads();
+    }
+    unsigned long long* Hw = H + (int64_t)w * nh;
+    constexpr int PF = 8;                               // row tiles a warp keeps in flight
+    const int64_t step = 32 * CT_NWARP;
+    uint32_t xn[PF];
+#pragma unroll
+    for (int i = 0; i < PF; ++i) { const int64_t r = r_begin + 32 * warp + i * step + lane; xn[i] = r < r_end ? c0[r] : 0u; }
+    for (int64_t rb = r_begin + 32 * warp; rb < r_end; rb += PF * step) {
+        uint32_t xc[PF];
+#pragma unroll
+        for (int i = 0; i < PF; ++i) xc[i] = xn[i];
+#pragma unroll
+        for (int i = 0; i < PF; ++i) { const int64_t r = rb + (PF + i) * step + lane; xn[i] = r < r_end ? c0[r] : 0u; }
+#pragma unroll
+        for (int i = 0; i < PF; ++i) {
+            uint32_t x = xc[i];
+            if (!__any_sync(0xffffffffu, x != 0u)) continue;            // the common tile: nothing set
+            const int64_t r = rb + i * step + lane;
+            // zero run that ends right before column 32 w of this row (only what the cap can see)
+            int tz = 0;
+            bool done = x == 0u;
+            for (int k = 1; k <= w && 32 * (k - 1) < max_size - 1; ++k) {   // warp-uniform bounds
+                if (__all_sync(0xffffffffu, done)) break;
+                if (!done) {
+                    const uint32_t xp = bits[(int64_t)(w - k) * N_pad + r];
+                    if (xp) { tz += __clz(xp); done = true; } else tz += 32;
+                }
+            }
+            int prev = -1 - tz;                         // the previous set bit, relative to column 32 w
+            while (__any_sync(0xffffffffu, x != 0u)) {
+                int key = -1;
+                if (x) {
+                    const int b = __ffs(x) - 1;
+                    x &= x - 1;
+                    key = b * max_size + min(b - prev - 1, max_size - 1);
+                    prev = b;
+                }
+                const unsigned peers = __match_any_sync(0xffffffffu, key);
+                if (key >= 0 && lane == __ffs(peers) - 1) {
+                    if (SMEM_HIST) atomicAdd(&s_h[key], __popc(peers));
+                    else atomicAdd(Hw + key, (unsigned long long)__popc(peers));
+                }
+            }
+        }
+    }
+    if (SMEM_HIST) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < nh; i += CT_BLOCK) {
+            const int v = s_h[i];
+            if (v) atomicAdd(Hw + i, (unsigned long long)v);
+        }
+    }
+}
+
+// H[c][g] -> S[c][k] = sum_{g >= k} H[c][g], in place; one thread per column
+__global__ void gap_suffix_kernel(unsigned long long* __restrict__ H, int64_t ncols, int max_size)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncols) return;
+    unsigned long long* h = H + c * max_size;
+    unsigned long long acc = 0;
+    for (int g = max_size - 1; g >= 0; --g) { acc += h[g]; h[g] = acc; }
+}
+
+// zero_counts[m][j] = N - sum_{k <= m} S[j + k][k]   (0 where the window leaves the matrix)
+__global__ void gap_to_zero_counts_kernel(const unsigned long long* __restrict__ S, int64_t N, int64_t p,
+                                          int max_size, unsigned long long* __restrict__ zero_counts)
+{
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= p) return;
+    unsigned long long covered = 0;
+    for (int m = 0; m < max_size; ++m) {
+        if (j + m >= p) break;                      // the output was zero-filled
+        covered += S[(j + m) * max_size + m];
+        zero_counts[(int64_t)m * p + j] = (unsigned long long)N - covered;
     }
 }
 
@@ -694,17 +797,34 @@ extern "C" int blipgpu_count_columns(blipgpu_bits* b, int64_t* counts, int32_t o
 extern "C" int blipgpu_count_sequential(blipgpu_bits* b, int32_t max_size, int64_t* zero_counts, int32_t out_is_device)
 {
     if (!b || !zero_counts || max_size <= 0) { blip_set_error("count_sequential: bad arguments"); return BLIP_ERR_ARG; }
-    if (max_size > 64) { blip_set_error("count_sequential: max_size %d > 64 is not supported", max_size); return BLIP_ERR_UNSUPPORTED; }
     BLIP_TRY(blip_ctx_activate(b->ctx));
+    // windows wider than the matrix do not exist: their rows of the output stay zero
+    const int eff = (int)std::min<int64_t>(max_size, b->p);
     const int64_t rpb = pick_rows_per_block(b->N, b->words, b->ctx->sm_count);
     const unsigned chunks = (unsigned)std::max<int64_t>(1, (b->N + rpb - 1) / rpb);
+    const bool legacy = getenv("BLIPGPU_COUNT_SEQ_TILES") != nullptr && max_size <= 64;   // the round-1 tile kernel, for A/B timing
+    DevBuf hist;
+    if (!legacy && b->N > 0) BLIP_TRY(hist.alloc(sizeof(unsigned long long) * 32 * (size_t)b->words * (size_t)eff));
     return with_output(b->ctx, (int64_t)max_size * b->p, zero_counts, out_is_device, [&](unsigned long long* dev) {
         if (b->N == 0) return;
         dim3 grid((unsigned)b->words, chunks);
-        if (max_size <= 32)
-            count_sequential_kernel<32><<<grid, CT_BLOCK, 0, b->ctx->stream>>>(b->bits, b->N, b->N_pad, b->p, (int)b->words, max_size, rpb, dev);
-        else
-            count_sequential_kernel<64><<<grid, CT_BLOCK, 0, b->ctx->stream>>>(b->bits, b->N, b->N_pad, b->p, (int)b->words, max_size, rpb, dev);
+        cudaStream_t st = b->ctx->stream;
+        if (legacy) {
+            if (max_size <= 32)
+                count_sequential_kernel<32><<<grid, CT_BLOCK, 0, st>>>(b->bits, b->N, b->N_pad, b->p, (int)b->words, max_size, rpb, dev);
+            else
+                count_sequential_kernel<64><<<grid, CT_BLOCK, 0, st>>>(b->bits, b->N, b->N_pad, b->p, (int)b->words, max_size, rpb, dev);
+            return;
+        }
+        unsigned long long* H = hist.as<unsigned long long>();
+        cudaMemsetAsync(H, 0, hist.bytes, st);
+        const size_t smem = sizeof(int) * 32 * (size_t)eff;
+        if (smem <= 40 * 1024) gap_hist_kernel<true><<<grid, CT_BLOCK, smem, st>>>(b->bits, b->N, b->N_pad, eff, rpb, H);
+        else gap_hist_kernel<false><<<grid, CT_BLOCK, 0, st>>>(b->bits, b->N, b->N_pad, eff, rpb, H);
+        const int64_t ncols = 32 * b->words;
+        gap_suffix_kernel<<<(unsigned)((ncols + 127) / 128), 128, 0, st>>>(H, ncols, eff);
+        gap_to_zero_counts_kernel<<<(unsigned)((b->p + 127) / 128), 128, 0, st>>>(H, b->N, b->p, eff, dev);
+        b->ctx->kernel_launches += 2;
     });
 }
 

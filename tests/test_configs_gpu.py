@@ -73,9 +73,10 @@ def _compare(name, refs, out, beta_tol=RTOL, beta_abs_scale=None):
         if beta_abs_scale is None:
             err = util.rel_err(out["betas"][c], ref["betas"])
         else:   # error against a per-sweep scale (see the caller)
-            den = np.maximum(np.abs(ref["betas"]), beta_abs_scale[c][:, None])
+            den = np.maximum(np.maximum(np.abs(ref["betas"]), beta_abs_scale[c][:, None]), 1e-300)
             err = float(np.max(np.abs(out["betas"][c] - ref["betas"]) / den))
         worst["betas"] = max(worst.get("betas", 0.0), err)
+        worst["betas_own_magnitude"] = max(worst.get("betas_own_magnitude", 0.0), util.rel_err(out["betas"][c], ref["betas"]))
         assert err <= beta_tol, f"{name} chain {c}: betas err {err:.3e} > {beta_tol:.1e}"
         if "y_latent" in out:
             err = util.latent_err(out["y_latent"][c], ref["y_latent"])
