@@ -308,6 +308,17 @@ int blipgpu_gridcounts_free(blipgpu_gridcounts* r);
 int blipgpu_overlap_bits(blipgpu_ctx* ctx, const float* centers, const float* radii, int64_t G,
                          int32_t d, int32_t circle, uint32_t* out_bits);
 
+/* ---- hardware probes (measurement only) ----------------------------------- */
+/* bench.py prints these next to its results so that a roofline fraction has a denominator measured in
+ * the same process under the same clocks.
+ * read_bandwidth: GB/s of 16-byte streaming loads over `bytes` for `passes` passes (after one warm-up
+ *   pass): a buffer well below the 126 MB L2 measures L2 -> SM bandwidth, one far above it HBM reads.
+ * fp64: TFLOP/s of kind 0 = DFMA (fp64 pipe), 1 = DMMA mma.sync.m8n8k4.f64 (the Gram build's instruction).
+ * latency: cycles per dependent load of a pointer chase over `bytes` (L2-resident when small). */
+int blipgpu_probe_read_bandwidth(blipgpu_ctx* ctx, int64_t bytes, int32_t passes, double* gb_per_s);
+int blipgpu_probe_fp64(blipgpu_ctx* ctx, int32_t kind, double* tflops);
+int blipgpu_probe_latency(blipgpu_ctx* ctx, int64_t bytes, double* cycles_per_load);
+
 /* ---- parity hooks ---------------------------------------------------------- */
 /* The device arithmetic of `sample_truncnorm` (pyblip/cython_utils/_truncnorm.pyx:42-107) on
  * RECORDED variate sequences instead of the keyed Philox stream: call i consumes uniforms

@@ -18,6 +18,7 @@ MODE_AUTO, MODE_RESIDUAL, MODE_GRAM = 0, 1, 2
 DESIGN_DENSE, DESIGN_CHANGEPOINT = 0, 1
 DTYPE_F64, DTYPE_U8 = 0, 1
 ERR_NUMERIC, ERR_NOMEM, ERR_ARG, ERR_UNSUPPORTED = 4, 3, 2, 5
+COUNT_PAIRS_MAX_P = 16384     # blipgpu_count_pairs: columns per call
 
 # every symbol include/blipgpu.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
@@ -38,6 +39,7 @@ SYMBOLS = [
     "blipgpu_grid_count", "blipgpu_gridcounts_sizes", "blipgpu_gridcounts_get", "blipgpu_gridcounts_free",
     "blipgpu_overlap_bits",
     "blipgpu_debug_truncnorm",
+    "blipgpu_probe_read_bandwidth", "blipgpu_probe_fp64", "blipgpu_probe_latency",
 ]
 
 
@@ -179,6 +181,24 @@ class Context:
         check(load().blipgpu_ctx_event_elapsed_ms(self._h, C.c_int(slot_begin), C.c_int(slot_end),
                                                   C.byref(ms)))
         return ms.value
+
+    def probe_read_bandwidth(self, nbytes, passes):
+        """GB/s of streaming loads over an `nbytes` buffer (L2-resident if small, HBM if large)."""
+        v = C.c_double()
+        check(load().blipgpu_probe_read_bandwidth(self._h, C.c_int64(int(nbytes)), C.c_int32(int(passes)), C.byref(v)))
+        return v.value
+
+    def probe_fp64(self, kind):
+        """TFLOP/s of DFMA (kind 0) or DMMA m8n8k4 (kind 1)."""
+        v = C.c_double()
+        check(load().blipgpu_probe_fp64(self._h, C.c_int32(int(kind)), C.byref(v)))
+        return v.value
+
+    def probe_latency(self, nbytes):
+        """Cycles per dependent load over an `nbytes` pointer chase."""
+        v = C.c_double()
+        check(load().blipgpu_probe_latency(self._h, C.c_int64(int(nbytes)), C.byref(v)))
+        return v.value
 
     def timing(self, reset=False):
         sm, ol = C.c_double(), C.c_double()
@@ -519,7 +539,7 @@ class Bits:
                                               C.c_void_p(out.ctypes.data), C.c_int32(0)))
         return out
 
-    def count_false_rows(self, groups):
+    def count_false_rows(self, groups, device_ptr=None):
         """#rows in which at least one of `groups` has no non-zero column (exact FWER numerator)."""
         G = len(groups)
         offsets = np.zeros(G + 1, dtype=np.int64)
@@ -528,14 +548,23 @@ class Bits:
         members = np.fromiter((int(j) for g in groups for j in g), dtype=np.int64, count=int(offsets[-1]))
         if members.size == 0:
             members = np.zeros(1, dtype=np.int64)
+        if device_ptr is not None:
+            check(load().blipgpu_count_false_rows(self._h, C.c_void_p(offsets.ctypes.data),
+                                                  C.c_void_p(members.ctypes.data), C.c_int64(G),
+                                                  C.c_void_p(device_ptr), C.c_int32(1)))
+            return None
         out = np.zeros(1, dtype=np.int64)
         check(load().blipgpu_count_false_rows(self._h, C.c_void_p(offsets.ctypes.data),
                                               C.c_void_p(members.ctypes.data), C.c_int64(G),
                                               C.c_void_p(out.ctypes.data), C.c_int32(0)))
         return int(out[0])
 
-    def count_pairs(self):
+    def count_pairs(self, device_ptr=None):
         """#rows in which both columns are non-zero, for every pair of columns (int64[p, p])."""
+        if device_ptr is not None:
+            if self.p:
+                check(load().blipgpu_count_pairs(self._h, C.c_void_p(device_ptr), C.c_int32(1)))
+            return None
         out = np.zeros((self.p, self.p), dtype=np.int64)
         if self.p:
             check(load().blipgpu_count_pairs(self._h, C.c_void_p(out.ctypes.data), C.c_int32(0)))

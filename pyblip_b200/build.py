@@ -18,7 +18,7 @@ OUT_DIR = os.path.join(HERE, "_C")
 LIB = os.path.join(OUT_DIR, "libblipgpu.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
-SOURCES = ["api.cu", "gram.cu", "gibbs.cu", "samples.cu", "counting.cu", "nprior.cu", "gridcount.cu"]
+SOURCES = ["api.cu", "gram.cu", "gibbs.cu", "samples.cu", "counting.cu", "nprior.cu", "gridcount.cu", "probe.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17",
     "-gencode", "arch=compute_100a,code=sm_100a",

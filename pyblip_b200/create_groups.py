@@ -62,36 +62,101 @@ class CandidateGroup():
 # ---------------------------------------------------------------------------
 # device plumbing
 # ---------------------------------------------------------------------------
-class _DeviceSamples:
-    """Bit-packed indicators on the device plus the global row count."""
+class _SampleSet:
+    """Counting interface over the sample rows of this rank, merged over ranks on request.
+    ``N`` is the GLOBAL row count (None until the first merge under torchrun: it rides in slot 0
+    of that stage's all-reduce).  Subclasses provide ``local(kind, *args)`` and ``p``, ``N_local``."""
 
-    def __init__(self, bits, owned):
-        self.bits = bits
-        self.owned = owned
-        self.N_local = bits.N
-        self.N = dist.allreduce_scalar(bits.N) if dist.world()[1] > 1 else bits.N
-        self.p = bits.p
+    def size_of(self, kind, *args):
+        if kind == "columns":
+            return (self.p,)
+        if kind == "sequential":
+            return (int(args[0]), self.p)
+        if kind == "groups":
+            return (len(args[0]),)
+        if kind == "false_rows":
+            return (1,)
+        if kind == "pairs":
+            return (self.p, self.p)
+        raise ValueError(kind)
 
-    def select(self, cols):
-        return _DeviceSamples(self.bits.select_columns(cols), True)
+    # ---- one request, merged over ranks (one all-reduce each; stages use dist.CountBatch) ----
+    def _one(self, kind, *args):
+        batch = dist.CountBatch()
+        batch.add(self, kind, *args)
+        return batch.run()[0]
+
+    def rows(self):
+        """Global number of sample rows."""
+        if self.N is None:
+            batch = dist.CountBatch()
+            batch.want_rows(self)
+            batch.run()
+        return self.N
 
     def column_counts(self):
-        return dist.allreduce_counts(self.bits.count_columns())
+        return self._one("columns")
 
     def sequential_counts(self, max_size):
-        return dist.allreduce_counts(self.bits.count_sequential(max_size))
+        return self._one("sequential", max_size)
 
     def group_counts(self, groups):
         if len(groups) == 0:
             return np.zeros(0, dtype=np.int64)
-        return dist.allreduce_counts(self.bits.count_groups(groups))
+        return self._one("groups", groups)
 
     def false_rows(self, groups):
-        return int(dist.allreduce_scalar(self.bits.count_false_rows(groups)) if dist.world()[1] > 1
-                   else self.bits.count_false_rows(groups))
+        return int(self._one("false_rows", groups)[0])
 
     def pair_counts(self):
-        return dist.allreduce_counts(self.bits.count_pairs())
+        return self._one("pairs")
+
+
+class _DeviceSamples(_SampleSet):
+    """Bit-packed indicators of this rank's chains on the device."""
+
+    def __init__(self, bits, owned, N=None):
+        self.bits = bits
+        self.owned = owned
+        self.N_local = bits.N
+        self.N = N if N is not None else (bits.N if dist.world()[1] == 1 else None)
+        self.N_per_rank = np.array([bits.N], dtype=np.int64) if dist.world()[1] == 1 else None
+        self.p = bits.p
+        self.device_index = bits.ctx.device
+
+    def select(self, cols):
+        sub = _DeviceSamples(self.bits.select_columns(cols), True, N=self.rows())
+        sub.N_per_rank = self.N_per_rank
+        return sub
+
+    def local(self, kind, *args):
+        """This rank's counts, on the host."""
+        if kind == "columns":
+            return self.bits.count_columns()
+        if kind == "sequential":
+            return self.bits.count_sequential(int(args[0]))
+        if kind == "groups":
+            return self.bits.count_groups(args[0])
+        if kind == "false_rows":
+            return np.array([self.bits.count_false_rows(args[0])], dtype=np.int64)
+        if kind == "pairs":
+            return self.bits.count_pairs()
+        raise ValueError(kind)
+
+    def local_into(self, kind, device_ptr, *args):
+        """The same counts written by the kernels into device memory (``out_is_device``)."""
+        if kind == "columns":
+            self.bits.count_columns(device_ptr=device_ptr)
+        elif kind == "sequential":
+            self.bits.count_sequential(int(args[0]), device_ptr=device_ptr)
+        elif kind == "groups":
+            self.bits.count_groups(args[0], device_ptr=device_ptr)
+        elif kind == "false_rows":
+            self.bits.count_false_rows(args[0], device_ptr=device_ptr)
+        elif kind == "pairs":
+            self.bits.count_pairs(device_ptr=device_ptr)
+        else:
+            raise ValueError(kind)
 
     def to_dense(self):
         return self.bits.to_dense()
@@ -164,41 +229,8 @@ def _sequential_peps_susie(susie_alphas, max_size):
     return peps
 
 
-def sequential_groups(
-    samples=None,
-    susie_alphas=None,
-    q=0,
-    max_pep=0.25,
-    max_size=25,
-    prenarrow=False,
-    min_purity=0.0,
-    X=None,
-    corr_matrix=None,
-):
-    """
-    Calculates all sequential candidate groups below max_size.
-
-    Same parameters and return value as the reference
-    (create_groups.py:272-320): a list of ``CandidateGroup`` objects for every
-    contiguous window ``{j, ..., j+m}``, ``m < max_size``, with ``pep < max_pep``.
-    """
-    if samples is not None:
-        dev = _as_device(samples)
-        try:
-            p = dev.p
-            max_size = min(max_size, p)
-            zero_counts = dev.sequential_counts(max_size)
-            all_PEPs = _sequential_peps_from_counts(zero_counts, dev.N, p, max_size)
-        finally:
-            if dev is not samples:
-                dev.close()
-    elif susie_alphas is not None:
-        p = susie_alphas.shape[1]
-        max_size = min(max_size, p)
-        all_PEPs = _sequential_peps_susie(susie_alphas, max_size)
-    else:
-        raise ValueError("Either samples or susie_alphas must be specified.")
-
+def _sequential_from_peps(all_PEPs, max_size, q, max_pep, prenarrow):
+    """Window PEPs -> candidate groups (create_groups.py:348-378)."""
     # start index of every admissible window of size m+1 (strict <, :350)
     active_inds = {m: np.where(all_PEPs[m] < max_pep)[0] for m in range(max_size)}
 
@@ -218,7 +250,46 @@ def sequential_groups(
         for ind in active_inds[m]:
             cand_groups.append(CandidateGroup(
                 group=set(range(ind, ind + m + 1)), pep=all_PEPs[m][ind]))
+    return cand_groups
 
+
+def sequential_groups(
+    samples=None,
+    susie_alphas=None,
+    q=0,
+    max_pep=0.25,
+    max_size=25,
+    prenarrow=False,
+    min_purity=0.0,
+    X=None,
+    corr_matrix=None,
+):
+    """
+    Calculates all sequential candidate groups below max_size.
+
+    Same parameters and return value as the reference
+    (create_groups.py:272-320): a list of ``CandidateGroup`` objects for every
+    contiguous window ``{j, ..., j+m}``, ``m < max_size``, with ``pep < max_pep``.
+    Under torchrun the window counts (and the row count) of all ranks are merged by
+    one all-reduce.
+    """
+    if samples is not None:
+        dev = _as_device(samples)
+        try:
+            p = dev.p
+            max_size = min(max_size, p)
+            zero_counts = dev.sequential_counts(max_size)       # one stage: [N | max_size x p]
+            all_PEPs = _sequential_peps_from_counts(zero_counts, dev.N, p, max_size)
+        finally:
+            if dev is not samples:
+                dev.close()
+    elif susie_alphas is not None:
+        p = susie_alphas.shape[1]
+        max_size = min(max_size, p)
+        all_PEPs = _sequential_peps_susie(susie_alphas, max_size)
+    else:
+        raise ValueError("Either samples or susie_alphas must be specified.")
+    cand_groups = _sequential_from_peps(all_PEPs, max_size, q, max_pep, prenarrow)
     return filter_by_purity(cand_groups, min_purity=min_purity, X=X, corr_matrix=corr_matrix)
 
 
@@ -295,26 +366,58 @@ def _samples_dist_matrix(samples):
 _DEVICE_CORR_MIN_ENTRIES = 50_000_000
 
 
-def _samples_dist_matrix_device(dev):
+def _corr_from_pair_counts(pair_counts, N):
     """The matrix of `_samples_dist_matrix` from exact integer counts: with the all-zero and the
     all-one row appended (:527-533) there are N' = N + 2 rows, column sums c + 1 and co-occurrence
     counts n11 + 1, and the Pearson correlation of two 0/1 columns is
     (N' n11' - c_a' c_b') / sqrt((N' c_a' - c_a'^2)(N' c_b' - c_b'^2)).
     All products stay below 2^53, so every entry is one correctly rounded expression of exact
     integers (np.corrcoef's own result depends on BLAS summation order in the last bits)."""
-    n11 = dev.pair_counts().astype(np.float64) + 1.0
+    n11 = pair_counts.astype(np.float64) + 1.0
     c = np.diag(n11).copy()                         # = column counts + 1
-    Np = float(dev.N + 2)
+    Np = float(N + 2)
     var = Np * c - c * c
     corr = (Np * n11 - np.outer(c, c)) / np.sqrt(np.outer(var, var))
     np.clip(corr, -1.0, 1.0, out=corr)              # np.corrcoef clips too
     return corr + 1
 
 
+def _samples_dist_matrix_device(dev):
+    pairs = dev.pair_counts()
+    return _corr_from_pair_counts(pairs, dev.N)
+
+
+def _wants_device_corr(dev):
+    return dev.rows() * dev.p >= _DEVICE_CORR_MIN_ENTRIES and dev.p <= _lib.COUNT_PAIRS_MAX_P
+
+
 def _sample_dist_matrix_auto(dev):
-    if dev.N * dev.p >= _DEVICE_CORR_MIN_ENTRIES and dev.p <= 16384:
+    if _wants_device_corr(dev):
         return _samples_dist_matrix_device(dev)
     return _samples_dist_matrix(_gathered_dense(dev))
+
+
+def _tree_candidates(dist_matrix, max_size, filter_sequential, **kwargs):
+    """Tree-node groups that can become candidates (:441-455): at most max_size members and, if
+    asked, not contiguous (those are sequential groups already)."""
+    kept = []
+    for group in _dist_matrices_to_groups(dist_matrix, **kwargs):
+        gsize = len(group)
+        if gsize > max_size:
+            continue
+        if filter_sequential and np.max(group) - np.min(group) == gsize - 1:
+            continue
+        kept.append(group)
+    return kept
+
+
+def _groups_from_counts(kept, counts, N, max_pep):
+    cand_groups = []
+    for group, cnt in zip(kept, counts):
+        pep = 1 - cnt / N                             # :459
+        if pep < max_pep:
+            cand_groups.append(CandidateGroup(group=set(group), pep=pep))
+    return cand_groups
 
 
 def hierarchical_groups(
@@ -341,38 +444,38 @@ def hierarchical_groups(
             return [CandidateGroup(group=set([0]), pep=pep)]
         if dist_matrix is None:
             dist_matrix = _sample_dist_matrix_auto(dev)
-        groups = _dist_matrices_to_groups(dist_matrix, **kwargs)
-
-        kept = []
-        for group in groups:
-            gsize = len(group)
-            if gsize > max_size:
-                continue
-            if filter_sequential and np.max(group) - np.min(group) == gsize - 1:
-                continue
-            kept.append(group)
+        kept = _tree_candidates(dist_matrix, max_size, filter_sequential, **kwargs)
         counts = dev.group_counts(kept)
-        cand_groups = []
-        for group, cnt in zip(kept, counts):
-            pep = 1 - cnt / dev.N
-            if pep < max_pep:
-                cand_groups.append(CandidateGroup(group=set(group), pep=pep))
+        cand_groups = _groups_from_counts(kept, counts, dev.rows(), max_pep)
     finally:
         if dev is not samples:
             dev.close()
     return filter_by_purity(cand_groups, min_purity=min_purity, X=X, corr_matrix=corr_matrix)
 
 
+def _pack_rows(dense):
+    """bool (N, p) -> uint32 (N, ceil(p/32)) words, 32 columns per word."""
+    packed = np.packbits(np.asarray(dense, dtype=bool), axis=1, bitorder="little")
+    pad = (-packed.shape[1]) % 4
+    if pad:
+        packed = np.concatenate([packed, np.zeros((packed.shape[0], pad), dtype=np.uint8)], axis=1)
+    return np.ascontiguousarray(packed).view(np.uint32)
+
+
+def _unpack_rows(words, p):
+    return np.unpackbits(np.ascontiguousarray(words).view(np.uint8), axis=1, bitorder="little")[:, :p].astype(bool)
+
+
 def _gathered_dense(dev):
-    """Dense boolean matrix of a (column-compacted) device sample set, rows of all
-    ranks concatenated in rank order.  Only used to feed the host clustering."""
+    """Dense boolean matrix of a (column-compacted) device sample set, rows of all ranks
+    concatenated in rank order.  Only feeds the host clustering (small sets: below
+    _DEVICE_CORR_MIN_ENTRIES entries); the rows travel bit-packed, one all_gather."""
     local = dev.to_dense()
-    d = dist._dist()
-    if d is None or d.get_world_size() == 1:
+    if dist.world()[1] == 1:
         return local
-    parts = [None] * d.get_world_size()
-    d.all_gather_object(parts, local)
-    return np.concatenate(parts, axis=0)
+    dev.rows()
+    words = dist.allgather_rows(_pack_rows(local), dev.N_per_rank, getattr(dev, "device_index", None))
+    return _unpack_rows(words, dev.p)
 
 
 # ---------------------------------------------------------------------------
@@ -393,29 +496,72 @@ def all_cand_groups(
     Creates many candidate groups by prefiltering locations at various thresholds
     and then creating sequential and hierarchical candidate groups
     (create_groups.py:56-149; same parameters, same result).
+
+    The counting is organised in three stages, each merged over ranks by ONE all-reduce of a
+    packed int64 buffer: (1) row count + marginal column counts; (2) for every threshold at
+    once, the window zero-counts of the prefiltered columns and -- for large sets -- their pair
+    counts; (3) for every threshold at once, the any-counts of the tree groups.
     """
     dev = _as_device(samples)
+    subs = []
     try:
-        marg_pips = dev.column_counts() / dev.N           # :105-106
-        all_groups = set()
-        all_cgs = []
+        marg_pips = dev.column_counts() / dev.N           # stage 1 (:105-106)
+        levels = []
         for thresh in prefilter_thresholds:
             rel_features = np.where(marg_pips > thresh)[0]
             if len(rel_features) == 0:
                 continue
             sub = dev if len(rel_features) == dev.p else dev.select(rel_features)
-            try:
-                cgs = sequential_groups(sub, q=q, max_pep=max_pep, max_size=max_size,
-                                        prenarrow=prenarrow)
-                dms = [_sample_dist_matrix_auto(sub)]
-                if X is not None:
-                    dms.append(np.abs(1 - np.corrcoef(X[:, rel_features].T)))
-                cgs.extend(hierarchical_groups(sub, dist_matrix=dms, max_pep=max_pep,
-                                               max_size=max_size, filter_sequential=True))
-            finally:
-                if sub is not dev:
-                    sub.close()
+            if sub is not dev:
+                subs.append(sub)
+            levels.append(dict(rel=rel_features, sub=sub, msize=min(max_size, sub.p)))
+        # stage 2: sequential counts (:117-123) and pair counts of every level
+        batch = dist.CountBatch()
+        for lv in levels:
+            lv["seq"] = batch.add(lv["sub"], "sequential", lv["msize"])
+            lv["pairs"] = batch.add(lv["sub"], "pairs") if _wants_device_corr(lv["sub"]) and lv["sub"].p > 1 else None
+        res = batch.run()
+        # levels whose tree is built from the dense matrix on the host (small sets): the rows of
+        # all ranks are gathered ONCE, for the widest such level, and narrower levels slice it
+        need_dense = [lv for lv in levels if lv["pairs"] is None and lv["sub"].p > 1]
+        dense_cols, dense_all = None, None
+        if need_dense:
+            widest = max(need_dense, key=lambda lv: lv["sub"].p)
+            dense_cols = {int(c): i for i, c in enumerate(widest["rel"])}
+            dense_all = _gathered_dense(widest["sub"])
+        for lv in levels:
+            sub = lv["sub"]
+            peps = _sequential_peps_from_counts(res[lv["seq"]], dev.N, sub.p, lv["msize"])
+            lv["cgs"] = _sequential_from_peps(peps, lv["msize"], q, max_pep, prenarrow)
+            if sub.p == 1:
+                lv["kept"] = None
+                continue
+            if lv["pairs"] is not None:
+                dms = [_corr_from_pair_counts(res[lv["pairs"]], dev.N)]
+            else:
+                cols = [dense_cols[int(c)] for c in lv["rel"]]          # thresholds nest: rel is a subset
+                dms = [_samples_dist_matrix(dense_all[:, cols])]         # :125
+            if X is not None:
+                dms.append(np.abs(1 - np.corrcoef(X[:, lv["rel"]].T)))
+            lv["kept"] = _tree_candidates(dms, max_size, True)
+        # stage 3: any-counts of every level's tree groups (:459)
+        batch = dist.CountBatch()
+        for lv in levels:
+            if lv["kept"] is None:
+                lv["grp"] = batch.add(lv["sub"], "columns")
+            else:
+                lv["grp"] = batch.add(lv["sub"], "groups", lv["kept"]) if len(lv["kept"]) else None
+        res = batch.run()
+        all_groups = set()
+        all_cgs = []
+        for lv in levels:
+            cgs = lv["cgs"]
+            if lv["kept"] is None:                                       # p == 1 (:437-439)
+                cgs.append(CandidateGroup(group=set([0]), pep=1 - res[lv["grp"]][0] / dev.N))
+            elif lv["grp"] is not None:
+                cgs.extend(_groups_from_counts(lv["kept"], res[lv["grp"]], dev.N, max_pep))
             # map the compacted indices back and drop duplicates across thresholds
+            rel_features = lv["rel"]
             fresh = []
             for cg in cgs:
                 group = tuple(sorted(rel_features[list(cg.group)].tolist()))
@@ -425,6 +571,8 @@ def all_cand_groups(
                     fresh.append(group)
             all_groups = all_groups.union(fresh)
     finally:
+        for sub in subs:
+            sub.close()
         if dev is not samples:
             dev.close()
     return filter_by_purity(all_cgs, min_purity=min_purity, X=X, corr_matrix=corr_matrix)

@@ -25,15 +25,19 @@ def normalize_locs(locs):
 
 
 def _merge_over_ranks(codes, counts):
-    d = dist._dist()
-    if d is None or d.get_world_size() == 1:
+    """(code, count) lists of all ranks -> sorted distinct codes with summed counts.  The lists
+    travel as one int64 tensor per rank (codes reinterpreted), one padded all_gather."""
+    if dist.world()[1] == 1:
         return codes, counts
-    parts = [None] * d.get_world_size()
-    d.all_gather_object(parts, (codes, counts))
-    allc = np.concatenate([p[0] for p in parts])
-    alln = np.concatenate([p[1] for p in parts]).astype(np.int64)
+    local = np.stack([np.ascontiguousarray(codes, dtype=np.uint64).view(np.int64),
+                      np.ascontiguousarray(counts).astype(np.int64)])
+    parts = dist.allgather_ragged_int64(local)
+    allc = np.concatenate([p[0] for p in parts]).view(np.uint64)
+    alln = np.concatenate([p[1] for p in parts])
     uniq, inv = np.unique(allc, return_inverse=True)
-    return uniq, np.bincount(inv, weights=alln, minlength=uniq.shape[0]).astype(np.int64)
+    merged = np.zeros(uniq.shape[0], dtype=np.int64)
+    np.add.at(merged, inv, alln)
+    return uniq, merged
 
 
 def grid_peps(
@@ -139,11 +143,10 @@ def grid_peps(
 
     # count_signals: distribution of the per-sample multiplicity of every key (:195-206)
     if world > 1:
-        d_ = dist._dist()
-        parts = [None] * world
-        d_.all_gather_object(parts, (pcodes, pmult))
-        pcodes = np.concatenate([p[0] for p in parts])
-        pmult = np.concatenate([p[1] for p in parts])
+        parts = dist.allgather_ragged_int64(np.stack([np.ascontiguousarray(pcodes, dtype=np.uint64).view(np.int64),
+                                                      np.ascontiguousarray(pmult).astype(np.int64)]))
+        pcodes = np.concatenate([p[0] for p in parts]).view(np.uint64)
+        pmult = np.concatenate([p[1] for p in parts]).astype(pmult.dtype)
     index = {int(c): i for i, c in enumerate(codes)}
     hist = {}
     if pcodes.size:

@@ -37,10 +37,18 @@ def _worker(rank, world, port, q):
     c0, c1 = dist.shard_chains(chains)
     local = samples[c0 * N:c1 * N]
     assert dist.world() == (rank, world)
+    n0 = dict(dist.STATS)
+    seq = util.cg_list(cg.sequential_groups(local, max_pep=0.5))
+    n1 = dict(dist.STATS)
+    allg = util.cg_list(cg.all_cand_groups(local, q=0.1, max_pep=0.5, max_size=12))
+    n2 = dict(dist.STATS)
     out = {
-        "seq": util.cg_list(cg.sequential_groups(local, max_pep=0.5)),
-        "all": util.cg_list(cg.all_cand_groups(local, q=0.1, max_pep=0.5, max_size=12)),
-        "n_local": local.shape[0],
+        "seq": seq, "all": allg, "n_local": local.shape[0],
+        # collectives: sequential_groups is ONE all-reduce; all_cand_groups is three stages
+        # (marginals -> windows of every threshold -> tree groups of every threshold) plus one
+        # all_gather of bit-packed rows for the host clustering of these small sets
+        "seq_collectives": (n1["all_reduce"] - n0["all_reduce"], n1["all_gather"] - n0["all_gather"]),
+        "all_collectives": (n2["all_reduce"] - n1["all_reduce"], n2["all_gather"] - n1["all_gather"]),
     }
     q.put((rank, out))
     td.destroy_process_group()
@@ -70,5 +78,7 @@ def test_two_rank_counting_matches_single_process(monkeypatch):
     assert results[0]["n_local"] + results[1]["n_local"] == samples.shape[0]
     assert results[0]["n_local"] != results[1]["n_local"]       # 3 chains vs 2 chains
     for r in range(world):
+        assert results[r]["seq_collectives"] == (1, 0), results[r]["seq_collectives"]
+        assert results[r]["all_collectives"] == (3, 1), results[r]["all_collectives"]
         assert results[r]["seq"] == want_seq
         assert sorted(results[r]["all"]) == sorted(want_all)
