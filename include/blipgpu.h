@@ -19,6 +19,8 @@
  * Environment (diagnostics; none changes a result)
  *   BLIPGPU_LAUNCH_LOG=1             every sweep-kernel launch with its CUDA-event time on stderr
  *   BLIPGPU_NO_L2_PIN=1              residual-form sweeps: do not pin the design matrix in L2
+ *   BLIPGPU_NO_WS=1                  gram form: never pick the role-specialised few-chains kernels
+ *   BLIPGPU_WS_CLUSTER=1             gram form: AUTO picks the 2-CTA cluster placement when chains <= SMs/2
  *   BLIPGPU_NPRIOR_WORKSPACE_MB=x    budget of the neuronized prior's joint-draw workspace
  *                                    (default: half of the free device memory; chains run in
  *                                    waves when all of them do not fit)
@@ -114,12 +116,18 @@ typedef struct blipgpu_streams {
 #define BLIPGPU_MODE_RESIDUAL 1  /* state r = y - X beta; one X column per update  */
 #define BLIPGPU_MODE_GRAM 2      /* state q = X^T r; one Gram column per change    */
 
+#define BLIPGPU_GRAM_KERNEL_AUTO 0        /* by chains per device: specialised (<= SMs), else classic              */
+#define BLIPGPU_GRAM_KERNEL_CLASSIC 1     /* one 256-thread CTA per chain, two chains per SM, work queue           */
+#define BLIPGPU_GRAM_KERNEL_SPECIALIZED 2 /* one SM per chain: decision warps + helper warps in one CTA            */
+#define BLIPGPU_GRAM_KERNEL_CLUSTER 3     /* two SMs per chain: a 2-CTA cluster, decisions | column stream (DSMEM) */
+
 typedef struct blipgpu_sample_options {
     int32_t mode;            /* BLIPGPU_MODE_*                                     */
     int32_t chunk_sweeps;    /* sweeps per kernel launch (0 = default)             */
     int32_t keep_latents;    /* probit: keep Z on the device                       */
     int32_t gram_refresh;    /* gram mode: rebuild q every this many sweeps (0=def) */
-    int32_t reserved[4];
+    int32_t gram_kernel;     /* BLIPGPU_GRAM_KERNEL_*: both kernels give bit-identical results */
+    int32_t reserved[3];
 } blipgpu_sample_options;
 
 /* Replaces `apply_pool(_sample_spikeslab, constant_inputs, N=[N+burn]*chains)`

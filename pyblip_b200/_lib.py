@@ -15,6 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "_C", "libblipgpu.so")
 
 MODE_AUTO, MODE_RESIDUAL, MODE_GRAM = 0, 1, 2
+GRAM_KERNEL_AUTO, GRAM_KERNEL_CLASSIC, GRAM_KERNEL_SPECIALIZED, GRAM_KERNEL_CLUSTER = 0, 1, 2, 3
 DESIGN_DENSE, DESIGN_CHANGEPOINT = 0, 1
 DTYPE_F64, DTYPE_U8 = 0, 1
 ERR_NUMERIC, ERR_NOMEM, ERR_ARG, ERR_UNSUPPORTED = 4, 3, 2, 5
@@ -76,7 +77,7 @@ class MultiStreams(C.Structure):
 class SampleOptions(C.Structure):
     _fields_ = [
         ("mode", C.c_int32), ("chunk_sweeps", C.c_int32), ("keep_latents", C.c_int32),
-        ("gram_refresh", C.c_int32), ("reserved", C.c_int32 * 4),
+        ("gram_refresh", C.c_int32), ("gram_kernel", C.c_int32), ("reserved", C.c_int32 * 3),
     ]
 
 
@@ -341,7 +342,8 @@ class Samples:
 
 def sample_spikeslab(design, cfg, y=None, z=None, probit=False, chains=1, chain_offset=0,
                      n_keep=1, burn=0, seed=0, streams=None, mode=MODE_AUTO, chunk_sweeps=0,
-                     keep_latents=True, gram_refresh=0, bsize=1, max_signals_per_block=0):
+                     keep_latents=True, gram_refresh=0, bsize=1, max_signals_per_block=0,
+                     gram_kernel=GRAM_KERNEL_AUTO):
     """All chains of this rank in one call (``blipgpu_sample_spikeslab``, or
     ``blipgpu_sample_spikeslab_multi`` when ``bsize > 1``)."""
     if bsize > 1:
@@ -382,7 +384,7 @@ def sample_spikeslab(design, cfg, y=None, z=None, probit=False, chains=1, chain_
         ptr = lambda a: None if a is None else a.ctypes.data  # noqa: E731
         st = Streams(ptr(perm), ptr(u), ptr(zn), ptr(ig), ptr(p0d), ptr(gd), nprop)
         st_ptr = C.byref(st)
-    opts = SampleOptions(int(mode), int(chunk_sweeps), int(bool(keep_latents)), int(gram_refresh))
+    opts = SampleOptions(int(mode), int(chunk_sweeps), int(bool(keep_latents)), int(gram_refresh), int(gram_kernel))
     h = C.c_void_p()
     check(load().blipgpu_sample_spikeslab(
         design.ctx._h, design._h, C.byref(cfg), C.c_void_p(yptr), C.c_void_p(zptr),

@@ -291,19 +291,31 @@ __device__ __forceinline__ int warp_sum_int(int v)
     return v;
 }
 
-// Sum over the whole block; result returned to every thread.  `scratch` must
-// hold >= 33 doubles of shared memory.  Contains two __syncthreads().
+// Barrier policies: the whole CTA, or a named barrier over a warp-specialised sub-group of NT
+// threads (warps [0, NT/32) by convention of the callers, which index scratch by threadIdx.x >> 5).
+struct SyncCta {
+    static __device__ __forceinline__ void sync() { __syncthreads(); }
+    static __device__ __forceinline__ int nwarp() { return (blockDim.x + 31) >> 5; }
+};
+template <int ID, int NT> struct SyncNamed {
+    static __device__ __forceinline__ void sync() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(NT) : "memory"); }
+    static __device__ __forceinline__ int nwarp() { return NT / 32; }
+};
+
+// Sum over the group SY synchronises (default: the whole block); result returned to every thread.
+// `scratch` must hold >= 33 doubles of shared memory.  Contains two barriers.
+template <class SY = SyncCta>
 __device__ __forceinline__ double block_sum(double v, double* scratch)
 {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = SY::nwarp();
     v = warp_sum(v);
     if (lane == 0) scratch[warp] = v;
-    __syncthreads();
+    SY::sync();
     if (warp == 0) {
         double t = (lane < nwarp) ? scratch[lane] : 0.0;
         t = warp_sum(t);
         if (lane == 0) scratch[32] = t;
     }
-    __syncthreads();
+    SY::sync();
     return scratch[32];
 }

@@ -12,6 +12,7 @@
 #include <vector>
 #include "gibbs_kernels.cuh"
 #include "gibbs_block.cuh"
+#include "gibbs_gram_ws.cuh"
 
 namespace {
 
@@ -243,6 +244,31 @@ static int sample_impl(blipgpu_ctx* ctx, blipgpu_design* design,
         return BLIP_ERR_UNSUPPORTED;
     }
 
+    // ---- few chains: role-specialised kernel, one SM per chain or a 2-CTA cluster per chain (gibbs_gram_ws.cuh)
+    const int want_kernel = opts ? opts->gram_kernel : BLIPGPU_GRAM_KERNEL_AUTO;
+    const size_t smem_ws = 2 * sizeof(double) * p2 + sizeof(uint32_t) * words;      // q twice + active-set mask
+    const bool ws_fits = gram && !block && smem_ws + 8192 <= ctx->smem_optin;
+    const bool ws_possible = ws_fits && chains <= ctx->sm_count;
+    const bool cl_possible = ws_fits && 2 * chains <= ctx->sm_count;
+    if ((want_kernel == BLIPGPU_GRAM_KERNEL_SPECIALIZED && !ws_possible) || (want_kernel == BLIPGPU_GRAM_KERNEL_CLUSTER && !cl_possible)) {
+        blip_set_error("sample_spikeslab: the role-specialised gram kernels need gram mode, bsize = 1, 16 p bytes of shared "
+                       "memory and at most %d chains per device (%d for the cluster placement)", ctx->sm_count, ctx->sm_count / 2);
+        return BLIP_ERR_UNSUPPORTED;
+    }
+    // AUTO never picks the cluster placement: measured SLOWER than one SM per chain (6.8 vs 5.7 ms per
+    // 32 sweeps of 64 chains at C2; classic 6.4): a distributed-shared-memory read of q is served by the
+    // helper SM's load/store pipeline, behind the helpers' own column stream.
+    // BLIPGPU_WS_CLUSTER=1 or gram_kernel = CLUSTER selects it.
+    const bool no_ws = getenv("BLIPGPU_NO_WS") != nullptr, env_cl = getenv("BLIPGPU_WS_CLUSTER") != nullptr;
+    bool use_cl = false, use_ws = false;
+    if (want_kernel == BLIPGPU_GRAM_KERNEL_CLUSTER) use_cl = true;
+    else if (want_kernel == BLIPGPU_GRAM_KERNEL_SPECIALIZED) use_ws = true;
+    else if (want_kernel == BLIPGPU_GRAM_KERNEL_AUTO && !no_ws) {
+        if (cl_possible && env_cl) use_cl = true;
+        else if (ws_possible) use_ws = true;
+    }
+    const bool use_role = use_cl || use_ws;          // double-buffered scratch, no work queue
+
     // ---- chunking
     int S = opts && opts->chunk_sweeps > 0 ? opts->chunk_sweeps : 32;
     {
@@ -286,7 +312,7 @@ static int sample_impl(blipgpu_ctx* ctx, blipgpu_design* design,
         BLIP_TRY(d_q.alloc(sizeof(double) * chains * p2)); BLIP_TRY(snap_q.alloc(d_q.bytes));
         BLIP_TRY(d_q0.alloc(sizeof(double) * p));
         BLIP_TRY(d_queue.alloc(sizeof(int) * (chains + 1)));
-        BLIP_TRY(d_scrL.alloc(sizeof(float) * chains * p)); BLIP_TRY(d_scrZ.alloc(sizeof(double2) * chains * p));
+        BLIP_TRY(d_scrL.alloc(sizeof(float) * chains * p * (use_role ? 2 : 1))); BLIP_TRY(d_scrZ.alloc(sizeof(double2) * chains * p));
     } else {
         BLIP_TRY(d_r.alloc(sizeof(double) * chains * n2)); BLIP_TRY(snap_r.alloc(d_r.bytes));
         if (probit) {
@@ -301,7 +327,7 @@ static int sample_impl(blipgpu_ctx* ctx, blipgpu_design* design,
     // the other kernels read permutation buffers filled ahead of them on the second stream
     const bool perm_in_kernel = gram && !inj_perm && !block;
     const bool gen_perms = !inj_perm && !perm_in_kernel && !block;
-    if (perm_in_kernel) BLIP_TRY(d_scrP.alloc(perm_elt * chains * p));
+    if (perm_in_kernel) BLIP_TRY(d_scrP.alloc(perm_elt * chains * p * (use_role ? 2 : 1)));
     else if (!block) {
         BLIP_TRY(d_perm[0].alloc(perm_elt * chains * PS * p));
         if (!inj_perm && n_total > S) BLIP_TRY(d_perm[1].alloc(perm_elt * chains * PS * p));
@@ -356,7 +382,7 @@ static int sample_impl(blipgpu_ctx* ctx, blipgpu_design* design,
     P.mask = d_mask.as<uint32_t>(); P.events = d_ev.as<uint32_t>();
     P.q0 = d_q0.as<double>(); P.zlab = d_z.as<int32_t>();
     P.scrL = d_scrL.as<float>(); P.scrZ = d_scrZ.as<double2>();
-    P.scrP = d_scrP.ptr;
+    P.scrP = d_scrP.ptr; P.scr_stride = chains * p;
     P.queue = d_queue.as<int>(); P.progress = d_queue.as<int>() + 1; P.n_chains = (int)chains;
     P.k0 = (uint32_t)seed; P.k1 = (uint32_t)(seed >> 32); P.chain_offset = (uint32_t)chain_offset;
     P.nprop = nprop; P.burn = (int)burn; P.n_keep = (int)n_keep;
@@ -429,11 +455,20 @@ static int sample_impl(blipgpu_ctx* ctx, blipgpu_design* design,
         kern = qsmem ? gibbs_gram_kernel<BLIPGPU_DESIGN_CHANGEPOINT, true> : gibbs_gram_kernel<BLIPGPU_DESIGN_CHANGEPOINT, false>;
     else
         kern = qsmem ? gibbs_gram_kernel<BLIPGPU_DESIGN_DENSE, true> : gibbs_gram_kernel<BLIPGPU_DESIGN_DENSE, false>;
+    if (use_ws) {
+        kern = design->kind == BLIPGPU_DESIGN_CHANGEPOINT ? gibbs_gram_ws_kernel<BLIPGPU_DESIGN_CHANGEPOINT, false>
+                                                          : gibbs_gram_ws_kernel<BLIPGPU_DESIGN_DENSE, false>;
+        smem = smem_ws;
+    } else if (use_cl) {
+        kern = design->kind == BLIPGPU_DESIGN_CHANGEPOINT ? gibbs_gram_ws_kernel<BLIPGPU_DESIGN_CHANGEPOINT, true>
+                                                          : gibbs_gram_ws_kernel<BLIPGPU_DESIGN_DENSE, true>;
+        smem = smem_ws;
+    }
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // gram mode: persistent CTAs (as many as are resident at once) draw (chain, 8-sweep) items
     // from a queue; with q in global memory (huge p) a chain stays on one CTA for the launch.
     int resident = 0;
-    if (gram && !block) {
+    if (gram && !block && !use_role) {
         int per_sm = 0;
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, GB_BLOCK, smem));
         resident = std::max(1, per_sm) * ctx->sm_count;
@@ -579,7 +614,7 @@ static int sample_impl(blipgpu_ctx* ctx, blipgpu_design* design,
             P.values = smp->values; P.arena_cap = smp->arena_cap;
             CUDA_TRY(cudaMemsetAsync(d_ovf.ptr, 0, sizeof(int), st));
             unsigned grid = (unsigned)chains;
-            if (gram && !block) {
+            if (gram && !block && !use_role) {
                 // no more chains than resident CTAs: one CTA per chain, spread by the hardware
                 P.sub_sweeps = (sub_sweeps_opt > 0 && chains > resident) ? std::min(sub_sweeps_opt, Sc) : Sc;
                 const int64_t n_items = chains * ((Sc + P.sub_sweeps - 1) / P.sub_sweeps);
@@ -588,7 +623,19 @@ static int sample_impl(blipgpu_ctx* ctx, blipgpu_design* design,
             }
             {
                 ScopedTimer timer(ctx, true);
-                kern<<<grid, GB_BLOCK, smem, st>>>(P);
+                if (use_cl) {
+                    // one 2-CTA cluster per chain: CTA 0 decides, CTA 1 streams the Gram columns
+                    cudaLaunchConfig_t lc;
+                    memset(&lc, 0, sizeof(lc));
+                    lc.gridDim = dim3(2 * grid); lc.blockDim = dim3(GB_BLOCK); lc.dynamicSmemBytes = smem; lc.stream = st;
+                    cudaLaunchAttribute at[1];
+                    at[0].id = cudaLaunchAttributeClusterDimension;
+                    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                    lc.attrs = at; lc.numAttrs = 1;
+                    CUDA_TRY(cudaLaunchKernelEx(&lc, kern, P));
+                } else {
+                    kern<<<grid, use_ws ? WS_THREADS : GB_BLOCK, smem, st>>>(P);
+                }
                 CUDA_TRY(cudaGetLastError());
                 const double ms = timer.stop(1);
                 smp->sweep_ms += ms;

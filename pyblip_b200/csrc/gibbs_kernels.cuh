@@ -69,6 +69,7 @@ struct SweepParams {
     // gram mode work queue: items (chain, sub-chunk of sub_sweeps sweeps) handed out in order;
     // progress[c] = sub-chunks of chain c completed in this launch
     int* queue; int* progress; int n_chains, sub_sweeps;
+    int64_t scr_stride;        // warp-specialised gram kernel: elements between the two halves of scrP / scrL
     void* scrP;                // gram mode, keyed visiting order: [chains][p] uint16/int32, rewritten every sweep
     float* scrL;               // gram mode: [chains][p]  logit of the spike uniform per position (NaN = exact path)
     double2* scrZ;             // gram mode: [chains][p]  (sqrt(post_var) * z, post_var) at positions of active coordinates
@@ -110,6 +111,7 @@ __device__ __forceinline__ double slab_draw(double XjTr, double xl2, const Hyper
 
 // block-wide exclusive scan of one int per thread; returns the exclusive prefix,
 // *total gets the block sum.  s_warp: >= GB_NWARP+1 ints of shared memory.
+template <class SY = SyncCta>
 __device__ __forceinline__ int block_excl_scan(int v, int* s_warp, int* total)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -120,7 +122,7 @@ __device__ __forceinline__ int block_excl_scan(int v, int* s_warp, int* total)
         if (lane >= o) incl += t;
     }
     if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
+    SY::sync();
     if (warp == 0) {
         int w = lane < GB_NWARP ? s_warp[lane] : 0;
         int wi = w;
@@ -132,10 +134,10 @@ __device__ __forceinline__ int block_excl_scan(int v, int* s_warp, int* total)
         if (lane < GB_NWARP) s_warp[lane] = wi - w;       // exclusive warp offsets
         if (lane == GB_NWARP - 1) s_warp[GB_NWARP] = wi;  // total
     }
-    __syncthreads();
+    SY::sync();
     int res = s_warp[warp] + incl - v;
     *total = s_warp[GB_NWARP];
-    __syncthreads();
+    SY::sync();
     return res;
 }
 
@@ -148,8 +150,10 @@ struct SweepShared {
     int scan[GB_NWARP + 2];
 };
 
-// Called by every thread of the block.  ssr = ||r||^2 (already reduced, same value
-// in every thread).  Updates sh->{sigma2,tau2,p0}; records the sweep if kept.
+// Called by every thread of the block (or of the sub-group SY synchronises: GB_BLOCK threads with
+// threadIdx.x < GB_BLOCK).  ssr = ||r||^2 (already reduced, same value in every thread).
+// Updates sh->{sigma2,tau2,p0}; records the sweep if kept.
+template <class SY = SyncCta>
 __device__ inline void sweep_epilogue(const SweepParams& P, SweepShared* sh, const uint32_t* mask_s,
                                       const double* beta_g, double* scratch, const RngKey& key,
                                       int c, int s, double ssr, const double* y_s, bool latents_dirty)
@@ -169,8 +173,8 @@ __device__ inline void sweep_epilogue(const SweepParams& P, SweepShared* sh, con
             ss = fma(v, v, ss);
         }
     }
-    ss = block_sum(ss, scratch);
-    const int k = (int)(block_sum((double)cnt, scratch) + 0.5);
+    ss = block_sum<SY>(ss, scratch);
+    const int k = (int)(block_sum<SY>((double)cnt, scratch) + 0.5);
 
     if (tid == 0) {
         const blipgpu_spikeslab_config& cf = P.cfg;
@@ -210,7 +214,7 @@ __device__ inline void sweep_epilogue(const SweepParams& P, SweepShared* sh, con
         // raises BLIPGPU_ERR_NUMERIC) instead of recording garbage.  p0 == 1 is legal (quirk 1).
         if (!isfinite(sh->sigma2) || !isfinite(sh->tau2) || isnan(sh->p0)) atomicMax(P.numeric_err, 2);
     }
-    __syncthreads();
+    SY::sync();
 
     if (sweep < P.burn) return;               // uniform across the block
     const int64_t row = (int64_t)c * P.n_keep + (sweep - P.burn);
@@ -226,7 +230,7 @@ __device__ inline void sweep_epilogue(const SweepParams& P, SweepShared* sh, con
         P.row_nnz[row] = k;
     }
     for (int w = tid; w < P.words; w += GB_BLOCK) P.bits[(int64_t)w * P.rows_pad + row] = mask_s[w];
-    __syncthreads();
+    SY::sync();
     const long long off = sh->off;
     if (off >= 0 && k > 0) {
         int base = 0;
@@ -234,7 +238,7 @@ __device__ inline void sweep_epilogue(const SweepParams& P, SweepShared* sh, con
             int w = w0 + tid;
             uint32_t m = (w < P.words) ? mask_s[w] : 0u;
             int total;
-            int pre = block_excl_scan(__popc(m), sh->scan, &total);
+            int pre = block_excl_scan<SY>(__popc(m), sh->scan, &total);
             double* dst = P.values + off + base + pre;
             while (m) {
                 int b = __ffs(m) - 1;
