@@ -44,9 +44,9 @@ constexpr int WS_RING = 16;                // ring slots (power of two)
 constexpr int WS_RMAX = BLIP_WS_RMAX;      // most changes ahead of the published buffer
 constexpr int WS_PEND = 2;                 // changes applied per pass over q
 #ifndef BLIP_WS_SLOTS
-#define BLIP_WS_SLOTS 5
+#define BLIP_WS_SLOTS 6
 #endif
-constexpr int WS_SLOTS = BLIP_WS_SLOTS;    // 16-byte Gram loads per column and load group of a helper thread
+constexpr int WS_SLOTS = BLIP_WS_SLOTS;    // depth of a helper thread's rotating load pipeline (16-byte loads per column)
 constexpr int WS_PRE_CHUNK = 2 * GB_BLOCK; // positions precomputed per helper action
 
 #ifdef BLIP_PHASE_CLOCKS
@@ -86,45 +86,42 @@ template <bool CLUSTER> __device__ __forceinline__ void ws_fence()
 }
 
 // dst = src - sum_k pd[k] * G[:, pj[k]] (k < n, in order), helper warps only (ftid in [0, 256)).
-// The loads of the next group are in flight while the current one is applied.
 // (A variant that streamed the columns with cp.async.bulk into shared-memory stages was measured at
 // ~500 cycles per bulk copy whatever its size, 3x slower than these loads; left out.)
 template <int DESIGN>
 __device__ __forceinline__ void ws_flush(const SweepParams& P, const double* __restrict__ src, double* __restrict__ dst,
                                          const int (&pj)[WS_PEND], const double (&pd)[WS_PEND], int n, int ftid)
 {
+    // A rotating register pipeline of WS_SLOTS groups, one 16-byte load per column and group: every
+    // step applies the oldest group and re-issues its loads WS_SLOTS steps ahead, so the helpers feed
+    // the L1 pipeline two loads at a time instead of in bursts of twenty -- the decision warps' gathers
+    // share that pipeline.
     const int p2 = P.p2;
-    constexpr int GROUP = 2 * GB_BLOCK * WS_SLOTS;      // doubles covered by one load group
-    double2 ga[WS_SLOTS][WS_PEND], gb[WS_SLOTS][WS_PEND];
-    auto load = [&](double2 (&g)[WS_SLOTS][WS_PEND], int k0) {
+    constexpr int STEP = 2 * GB_BLOCK;                  // doubles covered by one group step
+    double2 g[WS_SLOTS][WS_PEND];
+    auto load = [&](double2 (&gg)[WS_PEND], int kk) {
 #pragma unroll
-        for (int u = 0; u < WS_SLOTS; ++u) {
-            const int kk = k0 + u * 2 * GB_BLOCK;
+        for (int k = 0; k < WS_PEND; ++k)
+            gg[k] = (kk < p2 && k < n) ? gram_pair<DESIGN>(P, pj[k], kk) : make_double2(0.0, 0.0);
+    };
+    auto apply = [&](const double2 (&gg)[WS_PEND], int kk) {
+        if (kk < p2) {
+            double2 qq = *reinterpret_cast<const double2*>(src + kk);
 #pragma unroll
             for (int k = 0; k < WS_PEND; ++k)
-                g[u][k] = (kk < p2 && k < n) ? gram_pair<DESIGN>(P, pj[k], kk) : make_double2(0.0, 0.0);
-        }
-    };
-    auto apply = [&](const double2 (&g)[WS_SLOTS][WS_PEND], int k0) {
-#pragma unroll
-        for (int u = 0; u < WS_SLOTS; ++u) {
-            const int kk = k0 + u * 2 * GB_BLOCK;
-            if (kk < p2) {
-                double2 qq = *reinterpret_cast<const double2*>(src + kk);
-#pragma unroll
-                for (int k = 0; k < WS_PEND; ++k)
-                    if (k < n) { qq.x = fma(-pd[k], g[u][k].x, qq.x); qq.y = fma(-pd[k], g[u][k].y, qq.y); }
-                *reinterpret_cast<double2*>(dst + kk) = qq;
-            }
+                if (k < n) { qq.x = fma(-pd[k], gg[k].x, qq.x); qq.y = fma(-pd[k], gg[k].y, qq.y); }
+            *reinterpret_cast<double2*>(dst + kk) = qq;
         }
     };
     int k0 = 2 * ftid;
-    load(ga, k0);
-    for (; k0 < p2; k0 += 2 * GROUP) {
-        load(gb, k0 + GROUP);
-        apply(ga, k0);
-        load(ga, k0 + 2 * GROUP);
-        apply(gb, k0 + GROUP);
+#pragma unroll
+    for (int i = 0; i < WS_SLOTS; ++i) load(g[i], k0 + i * STEP);
+    for (; k0 < p2; k0 += WS_SLOTS * STEP) {
+#pragma unroll
+        for (int i = 0; i < WS_SLOTS; ++i) {
+            apply(g[i], k0 + i * STEP);
+            load(g[i], k0 + (i + WS_SLOTS) * STEP);
+        }
     }
 }
 
