@@ -8,9 +8,9 @@ spike-and-slab sampler (BASELINE.json metric) on N B200s.
     python bench.py --impl reference ...      # the reference's Cython sampler on the host cores
 
 Workload (BASELINE.json configs[1]): LinearSpikeSlab, n=1000,
-p=10000, AR(1) rho=0.95 design, 50 signals, 512 chains per rank (weak scaling: chains are
-independent units; `--scaling strong` splits one set of 512 chains over the ranks), default
-hyper-priors.  One step = one full sampler pass of `--sweeps` recorded sweeps after
+p=10000, AR(1) rho=0.95 design, 50 signals, 512 chains IN TOTAL, sharded over the ranks
+(strong scaling, north_star's "512 chains sharded over 1/2/4/8 GPUs"; at N > 1 the line also
+carries `weak`: 512 chains on every rank), default hyper-priors.  One step = one full sampler pass of `--sweeps` recorded sweeps after
 `--burn` burn-in sweeps for every chain -- by default the configuration's full job,
 N=5000 after 100 burn-in sweeps.  Rank 0 prints ONE JSON line.
 
@@ -21,7 +21,12 @@ N=5000 after 100 burn-in sweeps.  Rank 0 prints ONE JSON line.
             -> H2D of X, Gram build, sampling, D2H of hyper-parameters + the sparse
             coefficient matrix (everything lm.betas is made of).
   roofline  gram-mode sweep kernel: algorithmic bytes (8p per changed coordinate for the
-            Gram column + 24p per chain-sweep) / CUDA-event kernel time vs measured HBM.
+            Gram column + 24p per chain-sweep) / CUDA-event kernel time vs measured HBM, plus what
+            actually binds it: DRAM and L2 fractions from the committed ncu capture against the L2 /
+            HBM / fp64 peaks and the L2 latency probed in this process (blipgpu_probe_*).
+  e2e_pips  e2e followed by the PIP-counting half of the path on the device-resident samples:
+            sequential_groups + all_cand_groups (thresholds >= 0.01), counts merged over ranks by
+            one packed all-reduce per stage.
   cpu_baseline  the reference's own compiled sampler (oracle/_ref) on all host cores,
             bounded sample (rank 0, N=1 only).
 """
@@ -279,9 +284,10 @@ def run_reference_arm(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * res["seconds"], "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, impl="reference",
-                                  chains=CONFIG["chains"] * (int(os.environ.get("WORLD_SIZE", "1"))
-                                                             if args.scaling == "weak" else 1)),
+        "config": dict(workload_config(args, impl="reference"), chains_run=res["cores"],
+                       note=f"bounded sample: {res['cores']} chains (one per host core) x {args.ref_sweeps} sweeps of the "
+                            f"same n, p, design and hyper-priors; throughput per chain-sweep does not depend on the "
+                            f"number of chains or sweeps (BASELINE.md section 3)"),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": res["cores"], "kind": res["kind"],
                          "sample": res["sample"]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -290,20 +296,39 @@ def run_reference_arm(args):
     emit(line)
 
 
-def workload_config(args, impl="b200", chains=None):
+def workload_config(args, impl="b200", chains=None, chains_per_rank=None):
     c = dict(CONFIG)
     if chains is not None:
         c["chains"] = chains
-    weak = chains is not None and chains != CONFIG["chains"]
     return {"workload": "LinearSpikeSlab n=1000 p=10000 AR1 rho=0.95, 512 chains "
-                        "(BASELINE.json configs[1])" + (f" on every rank: {chains} chains in total (weak scaling)" if weak else ""),
+                        "(BASELINE.json configs[1])" + (f", {chains} chains in total" if chains not in (None, CONFIG["chains"]) else ""),
             "n": c["n"], "p": c["p"], "chains": c["chains"], "signals": c["k"],
+            "chains_per_rank": chains_per_rank,
             "sweeps_per_step": (args.sweeps + args.burn) if impl == "b200" else args.ref_sweeps,
             "burn": args.burn if impl == "b200" else 0,
-            "parallelism": f"chains sharded over {args.gpus} GPU(s), no data-path collective",
+            "parallelism": f"chains sharded over {args.gpus} GPU(s); sampling has no collective, PIP counts are merged "
+                           f"by one packed int64 all-reduce per counting stage (e2e_pips)",
             "mode": args.mode if impl == "b200" else "cython",
             "l2_policy": "no flush: X'X (0.8 GB) + chain state and scratch (0.2 GB) + the sample store exceed "
                          "the 126 MB L2; hot Gram columns legitimately stay L2-resident as in a real run"}
+
+
+def hardware_probes(ctx):
+    """Denominators measured in this process, under this run's clocks (libblipgpu probe kernels)."""
+    out = {}
+    try:
+        out["l2_read_gbs"] = ctx.probe_read_bandwidth(48 << 20, 40)       # 48 MB stays in the 126 MB L2
+        out["hbm_read_gbs"] = ctx.probe_read_bandwidth(4 << 30, 2)        # 4 GB does not
+        out["fp64_dfma_tflops"] = ctx.probe_fp64(0)
+        out["fp64_dmma_tflops"] = ctx.probe_fp64(1)
+        out["l2_latency_cycles"] = ctx.probe_latency(32 << 20)
+        out["how"] = ("blipgpu_probe_read_bandwidth: 16-byte ld.cg streaming, 8 loads in flight per thread, 8 CTAs "
+                      "per SM, 48 MB x 40 passes (L2) / 4 GB x 2 passes (HBM), best of 3; blipgpu_probe_fp64: 8 "
+                      "independent DFMA chains per thread / 8 independent mma.sync.m8n8k4.f64 per warp; "
+                      "blipgpu_probe_latency: dependent ld.cg pointer chase over 32 MB")
+    except Exception as err:       # a probe must not take the result down
+        out["error"] = f"{type(err).__name__}: {err}"
+    return out
 
 
 def main():
@@ -318,26 +343,25 @@ def main():
     ap.add_argument("--ref-sweeps", type=int, default=200, dest="ref_sweeps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-pips", action="store_true")
+    ap.add_argument("--no-weak", action="store_true")
     ap.add_argument("--no-clocks", action="store_true")
     ap.add_argument("--debug", action="store_true")
-    ap.add_argument("--scaling", default="weak", choices=["strong", "weak"],
-                    help="weak (default): chains are independent units, every rank runs the configuration's 512 "
-                         "chains (global chain ids rank*512 ..), no data-path collective; strong: the same 512 "
-                         "chains are split over the ranks (64 per GPU at N=8: fewer chains than SMs)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong (default): BASELINE's 512 chains in total, sharded over the ranks (64 per GPU at "
+                         "N=8); at N > 1 the weak configuration (512 chains on every rank, global chain ids "
+                         "rank*512 ..) is run as well and reported under `weak`.  weak: the headline is the weak run")
     args = ap.parse_args()
     _capture_stdout()
     if args.impl == "reference":
         return run_reference_arm(args)
 
     rank, world, local_rank, dist = dist_setup(args.gpus)
-    from pyblip_b200 import _lib, dist as bdist
+    from pyblip_b200 import _lib, dist as bdist, create_groups
     from pyblip_b200.linear import LinearSpikeSlab
 
     X, y, _ = make_data()
     n, p = X.shape
-    chains = CONFIG["chains"] * (world if args.scaling == "weak" else 1)
-    c0, c1 = bdist.shard_chains(chains, rank, world)
-    nloc = c1 - c0
     ctx = _lib.Context.get(local_rank)
     design = _lib.Design.upload(X, ctx)
     mode_id = {"gram": _lib.MODE_GRAM, "residual": _lib.MODE_RESIDUAL}[args.mode]
@@ -346,47 +370,66 @@ def main():
     cfg = LinearSpikeSlab(X, y)._config()
     S, B = args.sweeps, args.burn
 
-    def step(seed):
-        t0 = time.perf_counter()
-        smp = _lib.sample_spikeslab(design, cfg, y=y, chains=nloc, chain_offset=c0, n_keep=S,
-                                    burn=B, seed=seed, mode=mode_id)
-        t1 = time.perf_counter()
-        info = smp.info
-        out = dict(total_ms=info.total_ms, sweep_ms=info.sweep_ms, launches=info.sweep_launches,
-                   changes=info.n_changes, windows=info.n_windows, nnz=info.nnz)
-        smp.close()
-        if args.debug and rank == 0:
-            print(f"[step] call {1e3 * (t1 - t0):.1f} ms  device {info.total_ms:.1f} ms  sweep kernels "
-                  f"{info.sweep_ms:.1f} ms  close {1e3 * (time.perf_counter() - t1):.1f} ms  "
-                  f"nnz/row {info.nnz / max(info.rows, 1):.1f}", file=sys.stderr, flush=True)
-        return out
+    def timed_run(chains, c0, nloc, want_clocks):
+        """args.warmup untimed steps, then args.steps timed ones of `nloc` local chains."""
+        def step(seed):
+            t0 = time.perf_counter()
+            smp = _lib.sample_spikeslab(design, cfg, y=y, chains=nloc, chain_offset=c0, n_keep=S,
+                                        burn=B, seed=seed, mode=mode_id)
+            t1 = time.perf_counter()
+            info = smp.info
+            out = dict(total_ms=info.total_ms, sweep_ms=info.sweep_ms, launches=info.sweep_launches,
+                       changes=info.n_changes, windows=info.n_windows, nnz=info.nnz)
+            smp.close()
+            if args.debug and rank == 0:
+                print(f"[step] call {1e3 * (t1 - t0):.1f} ms  device {info.total_ms:.1f} ms  sweep kernels "
+                      f"{info.sweep_ms:.1f} ms  nnz/row {info.nnz / max(info.rows, 1):.1f}", file=sys.stderr, flush=True)
+            return out
+        for w in range(args.warmup):
+            step(1000 + w)
+        clocks = ClockSampler(local_rank)
+        if want_clocks:
+            clocks.start()
+        barrier(dist, ctx)
+        ctx.counters(reset=True)
+        ctx.event_record(0)
+        stats = [step(2000 + k) for k in range(args.steps)]
+        ctx.event_record(1)
+        barrier(dist, ctx)
+        ms_local = ctx.event_elapsed_ms(0, 1)
+        counters = ctx.counters()
+        ms_total = reduce_max(dist, ms_local)
+        clock_info = clocks.stop() if want_clocks else None
+        updates_total = float(chains) * p * (S + B) * args.steps
+        return dict(value=updates_total / (ms_total * 1e-3), ms_total=ms_total, ms_local=ms_local, stats=stats,
+                    counters=counters, clocks=clock_info, updates_total=updates_total)
 
-    for w in range(args.warmup):
-        step(1000 + w)
-    clocks = ClockSampler(local_rank)
-    if rank == 0 and not args.no_clocks:
-        clocks.start()
-    barrier(dist, ctx)
-    ctx.counters(reset=True)
-    ctx.event_record(0)
-    stats = [step(2000 + k) for k in range(args.steps)]
-    ctx.event_record(1)
-    barrier(dist, ctx)
-    ms_total = ctx.event_elapsed_ms(0, 1)
-    counters = ctx.counters()
-    ms_total = reduce_max(dist, ms_total)
-    clock_info = clocks.stop() if rank == 0 else None
-    updates_total = float(chains) * p * (S + B) * args.steps
-    value = updates_total / (ms_total * 1e-3)
+    chains = CONFIG["chains"] * (world if args.scaling == "weak" else 1)
+    c0, c1 = bdist.shard_chains(chains, rank, world)
+    nloc = c1 - c0
+    main_run = timed_run(chains, c0, nloc, rank == 0 and not args.no_clocks)
+    value, ms_total, stats, counters = main_run["value"], main_run["ms_total"], main_run["stats"], main_run["counters"]
+    updates_total = main_run["updates_total"]
+    kernel_variant = "classic (one CTA per chain, work queue)" if nloc > 148 else \
+        "role-specialised (decision warps + helper warps, one SM per chain)"
+
+    weak = None
+    if world > 1 and args.scaling == "strong" and not args.no_weak:
+        wchains = CONFIG["chains"] * world
+        w0, w1 = bdist.shard_chains(wchains, rank, world)
+        wr = timed_run(wchains, w0, w1 - w0, False)
+        weak = {"value": wr["value"], "unit": UNIT, "chains": wchains, "chains_per_rank": w1 - w0,
+                "ms_per_step": wr["ms_total"] / args.steps}
 
     # ---- roofline of the dominant kernel (this rank; ranks are symmetric)
+    probes = hardware_probes(ctx) if rank == 0 else {}
     sweep_ms = sum(s["sweep_ms"] for s in stats)
     n_launch = sum(s["launches"] for s in stats)
     chain_sweeps = float(nloc) * (S + B) * args.steps
     changes = float(sum(s["changes"] for s in stats))
     if mode_id == _lib.MODE_GRAM:
         alg_bytes = 8.0 * p * changes + 24.0 * p * chain_sweeps
-        kernel = "gibbs_gram_kernel"
+        kernel = "gibbs_gram_kernel" if nloc > 148 else "gibbs_gram_ws_kernel"
     else:
         alg_bytes = 8.0 * n * p * chain_sweeps
         kernel = "gibbs_residual_kernel"
@@ -397,47 +440,83 @@ def main():
     else:
         peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
     achieved = alg_bytes / (sweep_ms * 1e-3) / 1e9
-    # DRAM traffic of one launch from the committed ncu --set full capture (same launch shape:
+    avg_launch_ms = sweep_ms / max(n_launch, 1)
+    # DRAM / L2 traffic of one launch from the committed ncu --set full capture (same launch shape:
     # all 512 chains x 32 sweeps on one GPU); null for any other shape
-    traffic = None
+    traffic = l2_bytes = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath) and world == 1 and kernel in json.load(open(tpath)):
-        traffic = float(json.load(open(tpath))[kernel]["dram_bytes_per_launch"])
-    roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": peak_src, "launches": n_launch,
-                "avg_launch_ms": sweep_ms / max(n_launch, 1),
+    if os.path.exists(tpath) and world == 1:
+        tj = json.load(open(tpath)).get(kernel)
+        if tj:
+            traffic = float(tj["dram_bytes_per_launch"])
+            l2_bytes = float(tj["l2_to_sm_bytes_per_launch"]) if "l2_to_sm_bytes_per_launch" in tj else None
+    if mode_id == _lib.MODE_GRAM:
+        bound = "latency"
+        bound_note = ("the formula of SURVEY 8(d) gives an HBM-EQUIVALENT figure (`achieved`, `frac`); the kernel is not "
+                      "HBM-bound: its DRAM traffic is a fraction of the algorithmic bytes (hot Gram columns are L2 hits) "
+                      "and L2 / issue slots are far from saturated -- it is bound by the per-chain dependency chain "
+                      "(window -> barrier -> first change -> gathered Gram entry at L2 latency -> next window)")
+    else:
+        bound = "l2"
+        bound_note = "X (80 MB) is pinned in L2 and re-read by every chain: the binding resource is L2 -> SM bandwidth"
+    l2_peak = probes.get("l2_read_gbs")
+    roofline = {"bound": bound, "bound_note": bound_note, "kernel": kernel, "kernel_variant": kernel_variant,
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "peak_source": peak_src, "launches": n_launch, "avg_launch_ms": avg_launch_ms,
                 "alg_bytes_per_launch": alg_bytes / max(n_launch, 1),
+                "dram_frac": (traffic / (avg_launch_ms * 1e-3) / 1e9 / peak) if traffic else None,
+                "l2_peak": l2_peak, "l2_unit": "GB/s",
+                "l2_frac": (l2_bytes / (avg_launch_ms * 1e-3) / 1e9 / l2_peak) if (l2_bytes and l2_peak) else None,
+                "l2_frac_of_algorithmic_bytes": (achieved / l2_peak) if l2_peak else None,
+                "probes": probes,
                 "changes_per_chain_sweep": changes / chain_sweeps,
                 "windows_per_chain_sweep": float(sum(s["windows"] for s in stats)) / chain_sweeps,
-                "kernel_share_of_step": sweep_ms / (ctx.event_elapsed_ms(0, 1))}
+                "kernel_share_of_step": sweep_ms / main_run["ms_local"]}
 
     # ---- end to end through the reference-facing API, host buffers
-    e2e = None
+    e2e = e2e_pips = None
     if not args.no_e2e:
-        def e2e_step(seed):
+        def e2e_step(seed, with_pips):
             lm = LinearSpikeSlab(X, y)
             lm.sample(N=S, burn=B, chains=chains, seed=seed, mode=args.mode)
             indptr, indices, values = lm.samples_csr()
-            nnz = int(indptr[-1])
+            out = dict(nnz=int(indptr[-1]))
+            if with_pips:
+                # the other half of the path, on the device-resident samples of every rank
+                seq = create_groups.sequential_groups(lm, q=0.1, max_pep=0.25, max_size=25, prenarrow=True)
+                allg = create_groups.all_cand_groups(lm, q=0.1, max_pep=0.25, max_size=25,
+                                                     prefilter_thresholds=[0.01, 0.02, 0.03, 0.05, 0.1, 0.2])
+                out.update(n_seq=len(seq), n_all=len(allg))
             lm._release()
             lm._design.close()
-            return nnz
-        e2e_step(3000)                               # warm-up (allocator, page-in)
-        barrier(dist, ctx)
-        ctx.counters(reset=True)
-        ctx.event_record(2)
-        for k in range(args.steps):
-            e2e_step(4000 + k)
-        ctx.event_record(3)
-        barrier(dist, ctx)
-        e_ms = reduce_max(dist, ctx.event_elapsed_ms(2, 3))
-        ec = ctx.counters()
-        e2e = {"value": updates_total / (e_ms * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": reduce_sum(dist, ec["h2d_bytes"]) / args.steps,
-               "d2h_bytes_per_step": reduce_sum(dist, ec["d2h_bytes"]) / args.steps,
-               "ms_per_step": e_ms / args.steps,
-               "api": "LinearSpikeSlab(X, y).sample(N, burn, chains) + samples_csr()"}
+            return out
+
+        def timed_e2e(with_pips, ev0, ev1):
+            e2e_step(3000, with_pips)                    # warm-up (allocator, page-in)
+            barrier(dist, ctx)
+            ctx.counters(reset=True)
+            c_before = dict(bdist.STATS)
+            ctx.event_record(ev0)
+            outs = [e2e_step(4000 + k, with_pips) for k in range(args.steps)]
+            ctx.event_record(ev1)
+            barrier(dist, ctx)
+            e_ms = reduce_max(dist, ctx.event_elapsed_ms(ev0, ev1))
+            ec = ctx.counters()
+            res = {"value": updates_total / (e_ms * 1e-3), "unit": UNIT,
+                   "h2d_bytes_per_step": reduce_sum(dist, ec["h2d_bytes"]) / args.steps,
+                   "d2h_bytes_per_step": reduce_sum(dist, ec["d2h_bytes"]) / args.steps,
+                   "ms_per_step": e_ms / args.steps}
+            return res, outs, {k: (bdist.STATS[k] - c_before[k]) / args.steps for k in c_before}
+        e2e, _, _ = timed_e2e(False, 2, 3)
+        e2e["api"] = "LinearSpikeSlab(X, y).sample(N, burn, chains) + samples_csr()"
+        if not args.no_pips:
+            e2e_pips, outs, coll = timed_e2e(True, 4, 5)
+            e2e_pips.update(api="... + create_groups.sequential_groups(lm, prenarrow=True) + create_groups.all_cand_groups(lm, "
+                                "prefilter_thresholds >= 0.01) on the device-resident samples",
+                            pip_stage_ms_per_step=e2e_pips["ms_per_step"] - e2e["ms_per_step"],
+                            sequential_groups=outs[-1]["n_seq"], all_cand_groups=outs[-1]["n_all"],
+                            collectives_per_step=coll,
+                            sample_rows=int(chains) * S)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -454,7 +533,8 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, chains=chains), "clocks": clock_info, "e2e": e2e,
+            "config": workload_config(args, chains=chains, chains_per_rank=nloc), "clocks": main_run["clocks"],
+            "e2e": e2e, "e2e_pips": e2e_pips, "weak": weak,
             "gpu_launches": int(counters["kernel_launches"]),
             "roofline": roofline, "cpu_baseline": cpu,
         }

@@ -38,11 +38,10 @@ class ChangepointSpikeSlab(LinearSpikeSlab):
 
     def sample(self, N, burn=100, chains=1, num_processes=1, bsize=1,
                max_signals_per_block=None, **kw):
-        if bsize != 1:
-            raise NotImplementedError("the structured change-point design supports bsize=1 only; "
-                                      "use LinearSpikeSlab on the dense design for bsize > 1")
+        # bsize > 1: the block sampler on the same closed-form Gram (block Grams T - max(a, b))
         kw.setdefault("mode", "gram")
-        return super().sample(N, burn=burn, chains=chains, num_processes=num_processes, **kw)
+        return super().sample(N, burn=burn, chains=chains, num_processes=num_processes, bsize=bsize,
+                              max_signals_per_block=max_signals_per_block, **kw)
 
 
 def changepoint_cand_groups(model, **kwargs):

@@ -105,6 +105,17 @@ __global__ void block_gram_kernel(const double* __restrict__ XT, double* __restr
     }
 }
 
+// the same for the change-point design X[i][j] = 1{i >= j}: X_a . X_b = T - max(a, b)
+__global__ void block_gram_changepoint_kernel(double* __restrict__ gb, int64_t T, int64_t nblock, int bsize)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nblock * bsize * bsize) return;
+    const int64_t b = t / (bsize * bsize);
+    const int e = (int)(t % (bsize * bsize));
+    const int64_t ja = (b * bsize + e / bsize) % T, jb = (b * bsize + e % bsize) % T;
+    gb[t] = (double)(T - (ja > jb ? ja : jb));
+}
+
 template <class T>
 int upload_chunk(T* dst, const T* src_host, int64_t chains, int64_t total_per_chain,
                  int64_t off_per_chain, int64_t count_per_chain, cudaStream_t st)
@@ -168,8 +179,8 @@ static int sample_impl(blipgpu_ctx* ctx, blipgpu_design* design,
             blip_set_error("sample_spikeslab_multi: bsize %d is not supported (2 <= bsize <= min(%d, p))", bsize, BK_MAXB);
             return BLIP_ERR_UNSUPPORTED;
         }
-        if (design->kind != BLIPGPU_DESIGN_DENSE) {
-            blip_set_error("sample_spikeslab_multi: the block sampler needs a dense design"); return BLIP_ERR_UNSUPPORTED;
+        if (design->kind == BLIPGPU_DESIGN_CHANGEPOINT && probit) {
+            blip_set_error("sample_spikeslab_multi: the structured change-point design is linear only"); return BLIP_ERR_UNSUPPORTED;
         }
         const int cap = max_signals <= 0 ? bsize : std::min(max_signals, bsize);   // :403-404
         for (int m = 1; m <= cap; ++m) {                            // itertools.combinations order (:405-409)
@@ -405,7 +416,11 @@ static int sample_impl(blipgpu_ctx* ctx, blipgpu_design* design,
         if (blocks_host) CUDA_TRY(cudaMemcpyAsync(d_blocks.ptr, blocks_host, d_blocks.bytes, cudaMemcpyHostToDevice, ctx->stream));
         else block_table_kernel<<<(unsigned)((chains * nblock + 255) / 256), 256, 0, ctx->stream>>>(
                 d_blocks.as<int32_t>(), (int)chains, (int)nblock, bsize, (int)p, P.k0, P.k1, P.chain_offset);
-        block_gram_kernel<<<(unsigned)nblock, 256, 0, ctx->stream>>>(design->XT, d_gb.as<double>(), n, p, design->ldx, bsize);
+        if (design->kind == BLIPGPU_DESIGN_CHANGEPOINT)
+            block_gram_changepoint_kernel<<<(unsigned)((nblock * bsize * bsize + 255) / 256), 256, 0, ctx->stream>>>(
+                d_gb.as<double>(), p, nblock, bsize);
+        else
+            block_gram_kernel<<<(unsigned)nblock, 256, 0, ctx->stream>>>(design->XT, d_gb.as<double>(), n, p, design->ldx, bsize);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));       // model_masks / blocks_host are host temporaries
         P.blocks = d_blocks.as<int32_t>(); P.gb = d_gb.as<double>(); P.model_masks = d_masks.as<uint32_t>();
@@ -448,7 +463,8 @@ static int sample_impl(blipgpu_ctx* ctx, blipgpu_design* design,
 
     // ---- kernel selection
     void (*kern)(SweepParams) = nullptr;
-    if (block) kern = gram ? gibbs_block_kernel<true, false>
+    if (block) kern = gram ? (design->kind == BLIPGPU_DESIGN_CHANGEPOINT ? gibbs_block_kernel<true, false, BLIPGPU_DESIGN_CHANGEPOINT>
+                                                                        : gibbs_block_kernel<true, false>)
                            : (probit ? gibbs_block_kernel<false, true> : gibbs_block_kernel<false, false>);
     else if (!gram) kern = probit ? gibbs_residual_kernel<true> : gibbs_residual_kernel<false>;
     else if (design->kind == BLIPGPU_DESIGN_CHANGEPOINT)

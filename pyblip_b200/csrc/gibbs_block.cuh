@@ -293,7 +293,7 @@ struct BlockShared {
 #define BPH_PRINT do {} while (0)
 #endif
 
-template <bool GRAM, bool PROBIT>
+template <bool GRAM, bool PROBIT, int DESIGN = BLIPGPU_DESIGN_DENSE>
 __global__ void __launch_bounds__(GB_BLOCK, 2) gibbs_block_kernel(SweepParams P)
 {
     extern __shared__ __align__(16) double sm[];
@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(GB_BLOCK, 2) gibbs_block_kernel(SweepParams P)
         if (GRAM) {
             if (tid == 0) sh.rr = sh.rr + 2.0 * coef * q[j] + coef * coef * P.Xl2[j];   // ||r + coef X_j||^2
             __syncthreads();
-            gram_axpy<BLIPGPU_DESIGN_DENSE>(P, q, j, -coef);
+            gram_axpy<DESIGN>(P, q, j, -coef);
         } else {
             const double* xcol = P.XT + (int64_t)j * P.ldx;
             for (int k = tid; k < n; k += GB_BLOCK) {
@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(GB_BLOCK, 2) gibbs_block_kernel(SweepParams P)
                 while (m) {
                     int j = 32 * w + __ffs(m) - 1;
                     m &= m - 1;
-                    gram_axpy<BLIPGPU_DESIGN_DENSE>(P, q, j, __ldcg(beta_g + j));
+                    gram_axpy<DESIGN>(P, q, j, __ldcg(beta_g + j));
                 }
             }
             __syncthreads();

@@ -260,6 +260,32 @@ def test_changepoint_structured_design_equals_dense_design(gpu):
     assert len(groups) > 0 and (0,) not in [g for g, _ in groups]
 
 
+def test_changepoint_block_sampler_on_the_implicit_design(gpu):
+    """`detect_changepoints(..., sample_kwargs=dict(bsize=3))` (the reference forwards any sample_kwargs,
+    changepoint.py:37-40): the block sampler on the implicit design equals the block sampler on the dense
+    design -- same indicators, coefficients within 1e-9 -- and the block oracle."""
+    from oracle import gibbs_oracle as go
+    from pyblip_b200 import LinearSpikeSlab, changepoint
+    rng = np.random.default_rng(19)
+    T = 140
+    beta = np.zeros(T)
+    beta[[25, 70, 71, 110]] = [3.0, -2.0, -2.0, 2.5]
+    Y = np.cumsum(beta) + rng.standard_normal(T)
+    X = np.tril(np.ones((T, T)))
+    for bsize, cap in [(2, None), (3, 2), (5, None)]:
+        cp = changepoint.ChangepointSpikeSlab(Y)
+        cp.sample(N=30, burn=5, chains=2, seed=33, bsize=bsize, max_signals_per_block=cap)
+        lm = LinearSpikeSlab(X, Y)
+        lm.sample(N=30, burn=5, chains=2, seed=33, mode="gram", bsize=bsize, max_signals_per_block=cap)
+        assert np.array_equal(cp.betas != 0, lm.betas != 0), bsize
+        assert util.rel_err(cp.betas, lm.betas) <= RTOL
+        assert util.rel_err(cp.sigma2s, lm.sigma2s) <= RTOL
+        orc = go.sample_spikeslab_multi(35, bsize, X, y=Y, hp=go.hparams(), seed=33, chain=1,
+                                        max_signals_per_block=cap or 0)
+        assert np.array_equal(cp.betas[30:] != 0, orc["betas"][5:] != 0)
+        assert util.rel_err(cp.betas[30:], orc["betas"][5:]) <= RTOL
+
+
 def test_api_surface_matches_reference(gpu):
     """Constructor defaults and attributes of the drop-in classes (linear.py:63-80, 165-168)."""
     import inspect
