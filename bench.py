@@ -445,9 +445,9 @@ def main():
     # all 512 chains x 32 sweeps on one GPU); null for any other shape
     traffic = l2_bytes = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath) and world == 1:
+    if os.path.exists(tpath):
         tj = json.load(open(tpath)).get(kernel)
-        if tj:
+        if tj and nloc == {"gibbs_gram_kernel": 512, "gibbs_gram_ws_kernel": 64}.get(kernel):
             traffic = float(tj["dram_bytes_per_launch"])
             l2_bytes = float(tj["l2_to_sm_bytes_per_launch"]) if "l2_to_sm_bytes_per_launch" in tj else None
     if mode_id == _lib.MODE_GRAM:
@@ -480,13 +480,14 @@ def main():
             lm = LinearSpikeSlab(X, y)
             lm.sample(N=S, burn=B, chains=chains, seed=seed, mode=args.mode)
             indptr, indices, values = lm.samples_csr()
-            out = dict(nnz=int(indptr[-1]))
+            out = dict(nnz=int(indptr[-1]), pip_s=0.0)
             if with_pips:
+                t_p = time.perf_counter()
                 # the other half of the path, on the device-resident samples of every rank
                 seq = create_groups.sequential_groups(lm, q=0.1, max_pep=0.25, max_size=25, prenarrow=True)
                 allg = create_groups.all_cand_groups(lm, q=0.1, max_pep=0.25, max_size=25,
                                                      prefilter_thresholds=[0.01, 0.02, 0.03, 0.05, 0.1, 0.2])
-                out.update(n_seq=len(seq), n_all=len(allg))
+                out.update(n_seq=len(seq), n_all=len(allg), pip_s=time.perf_counter() - t_p)
             lm._release()
             lm._design.close()
             return out
@@ -513,7 +514,7 @@ def main():
             e2e_pips, outs, coll = timed_e2e(True, 4, 5)
             e2e_pips.update(api="... + create_groups.sequential_groups(lm, prenarrow=True) + create_groups.all_cand_groups(lm, "
                                 "prefilter_thresholds >= 0.01) on the device-resident samples",
-                            pip_stage_ms_per_step=e2e_pips["ms_per_step"] - e2e["ms_per_step"],
+                            pip_stage_ms_per_step=reduce_max(dist, 1e3 * float(np.mean([o["pip_s"] for o in outs]))),
                             sequential_groups=outs[-1]["n_seq"], all_cand_groups=outs[-1]["n_all"],
                             collectives_per_step=coll,
                             sample_rows=int(chains) * S)

@@ -194,6 +194,32 @@ def run_case(mod, name, n, p, k, N, chains, probit, bsize, maxsig, hp_over, data
     return worst
 
 
+def reference_run_multi(X, y, probit, hp, N, bsize, maxsig, chain, np_seed, mod=None):
+    """One chain of the reference's compiled `_sample_spikeslab_multi` (oracle/_ref) with its native RNG,
+    every variate recorded.  Returns (reference outputs, streams keyed like blipgpu_multi_streams).
+    Used by tests/test_configs_gpu.py at BASELINE's full sizes."""
+    if mod is None:
+        ref_loader.load()
+        from pyblip.linear import _linear_multi as mod
+    n, p = X.shape
+    np.random.seed(np_seed)
+    zlab = np.asarray(y).astype(np.int64) if probit else np.zeros(1, dtype=np.int64)
+    ybuf = np.zeros(n) if probit else np.array(y, dtype=np.float64)
+    Xc = np.ascontiguousarray(X, dtype=np.float64)
+    with MultiRecorder(N, n, p, bsize, chain, mod, probit) as rec:
+        ref = mod._sample_spikeslab_multi(
+            N=N, bsize=bsize, X=Xc, y=ybuf, z=zlab, probit=int(probit),
+            tau2=hp["tau2"], update_tau2=int(hp["update_tau2"]),
+            tau2_a0=hp["tau2_a0"], tau2_b0=hp["tau2_b0"],
+            sigma2=hp["sigma2"], update_sigma2=int(hp["update_sigma2"]),
+            sigma2_a0=hp["sigma2_a0"], sigma2_b0=hp["sigma2_b0"],
+            p0=hp["p0"], update_p0=int(hp["update_p0"]), min_p0=hp["min_p0"],
+            p0_a0=hp["p0_a0"], p0_b0=hp["p0_b0"], max_signals_per_block=maxsig)
+    st = rec.streams(hp)
+    st["z"] = st.pop("zn")
+    return ref, st
+
+
 def main():
     ref_loader.load()
     from pyblip.linear import _linear_multi as mod

@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(GB_BLOCK, 2) gibbs_residual_kernel(SweepParams
     double* r_s = sm;
     double* mu_s = PROBIT ? r_s + n2 : nullptr;
     double* y_s = PROBIT ? r_s + 2 * n2 : nullptr;
-    double* part = r_s + (PROBIT ? 3 : 1) * n2;        // [GB_NWARP][32]
+    double* part = r_s + (PROBIT ? 3 : 1) * n2;        // [2][GB_ROUND] dots of the current and of the next window (+ slack)
     double* scratch = part + GB_NWARP * 32;            // [40]
     uint32_t* mask_s = (uint32_t*)(scratch + 40);      // [words]
 
@@ -303,50 +303,66 @@ __global__ void __launch_bounds__(GB_BLOCK, 2) gibbs_residual_kernel(SweepParams
         __syncthreads();
         const Hyper h = { sh.sigma2, sh.tau2, sh.logodds };
 
-        int pos0 = 0;
+        // Two-stage pipeline over the speculation windows.  While warp 0 scores window w (dependent fp64
+        // math, ~1 us), warps 1-7 already stream their columns of window w+1 against the same residual
+        // (warp 0 streams its own four afterwards) -- valid if w turns out to be all null, which is the
+        // common case; a change in w discards them.
+        // part[cur] holds the dots of the window at pos0 when have_dots is set.  A warp always streams
+        // whole columns with the same lane -> element assignment, so a dot is the same number whichever
+        // warp computes it: results do not depend on the schedule.
+        int pos0 = 0, cur = 0;
+        bool have_dots = false;
         while (pos0 < p) {
             const int T = min(GB_ROUND, p - pos0);
             ++n_windows;
-            // ---- speculative dots of the next T columns against the current residual
-            const int jl = perm_s[min(pos0 + lane, p - 1)];
-            // warp 0 scores the window after the dots: what does not depend on them (indicator, uniform, ||X_j||^2)
-            // is fetched now, under the latency of the column loads
-            bool act = false;
-            double u_spec = 0.0, xl2_spec = 0.0;
-            if (warp == 0 && lane < T) {
-                act = (mask_s[jl >> 5] >> (jl & 31)) & 1u;
-                if (!act) {
-                    u_spec = u_s ? u_s[pos0 + lane] : rng_uniform(key, KIND_SPIKE_U, pos0 + lane, sweep, 0);
-                    xl2_spec = P.Xl2[jl];
-                }
-            }
-            // each warp owns GB_ROUND / GB_NWARP whole columns: few accumulators, so many loads stay in flight
-            constexpr int CPW = GB_ROUND / GB_NWARP;
-            const double* xc[CPW];
-            double acc[CPW];
-#pragma unroll
-            for (int i = 0; i < CPW; ++i) {
-                xc[i] = P.XT + (int64_t)__shfl_sync(0xffffffffu, jl, warp * CPW + i) * P.ldx;
-                acc[i] = 0.0;
-            }
-#pragma unroll 4
-            for (int k = 2 * lane; k < n2; k += 64) {
-                const double2 rk = *reinterpret_cast<const double2*>(r_s + k);
+            bool spec_skip = false;                        // (warp 0 only)
+            if (!have_dots) {
+                // ---- first window of a sweep, or the one after a change: all eight warps, four columns each
+                const int jl = perm_s[min(pos0 + lane, p - 1)];
+                constexpr int CPW = GB_ROUND / GB_NWARP;
+                const double* xc[CPW];
+                double acc[CPW];
 #pragma unroll
                 for (int i = 0; i < CPW; ++i) {
-                    const double2 x = __ldg(reinterpret_cast<const double2*>(xc[i] + k));
-                    acc[i] = fma(x.x, rk.x, acc[i]);
-                    acc[i] = fma(x.y, rk.y, acc[i]);
+                    xc[i] = P.XT + (int64_t)__shfl_sync(0xffffffffu, jl, warp * CPW + i) * P.ldx;
+                    acc[i] = 0.0;
                 }
-            }
+#pragma unroll 4
+                for (int k = 2 * lane; k < n2; k += 64) {
+                    const double2 rk = *reinterpret_cast<const double2*>(r_s + k);
 #pragma unroll
-            for (int i = 0; i < CPW; ++i) {
-                const double t = warp_sum(acc[i]);
-                if (lane == i) part[warp * CPW + i] = t;         // part[column of the window]
+                    for (int i = 0; i < CPW; ++i) {
+                        const double2 x = __ldg(reinterpret_cast<const double2*>(xc[i] + k));
+                        acc[i] = fma(x.x, rk.x, acc[i]);
+                        acc[i] = fma(x.y, rk.y, acc[i]);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < CPW; ++i) {
+                    const double t = warp_sum(acc[i]);
+                    if (lane == i) part[cur * GB_ROUND + warp * CPW + i] = t;   // part[column of the window]
+                }
+                __syncthreads();
             }
-            __syncthreads();
+            const int pos1 = pos0 + T;                     // start of the next window
+            // Measured at BASELINE's shapes: linear C2 (n = 1000) +25 % with the pipeline; probit C3 (n = 2000,
+            // a change -- hence a discarded window of 512 KB -- in 15 % of the windows, scoring only 5 % of a
+            // window's time) -7 %: probit keeps the plain schedule (dots by all warps, barrier, scoring).
+            constexpr bool PIPE = !PROBIT;
+            const bool has_next = PIPE && pos1 < p;
             if (warp == 0) {
-                const double d = part[lane];
+                // ---- score window pos0
+                const int jl = perm_s[min(pos0 + lane, p - 1)];
+                bool act = false;
+                double u_spec = 0.0, xl2_spec = 0.0;
+                if (lane < T) {
+                    act = (mask_s[jl >> 5] >> (jl & 31)) & 1u;
+                    if (!act) {
+                        u_spec = u_s ? u_s[pos0 + lane] : rng_uniform(key, KIND_SPIKE_U, pos0 + lane, sweep, 0);
+                        xl2_spec = P.Xl2[jl];
+                    }
+                }
+                const double d = part[cur * GB_ROUND + lane];
                 bool change = false;
                 if (lane < T) {
                     if (act) change = true;
@@ -359,10 +375,41 @@ __global__ void __launch_bounds__(GB_BLOCK, 2) gibbs_residual_kernel(SweepParams
                     bc.beta_old = act ? __ldcg(beta_g + jl) : 0.0;
                     bc.dspec = d;
                 }
+                spec_skip = tstar >= 0;                    // a change: the next window's dots would be discarded
+            }
+            if (has_next && !(warp == 0 && spec_skip)) {
+                // ---- meanwhile (warp 0: afterwards): the dots of window pos1, four columns per warp; the other
+                // seven warps' loads are in flight while warp 0 scores, and warp 0's own four columns stream
+                // at the bandwidth the others leave free
+                const int jl = perm_s[min(pos1 + lane, p - 1)];
+                constexpr int CPW = GB_ROUND / GB_NWARP;
+                const double* xc[CPW];
+                double acc[CPW];
+#pragma unroll
+                for (int i = 0; i < CPW; ++i) {
+                    xc[i] = P.XT + (int64_t)__shfl_sync(0xffffffffu, jl, warp * CPW + i) * P.ldx;
+                    acc[i] = 0.0;
+                }
+#pragma unroll 4
+                for (int k = 2 * lane; k < n2; k += 64) {
+                    const double2 rk = *reinterpret_cast<const double2*>(r_s + k);
+#pragma unroll
+                    for (int i = 0; i < CPW; ++i) {
+                        const double2 x = __ldg(reinterpret_cast<const double2*>(xc[i] + k));
+                        acc[i] = fma(x.x, rk.x, acc[i]);
+                        acc[i] = fma(x.y, rk.y, acc[i]);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < CPW; ++i) {
+                    const double t = warp_sum(acc[i]);
+                    if (lane == i) part[(cur ^ 1) * GB_ROUND + warp * CPW + i] = t;
+                }
             }
             __syncthreads();
             const int tstar = bc.tstar;
-            if (tstar < 0) { pos0 += T; continue; }
+            if (tstar < 0) { pos0 = pos1; cur ^= 1; have_dots = has_next; continue; }
+            have_dots = false;
 
             // ---- apply the first changing coordinate exactly like the reference
             ++n_changes;

@@ -157,28 +157,6 @@ def test_c5_global_q_gram_kernel_equals_residual(gpu):
     g["smp"].close(); r["smp"].close(); design.close()
 
 
-def test_c2_block_sampler_forms_agree_and_match_oracle(gpu):
-    """configs[1] shape with bsize=3 / bsize=5: the gram and residual forms of the block kernel --
-    different state, different arithmetic -- produce the same indicators and coefficients.  (The block
-    oracle is compared at sizes it can handle in tests/test_block_gpu.py: its X'X is a naive O(n p^2) loop.)"""
-    from pyblip_b200 import _lib
-    from pyblip_b200.linear import LinearSpikeSlab
-    import bench
-    X, y, _ = bench.make_data()
-    cfg = LinearSpikeSlab(X, y)._config()
-    design = _lib.Design.upload(X)
-    for bsize in (3, 5):
-        kw = dict(y=y, chains=3, chain_offset=7, n_keep=6, burn=0, seed=13, bsize=bsize)
-        g = _sample(design, cfg, _lib.MODE_GRAM, **kw)
-        r = _sample(design, cfg, _lib.MODE_RESIDUAL, **kw)
-        # first sweeps from beta = 0: ~1000 active coordinates, 5 x 5 blocks of rho = 0.95 columns --
-        # indicators identical, small coefficients agree to ~1e-8 element-wise
-        _csr_equal(g["csr"], r["csr"], tol=2e-8)
-        assert util.rel_err(g["hyper"], r["hyper"]) <= RTOL
-        g["smp"].close(); r["smp"].close()
-    design.close()
-
-
 def test_nprior_p2000_matches_oracle_prefix(gpu):
     """Neuronized prior at p=2000 (blocked Cholesky path is reached by some chains during burn-in):
     chain 0, first 4 sweeps against the oracle under the keyed stream."""
