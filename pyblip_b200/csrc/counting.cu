@@ -325,15 +325,22 @@ __global__ void __launch_bounds__(CT_BLOCK) gap_hist_kernel(
     unsigned long long* Hw = H + (int64_t)w * nh;
     constexpr int PF = 8;                               // row tiles a warp keeps in flight
     const int64_t step = 32 * CT_NWARP;
-    uint32_t xn[PF];
+    const uint32_t* cp = (w > 0 && max_size > 1) ? bits + (int64_t)(w - 1) * N_pad : nullptr;
+    // a lane that finds its word non-zero will need the zero run before it: the neighbouring word is
+    // requested together with the prefetch, PF tiles ahead of its use
+    uint32_t xn[PF], pn[PF];
+    auto fetch = [&](int64_t r, uint32_t& x, uint32_t& pv) {
+        x = r < r_end ? c0[r] : 0u;
+        pv = (x != 0u && cp) ? cp[r] : 0u;
+    };
 #pragma unroll
-    for (int i = 0; i < PF; ++i) { const int64_t r = r_begin + 32 * warp + i * step + lane; xn[i] = r < r_end ? c0[r] : 0u; }
+    for (int i = 0; i < PF; ++i) fetch(r_begin + 32 * warp + i * step + lane, xn[i], pn[i]);
     for (int64_t rb = r_begin + 32 * warp; rb < r_end; rb += PF * step) {
-        uint32_t xc[PF];
+        uint32_t xc[PF], pc[PF];
 #pragma unroll
-        for (int i = 0; i < PF; ++i) xc[i] = xn[i];
+        for (int i = 0; i < PF; ++i) { xc[i] = xn[i]; pc[i] = pn[i]; }
 #pragma unroll
-        for (int i = 0; i < PF; ++i) { const int64_t r = rb + (PF + i) * step + lane; xn[i] = r < r_end ? c0[r] : 0u; }
+        for (int i = 0; i < PF; ++i) fetch(rb + (PF + i) * step + lane, xn[i], pn[i]);
 #pragma unroll
         for (int i = 0; i < PF; ++i) {
             uint32_t x = xc[i];
@@ -341,8 +348,11 @@ __global__ void __launch_bounds__(CT_BLOCK) gap_hist_kernel(
             const int64_t r = rb + i * step + lane;
             // zero run that ends right before column 32 w of this row (only what the cap can see)
             int tz = 0;
-            bool done = x == 0u;
-            for (int k = 1; k <= w && 32 * (k - 1) < max_size - 1; ++k) {   // warp-uniform bounds
+            bool done = x == 0u || w == 0 || max_size == 1;
+            if (!done) {
+                if (pc[i]) { tz = __clz(pc[i]); done = true; } else tz = 32;
+            }
+            for (int k = 2; k <= w && 32 * (k - 1) < max_size - 1; ++k) {   // warp-uniform bounds; rare
                 if (__all_sync(0xffffffffu, done)) break;
                 if (!done) {
                     const uint32_t xp = bits[(int64_t)(w - k) * N_pad + r];
@@ -803,6 +813,11 @@ extern "C" int blipgpu_count_sequential(blipgpu_bits* b, int32_t max_size, int64
     const int64_t rpb = pick_rows_per_block(b->N, b->words, b->ctx->sm_count);
     const unsigned chunks = (unsigned)std::max<int64_t>(1, (b->N + rpb - 1) / rpb);
     const bool legacy = getenv("BLIPGPU_COUNT_SEQ_TILES") != nullptr && max_size <= 64;   // the round-1 tile kernel, for A/B timing
+    // The work of the gap histogram sits where the set bits are -- for posterior samples in the few words
+    // that hold the persistently active columns -- so the rows are cut into many short chunks: the CTAs of
+    // a heavy word then spread over all SMs instead of queueing on a few (0.78 ms with three chunks).
+    const int64_t rpb_gap = 16384;      // 2048 / 4096 / 8192 / 16384 rows measured: 0.54 / 0.44 / 0.39 / 0.38 ms at C2
+    const unsigned chunks_gap = (unsigned)std::max<int64_t>(1, (b->N + rpb_gap - 1) / rpb_gap);
     DevBuf hist;
     if (!legacy && b->N > 0) BLIP_TRY(hist.alloc(sizeof(unsigned long long) * 32 * (size_t)b->words * (size_t)eff));
     return with_output(b->ctx, (int64_t)max_size * b->p, zero_counts, out_is_device, [&](unsigned long long* dev) {
@@ -819,8 +834,9 @@ extern "C" int blipgpu_count_sequential(blipgpu_bits* b, int32_t max_size, int64
         unsigned long long* H = hist.as<unsigned long long>();
         cudaMemsetAsync(H, 0, hist.bytes, st);
         const size_t smem = sizeof(int) * 32 * (size_t)eff;
-        if (smem <= 40 * 1024) gap_hist_kernel<true><<<grid, CT_BLOCK, smem, st>>>(b->bits, b->N, b->N_pad, eff, rpb, H);
-        else gap_hist_kernel<false><<<grid, CT_BLOCK, 0, st>>>(b->bits, b->N, b->N_pad, eff, rpb, H);
+        dim3 ggrid((unsigned)b->words, chunks_gap);
+        if (smem <= 40 * 1024) gap_hist_kernel<true><<<ggrid, CT_BLOCK, smem, st>>>(b->bits, b->N, b->N_pad, eff, rpb_gap, H);
+        else gap_hist_kernel<false><<<ggrid, CT_BLOCK, 0, st>>>(b->bits, b->N, b->N_pad, eff, rpb_gap, H);
         const int64_t ncols = 32 * b->words;
         gap_suffix_kernel<<<(unsigned)((ncols + 127) / 128), 128, 0, st>>>(H, ncols, eff);
         gap_to_zero_counts_kernel<<<(unsigned)((b->p + 127) / 128), 128, 0, st>>>(H, b->N, b->p, eff, dev);
