@@ -199,7 +199,7 @@ __device__ inline double rng_beta(const RngKey& key, uint32_t proposal, uint32_t
 //               (blipgpu_debug_truncnorm, oracle/pin_truncnorm.py).
 // Attempts are capped so that a NaN argument (upstream bug) cannot hang the GPU.
 struct TnKeyed {
-    const RngKey& key; uint32_t kind, c0, c1; const double* first_normal; uint32_t attempt;
+    RngKey key; uint32_t kind, c0, c1; const double* first_normal; uint32_t attempt;
     static constexpr uint32_t kMaxAttempts = 1u << 14;
     __device__ __forceinline__ bool pair(double& y, double& u2) {
         if (attempt >= kMaxAttempts) return false;
@@ -260,16 +260,16 @@ __device__ __forceinline__ double truncnorm_from(Src& src, double mean, double v
     return mean + scale * z;
 }
 
-__device__ inline double truncnorm_std(const RngKey& key, uint32_t kind, uint32_t c0, uint32_t c1,
-                                       double a, const double* first_normal = nullptr)
+__device__ __forceinline__ double truncnorm_std(const RngKey& key, uint32_t kind, uint32_t c0, uint32_t c1,
+                                                double a, const double* first_normal = nullptr)
 {
     TnKeyed src{ key, kind, c0, c1, first_normal, 0u };
     return truncnorm_std_from(src, a);
 }
 
-__device__ inline double truncnorm(const RngKey& key, uint32_t kind, uint32_t c0, uint32_t c1,
-                                   double mean, double var, double b, int lower_interval,
-                                   const double* first_normal = nullptr)
+__device__ __forceinline__ double truncnorm(const RngKey& key, uint32_t kind, uint32_t c0, uint32_t c1,
+                                            double mean, double var, double b, int lower_interval,
+                                            const double* first_normal = nullptr)
 {
     TnKeyed src{ key, kind, c0, c1, first_normal, 0u };
     return truncnorm_from(src, mean, var, b, lower_interval);

@@ -312,104 +312,179 @@ __global__ void __launch_bounds__(GB_BLOCK, 2) gibbs_residual_kernel(SweepParams
         // warp computes it: results do not depend on the schedule.
         int pos0 = 0, cur = 0;
         bool have_dots = false;
+        int null_run = 0;                              // consecutive all-null windows so far
         while (pos0 < p) {
             const int T = min(GB_ROUND, p - pos0);
             ++n_windows;
-            bool spec_skip = false;                        // (warp 0 only)
-            if (!have_dots) {
-                // ---- first window of a sweep, or the one after a change: all eight warps, four columns each
-                const int jl = perm_s[min(pos0 + lane, p - 1)];
-                constexpr int CPW = GB_ROUND / GB_NWARP;
-                const double* xc[CPW];
-                double acc[CPW];
-#pragma unroll
-                for (int i = 0; i < CPW; ++i) {
-                    xc[i] = P.XT + (int64_t)__shfl_sync(0xffffffffu, jl, warp * CPW + i) * P.ldx;
-                    acc[i] = 0.0;
-                }
-#pragma unroll 4
-                for (int k = 2 * lane; k < n2; k += 64) {
-                    const double2 rk = *reinterpret_cast<const double2*>(r_s + k);
-#pragma unroll
-                    for (int i = 0; i < CPW; ++i) {
-                        const double2 x = __ldg(reinterpret_cast<const double2*>(xc[i] + k));
-                        acc[i] = fma(x.x, rk.x, acc[i]);
-                        acc[i] = fma(x.y, rk.y, acc[i]);
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < CPW; ++i) {
-                    const double t = warp_sum(acc[i]);
-                    if (lane == i) part[cur * GB_ROUND + warp * CPW + i] = t;   // part[column of the window]
-                }
-                __syncthreads();
-            }
-            const int pos1 = pos0 + T;                     // start of the next window
-            // Measured at BASELINE's shapes: linear C2 (n = 1000) +25 % with the pipeline; probit C3 (n = 2000,
-            // a change -- hence a discarded window of 512 KB -- in 15 % of the windows, scoring only 5 % of a
-            // window's time) -7 %: probit keeps the plain schedule (dots by all warps, barrier, scoring).
+            // Measured at BASELINE's shapes: the pipeline below gives linear C2 (n = 1000) +25 % in the stationary
+            // regime; probit C3 (n = 2000; a change -- hence a discarded 512 KB window -- in 15 % of the windows,
+            // scoring only 5 % of a window's time) loses 7 % with it, and 9 % even with speculation switched off
+            // inside the restructured loop: probit keeps the plain schedule of round 1, verbatim.
+            // The linear sweep uses it too until two windows in a row were null: from beta = 0 nearly every
+            // window holds a change, and every speculative window would be thrown away.
             constexpr bool PIPE = !PROBIT;
-            const bool has_next = PIPE && pos1 < p;
-            if (warp == 0) {
-                // ---- score window pos0
+            if (!PIPE || null_run < 2) {
+                // ---- speculative dots of the next T columns against the current residual
                 const int jl = perm_s[min(pos0 + lane, p - 1)];
+                // warp 0 scores the window after the dots: what does not depend on them (indicator, uniform, ||X_j||^2)
+                // is fetched now, under the latency of the column loads
                 bool act = false;
                 double u_spec = 0.0, xl2_spec = 0.0;
-                if (lane < T) {
+                if (warp == 0 && lane < T) {
                     act = (mask_s[jl >> 5] >> (jl & 31)) & 1u;
                     if (!act) {
                         u_spec = u_s ? u_s[pos0 + lane] : rng_uniform(key, KIND_SPIKE_U, pos0 + lane, sweep, 0);
                         xl2_spec = P.Xl2[jl];
                     }
                 }
-                const double d = part[cur * GB_ROUND + lane];
-                bool change = false;
-                if (lane < T) {
-                    if (act) change = true;
-                    else change = !(u_spec <= kappa_of(d, xl2_spec, h));   // NaN kappa -> slab, like the reference
-                }
-                const unsigned m = __ballot_sync(0xffffffffu, change);
-                const int tstar = m ? __ffs(m) - 1 : -1;
-                if (lane == (tstar < 0 ? 0 : tstar)) {
-                    bc.tstar = tstar; bc.jstar = jl;
-                    bc.beta_old = act ? __ldcg(beta_g + jl) : 0.0;
-                    bc.dspec = d;
-                }
-                spec_skip = tstar >= 0;                    // a change: the next window's dots would be discarded
-            }
-            if (has_next && !(warp == 0 && spec_skip)) {
-                // ---- meanwhile (warp 0: afterwards): the dots of window pos1, four columns per warp; the other
-                // seven warps' loads are in flight while warp 0 scores, and warp 0's own four columns stream
-                // at the bandwidth the others leave free
-                const int jl = perm_s[min(pos1 + lane, p - 1)];
+                // each warp owns GB_ROUND / GB_NWARP whole columns: few accumulators, so many loads stay in flight
                 constexpr int CPW = GB_ROUND / GB_NWARP;
                 const double* xc[CPW];
                 double acc[CPW];
-#pragma unroll
+    #pragma unroll
                 for (int i = 0; i < CPW; ++i) {
                     xc[i] = P.XT + (int64_t)__shfl_sync(0xffffffffu, jl, warp * CPW + i) * P.ldx;
                     acc[i] = 0.0;
                 }
-#pragma unroll 4
+    #pragma unroll 4
                 for (int k = 2 * lane; k < n2; k += 64) {
                     const double2 rk = *reinterpret_cast<const double2*>(r_s + k);
-#pragma unroll
+    #pragma unroll
                     for (int i = 0; i < CPW; ++i) {
                         const double2 x = __ldg(reinterpret_cast<const double2*>(xc[i] + k));
                         acc[i] = fma(x.x, rk.x, acc[i]);
                         acc[i] = fma(x.y, rk.y, acc[i]);
                     }
                 }
-#pragma unroll
+    #pragma unroll
                 for (int i = 0; i < CPW; ++i) {
                     const double t = warp_sum(acc[i]);
-                    if (lane == i) part[(cur ^ 1) * GB_ROUND + warp * CPW + i] = t;
+                    if (lane == i) part[warp * CPW + i] = t;         // part[column of the window]
                 }
+                __syncthreads();
+                if (warp == 0) {
+                    const double d = part[lane];
+                    bool change = false;
+                    if (lane < T) {
+                        if (act) change = true;
+                        else change = !(u_spec <= kappa_of(d, xl2_spec, h));   // NaN kappa -> slab, like the reference
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, change);
+                    const int tstar = m ? __ffs(m) - 1 : -1;
+                    if (lane == (tstar < 0 ? 0 : tstar)) {
+                        bc.tstar = tstar; bc.jstar = jl;
+                        bc.beta_old = act ? __ldcg(beta_g + jl) : 0.0;
+                        bc.dspec = d;
+                    }
+                }
+                __syncthreads();
+                const int tstar_plain = bc.tstar;
+                if (tstar_plain < 0) { pos0 += T; ++null_run; have_dots = false; continue; }
+                null_run = 0;
+            } else {
+                bool spec_skip = false;                        // (warp 0 only)
+                // what the scoring of window pos0 needs besides the dots (warp 0): indicator, uniform, ||X_j||^2
+                int jl0 = 0;
+                bool act = false;
+                double u_spec = 0.0, xl2_spec = 0.0;
+                auto score_inputs = [&]() {
+                    jl0 = perm_s[min(pos0 + lane, p - 1)];
+                    if (lane < T) {
+                        act = (mask_s[jl0 >> 5] >> (jl0 & 31)) & 1u;
+                        if (!act) {
+                            u_spec = u_s ? u_s[pos0 + lane] : rng_uniform(key, KIND_SPIKE_U, pos0 + lane, sweep, 0);
+                            xl2_spec = P.Xl2[jl0];
+                        }
+                    }
+                };
+                const bool had_dots = have_dots;
+                if (!have_dots) {
+                    // ---- first window of a sweep, or the one after a change: all eight warps, four columns each;
+                    // warp 0 fetches its scoring inputs first, under the latency of the column loads
+                    if (warp == 0) score_inputs();
+                    const int jl = perm_s[min(pos0 + lane, p - 1)];
+                    constexpr int CPW = GB_ROUND / GB_NWARP;
+                    const double* xc[CPW];
+                    double acc[CPW];
+    #pragma unroll
+                    for (int i = 0; i < CPW; ++i) {
+                        xc[i] = P.XT + (int64_t)__shfl_sync(0xffffffffu, jl, warp * CPW + i) * P.ldx;
+                        acc[i] = 0.0;
+                    }
+    #pragma unroll 4
+                    for (int k = 2 * lane; k < n2; k += 64) {
+                        const double2 rk = *reinterpret_cast<const double2*>(r_s + k);
+    #pragma unroll
+                        for (int i = 0; i < CPW; ++i) {
+                            const double2 x = __ldg(reinterpret_cast<const double2*>(xc[i] + k));
+                            acc[i] = fma(x.x, rk.x, acc[i]);
+                            acc[i] = fma(x.y, rk.y, acc[i]);
+                        }
+                    }
+    #pragma unroll
+                    for (int i = 0; i < CPW; ++i) {
+                        const double t = warp_sum(acc[i]);
+                        if (lane == i) part[cur * GB_ROUND + warp * CPW + i] = t;   // part[column of the window]
+                    }
+                    __syncthreads();
+                }
+                const int pos1 = pos0 + T;                     // start of the next window
+                const bool has_next = pos1 < p;             // (this branch runs only after two null windows)
+                if (warp == 0) {
+                    // ---- score window pos0 (its dots came from the previous iteration's speculation: the other
+                    // warps are already streaming the next window, so the inputs' latency hides behind them)
+                    if (had_dots) score_inputs();
+                    const int jl = jl0;
+                    const double d = part[cur * GB_ROUND + lane];
+                    bool change = false;
+                    if (lane < T) {
+                        if (act) change = true;
+                        else change = !(u_spec <= kappa_of(d, xl2_spec, h));   // NaN kappa -> slab, like the reference
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, change);
+                    const int tstar = m ? __ffs(m) - 1 : -1;
+                    if (lane == (tstar < 0 ? 0 : tstar)) {
+                        bc.tstar = tstar; bc.jstar = jl;
+                        bc.beta_old = act ? __ldcg(beta_g + jl) : 0.0;
+                        bc.dspec = d;
+                    }
+                    spec_skip = tstar >= 0;                    // a change: the next window's dots would be discarded
+                }
+                if (has_next && !(warp == 0 && spec_skip)) {
+                    // ---- meanwhile (warp 0: afterwards): the dots of window pos1, four columns per warp; the other
+                    // seven warps' loads are in flight while warp 0 scores, and warp 0's own four columns stream
+                    // at the bandwidth the others leave free
+                    const int jl = perm_s[min(pos1 + lane, p - 1)];
+                    constexpr int CPW = GB_ROUND / GB_NWARP;
+                    const double* xc[CPW];
+                    double acc[CPW];
+    #pragma unroll
+                    for (int i = 0; i < CPW; ++i) {
+                        xc[i] = P.XT + (int64_t)__shfl_sync(0xffffffffu, jl, warp * CPW + i) * P.ldx;
+                        acc[i] = 0.0;
+                    }
+    #pragma unroll 4
+                    for (int k = 2 * lane; k < n2; k += 64) {
+                        const double2 rk = *reinterpret_cast<const double2*>(r_s + k);
+    #pragma unroll
+                        for (int i = 0; i < CPW; ++i) {
+                            const double2 x = __ldg(reinterpret_cast<const double2*>(xc[i] + k));
+                            acc[i] = fma(x.x, rk.x, acc[i]);
+                            acc[i] = fma(x.y, rk.y, acc[i]);
+                        }
+                    }
+    #pragma unroll
+                    for (int i = 0; i < CPW; ++i) {
+                        const double t = warp_sum(acc[i]);
+                        if (lane == i) part[(cur ^ 1) * GB_ROUND + warp * CPW + i] = t;
+                    }
+                }
+                __syncthreads();
+                if (bc.tstar < 0) { pos0 = pos1; cur ^= 1; have_dots = has_next; ++null_run; continue; }
+                have_dots = false;
+                null_run = 0;
             }
-            __syncthreads();
             const int tstar = bc.tstar;
-            if (tstar < 0) { pos0 = pos1; cur ^= 1; have_dots = has_next; continue; }
-            have_dots = false;
 
             // ---- apply the first changing coordinate exactly like the reference
             ++n_changes;
