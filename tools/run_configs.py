@@ -55,7 +55,7 @@ if "c2" in which:      # bench workload, then all_cand_groups on the device samp
 if "c3" in which:      # probit n=2000 p=5000, N=2000, 256 chains
     rng = np.random.default_rng(1003)
     n, p = 2000, 5000
-    X = ar1(rng, n, p, 0.5)
+    X = ar1(rng, n, p, 0.95)        # AR(1) rho = 0.95
     beta = np.zeros(p)
     beta[rng.choice(p, 25, replace=False)] = rng.standard_normal(25)
     z = (X @ beta + rng.standard_normal(n) < 0).astype(float)
