@@ -120,6 +120,8 @@ typedef struct blipgpu_streams {
 #define BLIPGPU_GRAM_KERNEL_CLASSIC 1     /* one 256-thread CTA per chain, two chains per SM, work queue           */
 #define BLIPGPU_GRAM_KERNEL_SPECIALIZED 2 /* one SM per chain: decision warps + helper warps in one CTA            */
 #define BLIPGPU_GRAM_KERNEL_CLUSTER 3     /* two SMs per chain: a 2-CTA cluster, decisions | column stream (DSMEM) */
+#define BLIPGPU_GRAM_KERNEL_BATCHED 4     /* one SM per chain: batched decisions (resolver warp + evaluators) + helper warps */
+#define BLIPGPU_GRAM_KERNEL_BATCHED_CLUSTER 5 /* the batched kernel on a 2-CTA cluster per chain                   */
 
 typedef struct blipgpu_sample_options {
     int32_t mode;            /* BLIPGPU_MODE_*                                     */

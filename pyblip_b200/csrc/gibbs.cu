@@ -13,6 +13,7 @@
 #include "gibbs_kernels.cuh"
 #include "gibbs_block.cuh"
 #include "gibbs_gram_ws.cuh"
+#include "gibbs_gram_batch.cuh"
 
 namespace {
 
@@ -271,14 +272,28 @@ static int sample_impl(blipgpu_ctx* ctx, blipgpu_design* design,
     // helper SM's load/store pipeline, behind the helpers' own column stream.
     // BLIPGPU_WS_CLUSTER=1 or gram_kernel = CLUSTER selects it.
     const bool no_ws = getenv("BLIPGPU_NO_WS") != nullptr, env_cl = getenv("BLIPGPU_WS_CLUSTER") != nullptr;
-    bool use_cl = false, use_ws = false;
+    // batched decisions (gibbs_gram_batch.cuh): the same two placements, plus the visiting order in shared memory
+    const size_t smem_wb = smem_ws + (size_t)round_up(sizeof(uint16_t) * p, 16);
+    const bool wb_fits = gram && !block && p <= 65535 && smem_wb + 12288 <= ctx->smem_optin;
+    const bool wb_possible = wb_fits && chains <= ctx->sm_count, wbc_possible = wb_fits && 2 * chains <= ctx->sm_count;
+    if ((want_kernel == BLIPGPU_GRAM_KERNEL_BATCHED && !wb_possible) || (want_kernel == BLIPGPU_GRAM_KERNEL_BATCHED_CLUSTER && !wbc_possible)) {
+        blip_set_error("sample_spikeslab: the batched gram kernels need gram mode, bsize = 1, 18 p bytes of shared "
+                       "memory and at most %d chains per device (%d for the cluster placement)", ctx->sm_count, ctx->sm_count / 2);
+        return BLIP_ERR_UNSUPPORTED;
+    }
+    bool use_cl = false, use_ws = false, use_wb = false, use_wbc = false;
     if (want_kernel == BLIPGPU_GRAM_KERNEL_CLUSTER) use_cl = true;
     else if (want_kernel == BLIPGPU_GRAM_KERNEL_SPECIALIZED) use_ws = true;
+    else if (want_kernel == BLIPGPU_GRAM_KERNEL_BATCHED) use_wb = true;
+    else if (want_kernel == BLIPGPU_GRAM_KERNEL_BATCHED_CLUSTER) use_wbc = true;
     else if (want_kernel == BLIPGPU_GRAM_KERNEL_AUTO && !no_ws) {
-        if (cl_possible && env_cl) use_cl = true;
+        const char* env_wb = getenv("BLIPGPU_WB");
+        if (env_wb && env_wb[0] == '2' && wbc_possible) use_wbc = true;
+        else if (env_wb && env_wb[0] == '1' && wb_possible) use_wb = true;
+        else if (cl_possible && env_cl) use_cl = true;
         else if (ws_possible) use_ws = true;
     }
-    const bool use_role = use_cl || use_ws;          // double-buffered scratch, no work queue
+    const bool use_role = use_cl || use_ws || use_wb || use_wbc;   // double-buffered scratch, no work queue
 
     // ---- chunking
     int S = opts && opts->chunk_sweeps > 0 ? opts->chunk_sweeps : 32;
@@ -479,6 +494,14 @@ static int sample_impl(blipgpu_ctx* ctx, blipgpu_design* design,
         kern = design->kind == BLIPGPU_DESIGN_CHANGEPOINT ? gibbs_gram_ws_kernel<BLIPGPU_DESIGN_CHANGEPOINT, true>
                                                           : gibbs_gram_ws_kernel<BLIPGPU_DESIGN_DENSE, true>;
         smem = smem_ws;
+    } else if (use_wb) {
+        kern = design->kind == BLIPGPU_DESIGN_CHANGEPOINT ? gibbs_gram_batch_kernel<BLIPGPU_DESIGN_CHANGEPOINT, false>
+                                                          : gibbs_gram_batch_kernel<BLIPGPU_DESIGN_DENSE, false>;
+        smem = smem_wb;
+    } else if (use_wbc) {
+        kern = design->kind == BLIPGPU_DESIGN_CHANGEPOINT ? gibbs_gram_batch_kernel<BLIPGPU_DESIGN_CHANGEPOINT, true>
+                                                          : gibbs_gram_batch_kernel<BLIPGPU_DESIGN_DENSE, true>;
+        smem = smem_wb;
     }
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // gram mode: persistent CTAs (as many as are resident at once) draw (chain, 8-sweep) items
@@ -639,7 +662,7 @@ static int sample_impl(blipgpu_ctx* ctx, blipgpu_design* design,
             }
             {
                 ScopedTimer timer(ctx, true);
-                if (use_cl) {
+                if (use_cl || use_wbc) {
                     // one 2-CTA cluster per chain: CTA 0 decides, CTA 1 streams the Gram columns
                     cudaLaunchConfig_t lc;
                     memset(&lc, 0, sizeof(lc));
@@ -650,7 +673,7 @@ static int sample_impl(blipgpu_ctx* ctx, blipgpu_design* design,
                     lc.attrs = at; lc.numAttrs = 1;
                     CUDA_TRY(cudaLaunchKernelEx(&lc, kern, P));
                 } else {
-                    kern<<<grid, use_ws ? WS_THREADS : GB_BLOCK, smem, st>>>(P);
+                    kern<<<grid, (use_ws || use_wb) ? WS_THREADS : GB_BLOCK, smem, st>>>(P);
                 }
                 CUDA_TRY(cudaGetLastError());
                 const double ms = timer.stop(1);

@@ -18,6 +18,7 @@ ap.add_argument("--launches", type=int, default=20)
 ap.add_argument("--mode", default="gram")
 ap.add_argument("--chunk", type=int, default=32)
 ap.add_argument("--lib", default=None, help="variant library copied over the in-tree one first")
+ap.add_argument("--kernel", type=int, default=0, help="BLIPGPU_GRAM_KERNEL_* (0 = auto)")
 ap.add_argument("--child", action="store_true")
 args = ap.parse_args()
 if not args.child:
@@ -25,7 +26,7 @@ if not args.child:
         shutil.copy(args.lib, os.path.join(ROOT, "pyblip_b200", "_C", "libblipgpu.so"))
     env = dict(os.environ, BLIPGPU_LAUNCH_LOG="1")
     res = subprocess.run([sys.executable, __file__, "--child", "--chains", str(args.chains), "--launches",
-                          str(args.launches), "--mode", args.mode, "--chunk", str(args.chunk)],
+                          str(args.launches), "--mode", args.mode, "--chunk", str(args.chunk), "--kernel", str(args.kernel)],
                          env=env, capture_output=True, text=True)
     ms = [float(m.group(2)) / (int(m.group(1)) / 32.0) for m in
           re.finditer(r"launch sweeps \d+\.\.\d+ grid \d+: ([0-9.]+) ms", res.stderr) for m in [m]] if False else []
@@ -36,7 +37,10 @@ if not args.child:
         print(res.stdout[-2000:], res.stderr[-2000:])
         sys.exit(1)
     med = per32[len(per32) // 2]
-    print(f"{args.lib or 'in-tree'}: chains {args.chains} chunk {args.chunk} grid {rows[-1][2]}: median {med:.3f} ms per 32 sweeps "
+    for line in res.stdout.splitlines():
+        if "|" in line:
+            print(line)
+    print(f"{args.lib or 'in-tree'} kernel {args.kernel}: chains {args.chains} chunk {args.chunk} grid {rows[-1][2]}: median {med:.3f} ms per 32 sweeps "
           f"(min {per32[0]:.3f}, max {per32[-1]:.3f}, {len(per32)} launches)")
     sys.exit(0)
 
@@ -51,5 +55,5 @@ if mode == _lib.MODE_GRAM:
     design.build_gram()
 cfg = LinearSpikeSlab(X, y)._config()
 smp = _lib.sample_spikeslab(design, cfg, y=y, chains=args.chains, n_keep=args.chunk * args.launches, burn=96,
-                            seed=7, mode=mode, chunk_sweeps=args.chunk)
+                            seed=7, mode=mode, chunk_sweeps=args.chunk, gram_kernel=args.kernel)
 smp.close()
