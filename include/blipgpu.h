@@ -122,6 +122,7 @@ typedef struct blipgpu_streams {
 #define BLIPGPU_GRAM_KERNEL_CLUSTER 3     /* two SMs per chain: a 2-CTA cluster, decisions | column stream (DSMEM) */
 #define BLIPGPU_GRAM_KERNEL_BATCHED 4     /* one SM per chain: batched decisions (resolver warp + evaluators) + helper warps */
 #define BLIPGPU_GRAM_KERNEL_BATCHED_CLUSTER 5 /* the batched kernel on a 2-CTA cluster per chain                   */
+#define BLIPGPU_GRAM_KERNEL_STREAM 6      /* one SM per chain: resolver warp + checked column stream (stationary regime) */
 
 typedef struct blipgpu_sample_options {
     int32_t mode;            /* BLIPGPU_MODE_*                                     */

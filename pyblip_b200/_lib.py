@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(HERE, "_C", "libblipgpu.so")
 MODE_AUTO, MODE_RESIDUAL, MODE_GRAM = 0, 1, 2
 GRAM_KERNEL_AUTO, GRAM_KERNEL_CLASSIC, GRAM_KERNEL_SPECIALIZED, GRAM_KERNEL_CLUSTER = 0, 1, 2, 3
 GRAM_KERNEL_BATCHED, GRAM_KERNEL_BATCHED_CLUSTER = 4, 5
+GRAM_KERNEL_STREAM = 6
 DESIGN_DENSE, DESIGN_CHANGEPOINT = 0, 1
 DTYPE_F64, DTYPE_U8 = 0, 1
 ERR_NUMERIC, ERR_NOMEM, ERR_ARG, ERR_UNSUPPORTED = 4, 3, 2, 5

@@ -296,10 +296,13 @@ __device__ __forceinline__ int warp_sum_int(int v)
 struct SyncCta {
     static __device__ __forceinline__ void sync() { __syncthreads(); }
     static __device__ __forceinline__ int nwarp() { return (blockDim.x + 31) >> 5; }
+    static __device__ __forceinline__ int tid() { return threadIdx.x; }
 };
-template <int ID, int NT> struct SyncNamed {
+// the sub-group is threads [T0, T0 + NT) of the CTA; tid() is the index within it
+template <int ID, int NT, int T0 = 0> struct SyncNamed {
     static __device__ __forceinline__ void sync() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(NT) : "memory"); }
     static __device__ __forceinline__ int nwarp() { return NT / 32; }
+    static __device__ __forceinline__ int tid() { return (int)threadIdx.x - T0; }
 };
 
 // Sum over the group SY synchronises (default: the whole block); result returned to every thread.
@@ -307,7 +310,7 @@ template <int ID, int NT> struct SyncNamed {
 template <class SY = SyncCta>
 __device__ __forceinline__ double block_sum(double v, double* scratch)
 {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = SY::nwarp();
+    const int lane = SY::tid() & 31, warp = SY::tid() >> 5, nwarp = SY::nwarp();
     v = warp_sum(v);
     if (lane == 0) scratch[warp] = v;
     SY::sync();

@@ -14,6 +14,7 @@
 #include "gibbs_block.cuh"
 #include "gibbs_gram_ws.cuh"
 #include "gibbs_gram_batch.cuh"
+#include "gibbs_gram_stream.cuh"
 
 namespace {
 
@@ -281,6 +282,15 @@ static int sample_impl(blipgpu_ctx* ctx, blipgpu_design* design,
                        "memory and at most %d chains per device (%d for the cluster placement)", ctx->sm_count, ctx->sm_count / 2);
         return BLIP_ERR_UNSUPPORTED;
     }
+    // checked column stream (gibbs_gram_stream.cuh): q twice, the tracked Gram sub-matrix, the resolver's snapshots
+    const size_t smem_st = st_smem_bytes(p2, words);
+    const bool st_fits = gram && !block && smem_st + sizeof(StCtl) + sizeof(StPass) + 1024 <= ctx->smem_optin;
+    const bool st_possible = st_fits && chains <= ctx->sm_count;
+    if (want_kernel == BLIPGPU_GRAM_KERNEL_STREAM && !st_possible) {
+        blip_set_error("sample_spikeslab: the column-stream gram kernel needs gram mode, bsize = 1, %zu bytes of shared memory "
+                       "per chain (device allows %zu) and at most %d chains per device", smem_st + sizeof(StCtl) + sizeof(StPass), ctx->smem_optin, ctx->sm_count);
+        return BLIP_ERR_UNSUPPORTED;
+    }
     bool use_cl = false, use_ws = false, use_wb = false, use_wbc = false;
     if (want_kernel == BLIPGPU_GRAM_KERNEL_CLUSTER) use_cl = true;
     else if (want_kernel == BLIPGPU_GRAM_KERNEL_SPECIALIZED) use_ws = true;
@@ -293,7 +303,14 @@ static int sample_impl(blipgpu_ctx* ctx, blipgpu_design* design,
         else if (cl_possible && env_cl) use_cl = true;
         else if (ws_possible) use_ws = true;
     }
-    const bool use_role = use_cl || use_ws || use_wb || use_wbc;   // double-buffered scratch, no work queue
+    // The column-stream kernel is a stationary-regime kernel: forced by gram_kernel = STREAM, or taking over from the
+    // role-specialised kernel launch by launch, once a launch has seen few enough changes per sweep for the resolver
+    // to track them (chain state crosses launches in global memory; all kernels agree bit for bit)
+    const bool st_forced = want_kernel == BLIPGPU_GRAM_KERNEL_STREAM;
+    // (AUTO hands over only on request, BLIPGPU_STREAM=1: at C2 the column-stream kernel measures 12.4 ms per 32 sweeps of
+    // 64 chains against 5.7 ms for the role-specialised kernel)
+    const bool st_auto = use_ws && st_possible && 2 * chains <= ctx->sm_count && want_kernel == BLIPGPU_GRAM_KERNEL_AUTO && getenv("BLIPGPU_STREAM") != nullptr;
+    const bool use_role = use_cl || use_ws || use_wb || use_wbc || st_forced;   // double-buffered scratch, no work queue
 
     // ---- chunking
     int S = opts && opts->chunk_sweeps > 0 ? opts->chunk_sweeps : 32;
@@ -327,7 +344,7 @@ static int sample_impl(blipgpu_ctx* ctx, blipgpu_design* design,
 
     // ---- allocate
     DevBuf d_beta, d_r, d_mu, d_ylat, d_q, d_h, d_mask, d_ev, d_q0, d_y, d_z, d_ovf, d_scrL, d_scrZ, d_scrP, d_queue;
-    DevBuf d_perm[2], d_u, d_zn, d_ig, d_p0, d_g;
+    DevBuf d_perm[2], d_u, d_zn, d_ig, d_p0, d_g, d_scrI;
     DevBuf snap_beta, snap_r, snap_mu, snap_ylat, snap_q, snap_h, snap_mask, snap_ev;
     BLIP_TRY(d_beta.alloc(sizeof(double) * chains * p));
     BLIP_TRY(d_h.alloc(sizeof(double) * chains * GB_HS));
@@ -339,6 +356,7 @@ static int sample_impl(blipgpu_ctx* ctx, blipgpu_design* design,
         BLIP_TRY(d_q0.alloc(sizeof(double) * p));
         BLIP_TRY(d_queue.alloc(sizeof(int) * (chains + 1)));
         BLIP_TRY(d_scrL.alloc(sizeof(float) * chains * p * (use_role ? 2 : 1))); BLIP_TRY(d_scrZ.alloc(sizeof(double2) * chains * p));
+        if (st_forced || st_auto) BLIP_TRY(d_scrI.alloc(sizeof(int) * 2 * chains * p2));
     } else {
         BLIP_TRY(d_r.alloc(sizeof(double) * chains * n2)); BLIP_TRY(snap_r.alloc(d_r.bytes));
         if (probit) {
@@ -408,7 +426,7 @@ static int sample_impl(blipgpu_ctx* ctx, blipgpu_design* design,
     P.mask = d_mask.as<uint32_t>(); P.events = d_ev.as<uint32_t>();
     P.q0 = d_q0.as<double>(); P.zlab = d_z.as<int32_t>();
     P.scrL = d_scrL.as<float>(); P.scrZ = d_scrZ.as<double2>();
-    P.scrP = d_scrP.ptr; P.scr_stride = chains * p;
+    P.scrP = d_scrP.ptr; P.scr_stride = chains * p; P.scrI = d_scrI.as<int>();
     P.queue = d_queue.as<int>(); P.progress = d_queue.as<int>() + 1; P.n_chains = (int)chains;
     P.k0 = (uint32_t)seed; P.k1 = (uint32_t)(seed >> 32); P.chain_offset = (uint32_t)chain_offset;
     P.nprop = nprop; P.burn = (int)burn; P.n_keep = (int)n_keep;
@@ -504,6 +522,13 @@ static int sample_impl(blipgpu_ctx* ctx, blipgpu_design* design,
         smem = smem_wb;
     }
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    void (*kern_st)(SweepParams) = design->kind == BLIPGPU_DESIGN_CHANGEPOINT ? gibbs_gram_stream_kernel<BLIPGPU_DESIGN_CHANGEPOINT>
+                                                                              : gibbs_gram_stream_kernel<BLIPGPU_DESIGN_DENSE>;
+    if (st_forced || st_auto) CUDA_TRY(cudaFuncSetAttribute(kern_st, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_st));
+    // AUTO: changes per chain-sweep (mean, max over chains) of the previous launch decide which kernel runs the next one
+    bool st_now = st_forced;
+    std::vector<double> hs_prev, hs_now;
+    const double st_mean_max = getenv("BLIPGPU_STREAM_MEAN") ? atof(getenv("BLIPGPU_STREAM_MEAN")) : 90.0;
     // gram mode: persistent CTAs (as many as are resident at once) draw (chain, 8-sweep) items
     // from a queue; with q in global memory (huge p) a chain stays on one CTA for the launch.
     int resident = 0;
@@ -672,6 +697,16 @@ static int sample_impl(blipgpu_ctx* ctx, blipgpu_design* design,
                     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
                     lc.attrs = at; lc.numAttrs = 1;
                     CUDA_TRY(cudaLaunchKernelEx(&lc, kern, P));
+                } else if (st_now) {
+                    // one 2-CTA cluster per chain: CTA 0 resolves and keeps the books, CTA 1 owns q and streams
+                    cudaLaunchConfig_t lc;
+                    memset(&lc, 0, sizeof(lc));
+                    lc.gridDim = dim3(2 * grid); lc.blockDim = dim3(ST_THREADS); lc.dynamicSmemBytes = smem_st; lc.stream = st;
+                    cudaLaunchAttribute at[1];
+                    at[0].id = cudaLaunchAttributeClusterDimension;
+                    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                    lc.attrs = at; lc.numAttrs = 1;
+                    CUDA_TRY(cudaLaunchKernelEx(&lc, kern_st, P));
                 } else {
                     kern<<<grid, (use_ws || use_wb) ? WS_THREADS : GB_BLOCK, smem, st>>>(P);
                 }
@@ -679,14 +714,18 @@ static int sample_impl(blipgpu_ctx* ctx, blipgpu_design* design,
                 const double ms = timer.stop(1);
                 smp->sweep_ms += ms;
                 smp->sweep_launches += 1;
-                if (launch_log) fprintf(stderr, "[blipgpu] launch sweeps %lld..%lld grid %u: %.3f ms\n",
-                                        (long long)sweep0, (long long)(sweep0 + Sc), grid, ms);
+                if (launch_log) fprintf(stderr, "[blipgpu] launch sweeps %lld..%lld grid %u: %.3f ms%s\n",
+                                        (long long)sweep0, (long long)(sweep0 + Sc), grid, ms, st_now ? " (stream)" : "");
             }
             int ovf = 0, nerr = 0;
             unsigned long long used = 0;
             CUDA_TRY(cudaMemcpyAsync(&ovf, d_ovf.ptr, sizeof(int), cudaMemcpyDeviceToHost, st));
             CUDA_TRY(cudaMemcpyAsync(&nerr, d_numerr.ptr, sizeof(int), cudaMemcpyDeviceToHost, st));
             CUDA_TRY(cudaMemcpyAsync(&used, smp->arena_used, sizeof(used), cudaMemcpyDeviceToHost, st));
+            if (st_auto) {
+                hs_now.resize((size_t)chains * GB_HS);
+                CUDA_TRY(cudaMemcpyAsync(hs_now.data(), d_h.ptr, d_h.bytes, cudaMemcpyDeviceToHost, st));
+            }
             CUDA_TRY(cudaStreamSynchronize(st));
             {
                 if (nerr == 1) {
@@ -698,6 +737,15 @@ static int sample_impl(blipgpu_ctx* ctx, blipgpu_design* design,
                                    "(degenerate data or hyper-priors)", (long long)sweep0, (long long)(sweep0 + Sc));
                     return BLIP_ERR_NUMERIC;
                 }
+            }
+            if (!ovf && st_auto) {
+                double sum = 0.0, mx = 0.0;
+                for (int64_t cc = 0; cc < chains; ++cc) {
+                    const double d = hs_now[(size_t)(GB_HS * cc + 4)] - (hs_prev.empty() ? 0.0 : hs_prev[(size_t)(GB_HS * cc + 4)]);
+                    sum += d; mx = std::max(mx, d);
+                }
+                hs_prev = hs_now;
+                st_now = sum / (double)(chains * Sc) <= st_mean_max && mx / (double)Sc <= 1.5 * st_mean_max;
             }
             if (!ovf) {
                 max_chunk_use = std::max<int64_t>(max_chunk_use, (int64_t)(used - used_before));

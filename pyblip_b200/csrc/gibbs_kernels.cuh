@@ -73,6 +73,7 @@ struct SweepParams {
     void* scrP;                // gram mode, keyed visiting order: [chains][p] uint16/int32, rewritten every sweep
     float* scrL;               // gram mode: [chains][p]  logit of the spike uniform per position (NaN = exact path)
     double2* scrZ;             // gram mode: [chains][p]  (sqrt(post_var) * z, post_var) at positions of active coordinates
+    int* scrI;                 // column-stream gram kernel: [2][chains][p2]  position of every coordinate in the visiting order
 };
 
 struct PermView {           // visiting order of one (chain, sweep)
@@ -114,7 +115,7 @@ __device__ __forceinline__ double slab_draw(double XjTr, double xl2, const Hyper
 template <class SY = SyncCta>
 __device__ __forceinline__ int block_excl_scan(int v, int* s_warp, int* total)
 {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = SY::tid() & 31, warp = SY::tid() >> 5;
     int incl = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -158,7 +159,7 @@ __device__ inline void sweep_epilogue(const SweepParams& P, SweepShared* sh, con
                                       const double* beta_g, double* scratch, const RngKey& key,
                                       int c, int s, double ssr, const double* y_s, bool latents_dirty)
 {
-    const int tid = threadIdx.x;
+    const int tid = SY::tid();
     const int sweep = P.sweep0 + s;
     // number of active coordinates and sum of squares (_update_hparams.pyx:52-54, 85-88)
     int cnt = 0;

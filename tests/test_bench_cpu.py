@@ -33,4 +33,4 @@ def test_workload_config_names_the_baseline_configuration():
     cfg = bench.workload_config(args)
     assert "configs[1]" in cfg["workload"] and cfg["chains"] == 512 and cfg["sweeps_per_step"] == 5100
     weak = bench.workload_config(args, chains=1024)
-    assert "weak" in weak["workload"] and weak["chains"] == 1024
+    assert "1024 chains in total" in weak["workload"] and weak["chains"] == 1024
