@@ -16,6 +16,7 @@
 #include <new>
 #include <vector>
 #include "internal.cuh"
+#include "pairs_tc.cuh"
 
 namespace {
 
@@ -844,11 +845,48 @@ extern "C" int blipgpu_count_sequential(blipgpu_bits* b, int32_t max_size, int64
     });
 }
 
+static void ensure_colbits(blipgpu_bits* b, cudaStream_t st);
+
+// Tensor-core path (pairs_tc.cuh): u8 x u8 -> s32 GEMM over the column-major bit matrix, any number of columns.
+// Chosen from 512 columns up (below that the scalar kernel's work is a few dozen word pairs); BLIPGPU_PAIRS_TC=1
+// forces it, BLIPGPU_PAIRS_TC=0 forbids it.
+static int count_pairs_tc(blipgpu_bits* b, int64_t* pair_counts, int32_t out_is_device)
+{
+    cudaStream_t st = b->ctx->stream;
+    const int64_t C = 32 * b->words;
+    const int n_mt = (int)((C + PT_M - 1) / PT_M), n_nt = (int)((C + PT_N - 1) / PT_N);
+    int64_t tiles = 0;
+    for (int mt = 0; mt < n_mt; ++mt) tiles += n_nt - (mt * PT_M) / PT_N;
+    const int64_t n_octs = b->NW / 8;
+    int64_t ksplit = std::max<int64_t>(1, std::min<int64_t>(n_octs, (2LL * b->ctx->sm_count + tiles - 1) / tiles));
+    const int64_t octs_per_split = (n_octs + ksplit - 1) / ksplit;
+    ksplit = (n_octs + octs_per_split - 1) / octs_per_split;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(count_pairs_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM) != cudaSuccess) {
+            blip_set_error("count_pairs: cannot reserve %d bytes of shared memory", PT_SMEM); return BLIP_ERR_CUDA;
+        }
+        attr_set = true;
+    }
+    return with_output(b->ctx, b->p * b->p, pair_counts, out_is_device, [&](unsigned long long* dev) {
+        count_pairs_tc_kernel<<<dim3((unsigned)tiles, (unsigned)ksplit), PT_THREADS, PT_SMEM, st>>>(
+            b->colbits, b->NW, C, b->p, n_nt, octs_per_split, n_octs, dev);
+    });
+}
+
 extern "C" int blipgpu_count_pairs(blipgpu_bits* b, int64_t* pair_counts, int32_t out_is_device)
 {
     if (!b || !pair_counts) { blip_set_error("count_pairs: bad arguments"); return BLIP_ERR_ARG; }
     BLIP_TRY(blip_ctx_activate(b->ctx));
-    if (b->p > 16384) { blip_set_error("count_pairs: at most 16384 columns (select the relevant ones first)"); return BLIP_ERR_UNSUPPORTED; }
+    {
+        const char* env = getenv("BLIPGPU_PAIRS_TC");
+        const bool want_tc = env ? env[0] == '1' : b->p >= 512;
+        if (want_tc && b->N > 0 && b->p > 0) {
+            ensure_colbits(b, b->ctx->stream);
+            if (b->colbits) return count_pairs_tc(b, pair_counts, out_is_device);
+        }
+    }
+    if (b->p > 16384) { blip_set_error("count_pairs: more than 16384 columns need the tensor-core path (column-major copy could not be allocated)"); return BLIP_ERR_UNSUPPORTED; }
     const int64_t npair = b->words * (b->words + 1) / 2;
     const int64_t rpb = pick_rows_per_block(b->N, npair, b->ctx->sm_count);
     const unsigned chunks = (unsigned)std::max<int64_t>(1, (b->N + rpb - 1) / rpb);

@@ -189,3 +189,31 @@ def test_column_major_copy_gives_the_same_counts(gpu):
         assert bits.count_false_rows(sel) == want_false(sel)                      # column-major scan
         assert bits.count_false_rows([[p // 2]]) == N                             # an all-zero column
         bits.close()
+
+
+def test_pair_counts_on_the_tensor_cores(gpu, monkeypatch):
+    """The tcgen05 integer GEMM (pairs_tc.cuh) gives exactly S^T S: ragged row counts (K padding), column counts
+    that end inside a 128 x 256 tile, dense and empty columns, several k-splits; it is the default from 512 columns
+    up, can be forced for small sets, and agrees with the scalar kernel entry for entry."""
+    from pyblip_b200 import _lib
+    rng = np.random.default_rng(23)
+    cases = [(1, 1, 0.5), (33, 5, 0.3), (777, 130, 0.2), (5000, 700, 0.03), (40013, 1031, 0.01), (100, 2050, 0.2),
+             (300001, 513, 0.02)]
+    for N, p, dens in cases:
+        S = rng.random((N, p)) < dens
+        if p > 3:
+            S[:, 2] = True
+            S[:, 3] = False
+        Si = S.astype(np.float64)                      # exact below 2^53, and BLAS is quick
+        want = (Si.T @ Si).astype(np.int64)
+        bits = _lib.Bits.from_dense(S)
+        monkeypatch.setenv("BLIPGPU_PAIRS_TC", "1")
+        pc = bits.count_pairs()
+        assert np.array_equal(pc, want), (N, p)
+        if p <= 1031:
+            monkeypatch.setenv("BLIPGPU_PAIRS_TC", "0")
+            assert np.array_equal(bits.count_pairs(), want), (N, p)
+        monkeypatch.delenv("BLIPGPU_PAIRS_TC")
+        if p >= 512:
+            assert np.array_equal(bits.count_pairs(), want), (N, p)
+        bits.close()
