@@ -122,7 +122,9 @@ typedef struct blipgpu_streams {
 #define BLIPGPU_GRAM_KERNEL_CLUSTER 3     /* two SMs per chain: a 2-CTA cluster, decisions | column stream (DSMEM) */
 #define BLIPGPU_GRAM_KERNEL_BATCHED 4     /* one SM per chain: batched decisions (resolver warp + evaluators) + helper warps */
 #define BLIPGPU_GRAM_KERNEL_BATCHED_CLUSTER 5 /* the batched kernel on a 2-CTA cluster per chain                   */
-#define BLIPGPU_GRAM_KERNEL_STREAM 6      /* one SM per chain: resolver warp + checked column stream (stationary regime) */
+#define BLIPGPU_GRAM_KERNEL_STREAM 6      /* two SMs per chain: resolver warp | checked column stream (stationary regime) */
+#define BLIPGPU_GRAM_KERNEL_SPECIALIZED2 7 /* SPECIALIZED with two tracked positions per thread and Gram entries requested a change ahead */
+#define BLIPGPU_GRAM_KERNEL_SPECIALIZED2_CLUSTER 8 /* the same on a 2-CTA cluster: q on both SMs, a control warp does the fences */
 
 typedef struct blipgpu_sample_options {
     int32_t mode;            /* BLIPGPU_MODE_*                                     */

@@ -18,10 +18,12 @@ MODE_AUTO, MODE_RESIDUAL, MODE_GRAM = 0, 1, 2
 GRAM_KERNEL_AUTO, GRAM_KERNEL_CLASSIC, GRAM_KERNEL_SPECIALIZED, GRAM_KERNEL_CLUSTER = 0, 1, 2, 3
 GRAM_KERNEL_BATCHED, GRAM_KERNEL_BATCHED_CLUSTER = 4, 5
 GRAM_KERNEL_STREAM = 6
+GRAM_KERNEL_SPECIALIZED2 = 7
+GRAM_KERNEL_SPECIALIZED2_CLUSTER = 8
 DESIGN_DENSE, DESIGN_CHANGEPOINT = 0, 1
 DTYPE_F64, DTYPE_U8 = 0, 1
 ERR_NUMERIC, ERR_NOMEM, ERR_ARG, ERR_UNSUPPORTED = 4, 3, 2, 5
-COUNT_PAIRS_MAX_P = 16384     # blipgpu_count_pairs: columns per call
+COUNT_PAIRS_MAX_P = 32768     # blipgpu_count_pairs: columns per call (tensor-core path; the scalar kernel stops at 16384)
 
 # every symbol include/blipgpu.h declares (checked by tests/test_abi.py)
 SYMBOLS = [

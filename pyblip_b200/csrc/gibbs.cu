@@ -15,6 +15,7 @@
 #include "gibbs_gram_ws.cuh"
 #include "gibbs_gram_batch.cuh"
 #include "gibbs_gram_stream.cuh"
+#include "gibbs_gram_ws2.cuh"
 
 namespace {
 
@@ -291,8 +292,20 @@ static int sample_impl(blipgpu_ctx* ctx, blipgpu_design* design,
                        "per chain (device allows %zu) and at most %d chains per device", smem_st + sizeof(StCtl) + sizeof(StPass), ctx->smem_optin, ctx->sm_count);
         return BLIP_ERR_UNSUPPORTED;
     }
-    bool use_cl = false, use_ws = false, use_wb = false, use_wbc = false;
-    if (want_kernel == BLIPGPU_GRAM_KERNEL_CLUSTER) use_cl = true;
+    if (want_kernel == BLIPGPU_GRAM_KERNEL_SPECIALIZED2_CLUSTER && !cl_possible) {
+        blip_set_error("sample_spikeslab: the 2-CTA cluster placement needs gram mode, bsize = 1, 16 p bytes of shared "
+                       "memory and at most %d chains per device", ctx->sm_count / 2);
+        return BLIP_ERR_UNSUPPORTED;
+    }
+    if (want_kernel == BLIPGPU_GRAM_KERNEL_SPECIALIZED2 && !ws_possible) {
+        blip_set_error("sample_spikeslab: the role-specialised gram kernels need gram mode, bsize = 1, 16 p bytes of shared "
+                       "memory and at most %d chains per device", ctx->sm_count);
+        return BLIP_ERR_UNSUPPORTED;
+    }
+    bool use_cl = false, use_ws = false, use_wb = false, use_wbc = false, use_ws2 = false, use_ws2c = false;
+    if (want_kernel == BLIPGPU_GRAM_KERNEL_SPECIALIZED2) { use_ws = true; use_ws2 = true; }
+    else if (want_kernel == BLIPGPU_GRAM_KERNEL_SPECIALIZED2_CLUSTER) use_ws2c = true;
+    else if (want_kernel == BLIPGPU_GRAM_KERNEL_CLUSTER) use_cl = true;
     else if (want_kernel == BLIPGPU_GRAM_KERNEL_SPECIALIZED) use_ws = true;
     else if (want_kernel == BLIPGPU_GRAM_KERNEL_BATCHED) use_wb = true;
     else if (want_kernel == BLIPGPU_GRAM_KERNEL_BATCHED_CLUSTER) use_wbc = true;
@@ -301,7 +314,8 @@ static int sample_impl(blipgpu_ctx* ctx, blipgpu_design* design,
         if (env_wb && env_wb[0] == '2' && wbc_possible) use_wbc = true;
         else if (env_wb && env_wb[0] == '1' && wb_possible) use_wb = true;
         else if (cl_possible && env_cl) use_cl = true;
-        else if (ws_possible) use_ws = true;
+        else if (cl_possible && getenv("BLIPGPU_WS2C") != nullptr) use_ws2c = true;
+        else if (ws_possible) { use_ws = true; use_ws2 = getenv("BLIPGPU_WS2") != nullptr; }
     }
     // The column-stream kernel is a stationary-regime kernel: forced by gram_kernel = STREAM, or taking over from the
     // role-specialised kernel launch by launch, once a launch has seen few enough changes per sweep for the resolver
@@ -310,7 +324,7 @@ static int sample_impl(blipgpu_ctx* ctx, blipgpu_design* design,
     // (AUTO hands over only on request, BLIPGPU_STREAM=1: at C2 the column-stream kernel measures 12.4 ms per 32 sweeps of
     // 64 chains against 5.7 ms for the role-specialised kernel)
     const bool st_auto = use_ws && st_possible && 2 * chains <= ctx->sm_count && want_kernel == BLIPGPU_GRAM_KERNEL_AUTO && getenv("BLIPGPU_STREAM") != nullptr;
-    const bool use_role = use_cl || use_ws || use_wb || use_wbc || st_forced;   // double-buffered scratch, no work queue
+    const bool use_role = use_cl || use_ws || use_wb || use_wbc || use_ws2c || st_forced;   // double-buffered scratch, no work queue
 
     // ---- chunking
     int S = opts && opts->chunk_sweeps > 0 ? opts->chunk_sweeps : 32;
@@ -504,7 +518,12 @@ static int sample_impl(blipgpu_ctx* ctx, blipgpu_design* design,
         kern = qsmem ? gibbs_gram_kernel<BLIPGPU_DESIGN_CHANGEPOINT, true> : gibbs_gram_kernel<BLIPGPU_DESIGN_CHANGEPOINT, false>;
     else
         kern = qsmem ? gibbs_gram_kernel<BLIPGPU_DESIGN_DENSE, true> : gibbs_gram_kernel<BLIPGPU_DESIGN_DENSE, false>;
-    if (use_ws) {
+    if (use_ws2 || use_ws2c) {
+        kern = design->kind == BLIPGPU_DESIGN_CHANGEPOINT
+                   ? (use_ws2c ? gibbs_gram_ws2_kernel<BLIPGPU_DESIGN_CHANGEPOINT, true> : gibbs_gram_ws2_kernel<BLIPGPU_DESIGN_CHANGEPOINT, false>)
+                   : (use_ws2c ? gibbs_gram_ws2_kernel<BLIPGPU_DESIGN_DENSE, true> : gibbs_gram_ws2_kernel<BLIPGPU_DESIGN_DENSE, false>);
+        smem = smem_ws;
+    } else if (use_ws) {
         kern = design->kind == BLIPGPU_DESIGN_CHANGEPOINT ? gibbs_gram_ws_kernel<BLIPGPU_DESIGN_CHANGEPOINT, false>
                                                           : gibbs_gram_ws_kernel<BLIPGPU_DESIGN_DENSE, false>;
         smem = smem_ws;
@@ -687,7 +706,17 @@ static int sample_impl(blipgpu_ctx* ctx, blipgpu_design* design,
             }
             {
                 ScopedTimer timer(ctx, true);
-                if (use_cl || use_wbc) {
+                if (use_ws2c) {
+                    // one 2-CTA cluster per chain: CTA 0 = decision warps + control warp, CTA 1 = helpers; q on both
+                    cudaLaunchConfig_t lc;
+                    memset(&lc, 0, sizeof(lc));
+                    lc.gridDim = dim3(2 * grid); lc.blockDim = dim3(WS2_D_THREADS); lc.dynamicSmemBytes = smem; lc.stream = st;
+                    cudaLaunchAttribute at[1];
+                    at[0].id = cudaLaunchAttributeClusterDimension;
+                    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                    lc.attrs = at; lc.numAttrs = 1;
+                    CUDA_TRY(cudaLaunchKernelEx(&lc, kern, P));
+                } else if (use_cl || use_wbc) {
                     // one 2-CTA cluster per chain: CTA 0 decides, CTA 1 streams the Gram columns
                     cudaLaunchConfig_t lc;
                     memset(&lc, 0, sizeof(lc));

@@ -90,7 +90,8 @@ template <bool CLUSTER> __device__ __forceinline__ void ws_fence()
 // ~500 cycles per bulk copy whatever its size, 3x slower than these loads; left out.)
 template <int DESIGN>
 __device__ __forceinline__ void ws_flush(const SweepParams& P, const double* __restrict__ src, double* __restrict__ dst,
-                                         const int (&pj)[WS_PEND], const double (&pd)[WS_PEND], int n, int ftid)
+                                         const int (&pj)[WS_PEND], const double (&pd)[WS_PEND], int n, int ftid,
+                                         double* dst2 = nullptr)
 {
     // A rotating register pipeline of WS_SLOTS groups, one 16-byte load per column and group: every
     // step applies the oldest group and re-issues its loads WS_SLOTS steps ahead, so the helpers feed
@@ -111,6 +112,7 @@ __device__ __forceinline__ void ws_flush(const SweepParams& P, const double* __r
             for (int k = 0; k < WS_PEND; ++k)
                 if (k < n) { qq.x = fma(-pd[k], gg[k].x, qq.x); qq.y = fma(-pd[k], gg[k].y, qq.y); }
             *reinterpret_cast<double2*>(dst + kk) = qq;
+            if (dst2) *reinterpret_cast<double2*>(dst2 + kk) = qq;
         }
     };
     int k0 = 2 * ftid;
@@ -129,7 +131,8 @@ __device__ __forceinline__ void ws_flush(const SweepParams& P, const double* __r
 // helper role: `mine` is polled, `peer` is D's copy of the control words; qbuf is local
 // =================================================================================================
 template <int DESIGN, bool CLUSTER>
-__device__ __forceinline__ void ws_helper_role(const SweepParams& P, int c, int ftid, double* qbuf, WsCtl* mine, WsCtl* peer)
+__device__ __forceinline__ void ws_helper_role(const SweepParams& P, int c, int ftid, double* qbuf, WsCtl* mine, WsCtl* peer,
+                                               double* q_peer = nullptr)
 {
     const int p = P.p, p2 = P.p2, s_end = P.S;
     const RngKey key = { P.k0, P.k1, P.chain_offset + (uint32_t)c };
@@ -162,7 +165,10 @@ __device__ __forceinline__ void ws_helper_role(const SweepParams& P, int c, int 
                 pj[k] = k < n ? mine->ring_j[slot] : 0;
                 pd[k] = k < n ? mine->ring_d[slot] : 0.0;
             }
-            ws_flush<DESIGN>(P, qbuf + (size_t)(epoch & 1) * p2, qbuf + (size_t)((epoch + 1) & 1) * p2, pj, pd, n, ftid);
+            // (q_peer: a second copy of q in the decision CTA's shared memory, gibbs_gram_ws2.cuh -- the new buffer is
+            //  pushed into it with distributed-shared-memory stores, ordered before `pub` by the fence below)
+            ws_flush<DESIGN>(P, qbuf + (size_t)(epoch & 1) * p2, qbuf + (size_t)((epoch + 1) & 1) * p2, pj, pd, n, ftid,
+                             q_peer ? q_peer + (size_t)((epoch + 1) & 1) * p2 : nullptr);
             applied += n;
             ++epoch;
             SyncF::sync();

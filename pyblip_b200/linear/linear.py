@@ -91,7 +91,10 @@ class _SpikeSlabBase:
             Accepted for compatibility and ignored: every chain of this rank runs
             in one device launch; under ``torchrun`` chains are sharded over ranks.
         bsize : int
-            Maximum block size within gibbs sampling. Default: 1.
+            Maximum block size within gibbs sampling. Default: 1.  The device block
+            sampler scores all ``2**bsize`` sub-models of a block at once and supports
+            ``bsize <= 8`` (the reference documents 2-5); a larger value raises
+            ``NotImplementedError`` instead of falling back to another sampler.
         max_signals_per_block : int
             Maximum number of signals allowed per block (``bsize > 1`` only).
         seed : int, keyword-only

@@ -35,7 +35,7 @@ def _same(a, b):
     assert a[2] == b[2] and a[3] == b[3]
 
 
-@pytest.mark.parametrize("kernel", [2, 3])
+@pytest.mark.parametrize("kernel", [2, 3, 7, 8])
 @pytest.mark.parametrize("name", util.LINEAR_CASES)
 def test_specialised_kernel_matches_reference_goldens(gpu, name, kernel):
     """The reference's recorded runs (injected permutations, uniforms, normals, hyper variates)."""
@@ -76,11 +76,36 @@ def test_specialised_equals_classic_bit_for_bit(gpu):
         kw = dict(y=y, chains=chains, chain_offset=3, n_keep=sweeps - 5, burn=5, seed=99, chunk_sweeps=chunk,
                   gram_refresh=refresh)
         a = _run(design, cfg, _lib.GRAM_KERNEL_CLASSIC, **kw)
-        for kernel in (_lib.GRAM_KERNEL_SPECIALIZED, _lib.GRAM_KERNEL_CLUSTER):
+        for kernel in (_lib.GRAM_KERNEL_SPECIALIZED, _lib.GRAM_KERNEL_CLUSTER, _lib.GRAM_KERNEL_SPECIALIZED2,
+                       _lib.GRAM_KERNEL_SPECIALIZED2_CLUSTER):
             b = _run(design, cfg, kernel, **kw)
             _same(a, b)
             b2 = _run(design, cfg, kernel, **kw)       # scheduling differs run to run
             _same(b, b2)
+        design.close()
+
+
+def test_two_position_kernel_equals_classic_on_dense_and_tiny_problems(gpu):
+    """gibbs_gram_ws2.cuh: predicted Gram entries and a second tracked position per thread.  Dense signals (more
+    active coordinates than the prediction list holds, every change a misprediction), p below one window, p = 1,
+    long runs across launches and q rebuilds."""
+    from pyblip_b200 import _lib
+    from pyblip_b200.linear import LinearSpikeSlab
+    rng = np.random.default_rng(6)
+    for (n, p, chains, sweeps, chunk, refresh, nsig) in [(400, 2000, 2, 30, 0, 0, 150), (300, 3000, 3, 80, 32, 0, 40),
+                                                         (600, 1200, 2, 25, 0, 0, 330), (30, 1, 2, 20, 0, 0, 1),
+                                                         (80, 300, 4, 150, 16, 11, 8), (60, 257, 3, 40, 0, 0, 5)]:
+        X = _ar1(rng, n, p, 0.9)
+        beta = np.zeros(p)
+        beta[rng.choice(p, nsig, replace=False)] = 2.0 * rng.standard_normal(nsig)
+        y = X @ beta + rng.standard_normal(n)
+        cfg = LinearSpikeSlab(X, y)._config()
+        design = _lib.Design.upload(X)
+        kw = dict(y=y, chains=chains, chain_offset=1, n_keep=sweeps - 5, burn=5, seed=17, chunk_sweeps=chunk,
+                  gram_refresh=refresh)
+        a = _run(design, cfg, _lib.GRAM_KERNEL_CLASSIC, **kw)
+        _same(a, _run(design, cfg, _lib.GRAM_KERNEL_SPECIALIZED2, **kw))
+        _same(a, _run(design, cfg, _lib.GRAM_KERNEL_SPECIALIZED2_CLUSTER, **kw))
         design.close()
 
 
@@ -96,9 +121,12 @@ def test_specialised_c2_equals_classic_and_auto_picks_it(gpu):
     a = _run(design, cfg, _lib.GRAM_KERNEL_CLASSIC, **kw)
     b = _run(design, cfg, _lib.GRAM_KERNEL_SPECIALIZED, **kw)
     b3 = _run(design, cfg, _lib.GRAM_KERNEL_CLUSTER, **kw)
+    b7 = _run(design, cfg, _lib.GRAM_KERNEL_SPECIALIZED2, **kw)
+    _same(a, _run(design, cfg, _lib.GRAM_KERNEL_SPECIALIZED2_CLUSTER, **kw))
     c = _run(design, cfg, _lib.GRAM_KERNEL_AUTO, **kw)
     _same(a, b)
     _same(a, b3)
+    _same(a, b7)
     _same(a, c)
     # 100 chains: too many for two SMs each
     with pytest.raises(NotImplementedError):
@@ -122,6 +150,7 @@ def test_specialised_changepoint_equals_classic(gpu):
     design = _lib.Design.changepoint(T)
     kw = dict(y=Y, chains=4, n_keep=25, burn=5, seed=4)
     a = _run(design, cfg, _lib.GRAM_KERNEL_CLASSIC, **kw)
-    for kernel in (_lib.GRAM_KERNEL_SPECIALIZED, _lib.GRAM_KERNEL_CLUSTER):
+    for kernel in (_lib.GRAM_KERNEL_SPECIALIZED, _lib.GRAM_KERNEL_CLUSTER, _lib.GRAM_KERNEL_SPECIALIZED2,
+                       _lib.GRAM_KERNEL_SPECIALIZED2_CLUSTER):
         _same(a, _run(design, cfg, kernel, **kw))
     design.close()
