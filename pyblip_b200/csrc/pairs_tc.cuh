@@ -124,11 +124,18 @@ __global__ void __launch_bounds__(PT_THREADS, 1) count_pairs_tc_kernel(
         const uint32_t op_off = (is_a ? 0u : (uint32_t)(PT_A_KSTEP * PT_KS)) + (uint32_t)((r >> 3) * 256 + (r & 7) * 16);
         const uint32_t ks_stride = is_a ? (uint32_t)PT_A_KSTEP : (uint32_t)PT_B_KSTEP;
         int it = 0;
+        // the 32 bytes of the next oct are requested before the current ones are expanded (an L2 / HBM round trip
+        // per two stages would otherwise sit in front of every expansion)
+        uint4 nx0 = make_uint4(0u, 0u, 0u, 0u), nx1 = nx0;
+        if (valid && oct0 < oct1) {
+            nx0 = __ldg(reinterpret_cast<const uint4*>(src + oct0 * 8));
+            nx1 = __ldg(reinterpret_cast<const uint4*>(src + oct0 * 8 + 4));
+        }
         for (int64_t oct = oct0; oct < oct1; ++oct) {
-            uint4 w0 = make_uint4(0u, 0u, 0u, 0u), w1 = w0;
-            if (valid) {
-                w0 = __ldg(reinterpret_cast<const uint4*>(src + oct * 8));
-                w1 = __ldg(reinterpret_cast<const uint4*>(src + oct * 8 + 4));
+            const uint4 w0 = nx0, w1 = nx1;
+            if (valid && oct + 1 < oct1) {
+                nx0 = __ldg(reinterpret_cast<const uint4*>(src + (oct + 1) * 8));
+                nx1 = __ldg(reinterpret_cast<const uint4*>(src + (oct + 1) * 8 + 4));
             }
 #pragma unroll
             for (int half = 0; half < 2; ++half, ++it) {
