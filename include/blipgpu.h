@@ -21,6 +21,12 @@
  *   BLIPGPU_NO_L2_PIN=1              residual-form sweeps: do not pin the design matrix in L2
  *   BLIPGPU_NO_WS=1                  gram form: never pick the role-specialised few-chains kernels
  *   BLIPGPU_WS_CLUSTER=1             gram form: AUTO picks the 2-CTA cluster placement when chains <= SMs/2
+ *   BLIPGPU_WB=1|2                   gram form: AUTO picks the batched-decision kernel (2: its cluster placement)
+ *   BLIPGPU_WS2=1 / BLIPGPU_WS2C=1   gram form: AUTO picks the two-position kernel (one SM / 2-CTA cluster)
+ *   BLIPGPU_STREAM=1                 gram form: AUTO hands stationary launches over to the column-stream kernel
+ *   BLIPGPU_STREAM_MEAN=x            ... when the previous launch saw at most x changes per chain-sweep (default 90)
+ *   BLIPGPU_PAIRS_TC=0|1             count_pairs: forbid / force the tensor-core kernel (default: from 512 columns up)
+ *   BLIPGPU_COUNT_SEQ_TILES=1        count_sequential: the round-1 tile kernel (A/B timing, max_size <= 64)
  *   BLIPGPU_NPRIOR_WORKSPACE_MB=x    budget of the neuronized prior's joint-draw workspace
  *                                    (default: half of the free device memory; chains run in
  *                                    waves when all of them do not fit)
@@ -283,7 +289,9 @@ int blipgpu_count_groups(blipgpu_bits* b, const int64_t* offsets, const int64_t*
 /* pair_counts[a][b] = #rows with columns a and b both non-zero, layout [p][p], symmetric, the
  * diagonal holds the column counts.  The integer content of `np.corrcoef(precorr.T)` in
  * `_samples_dist_matrix` (create_groups.py:523-535): the correlation matrix follows from these
- * counts and N exactly.  p <= 16384 (use blipgpu_bits_select_columns first). */
+ * counts and N exactly.  From 512 columns up the counts are an integer GEMM on the tensor cores
+ * (tcgen05.mma kind::i8 over the column-major copy of the bit matrix, any p); the scalar kernel for
+ * smaller sets stops at p = 16384. */
 int blipgpu_count_pairs(blipgpu_bits* b, int64_t* pair_counts, int32_t out_is_device);
 /* *count = #rows in which at least one of the given groups has no non-zero column: the exact
  * family-wise error count of a selection of groups (pyblip/blip.py:270-276, evaluated up to 100
