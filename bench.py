@@ -442,14 +442,17 @@ def main():
     achieved = alg_bytes / (sweep_ms * 1e-3) / 1e9
     avg_launch_ms = sweep_ms / max(n_launch, 1)
     # DRAM / L2 traffic of one launch from the committed ncu --set full capture (same launch shape:
-    # all 512 chains x 32 sweeps on one GPU); null for any other shape
+    # all 512 chains of one GPU, stationary regime); null for any other shape
     traffic = l2_bytes = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         tj = json.load(open(tpath)).get(kernel)
         if tj and nloc == {"gibbs_gram_kernel": 512, "gibbs_gram_ws_kernel": 64}.get(kernel):
-            traffic = float(tj["dram_bytes_per_launch"])
-            l2_bytes = float(tj["l2_to_sm_bytes_per_launch"]) if "l2_to_sm_bytes_per_launch" in tj else None
+            # the capture is a 32-sweep launch of the same chains; a bench launch holds more sweeps (the library's
+            # default is 128 per launch in gram form), so the captured bytes are scaled by chain-sweeps per launch
+            scale = (chain_sweeps / max(n_launch, 1)) / float(tj.get("chain_sweeps_per_captured_launch", nloc * 32))
+            traffic = float(tj["dram_bytes_per_launch"]) * scale
+            l2_bytes = float(tj["l2_to_sm_bytes_per_launch"]) * scale if "l2_to_sm_bytes_per_launch" in tj else None
     if mode_id == _lib.MODE_GRAM:
         bound = "latency"
         bound_note = ("the formula of SURVEY 8(d) gives an HBM-EQUIVALENT figure (`achieved`, `frac`); the kernel is not "

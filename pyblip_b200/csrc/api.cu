@@ -144,8 +144,20 @@ extern "C" int blipgpu_ctx_create(int device, blipgpu_ctx** out)
     for (int i = 0; i < 8; ++i) CUDA_TRY(cudaEventCreate(&ctx->ev[i]));
     for (int i = 0; i < 4; ++i) { ctx->pinned[i] = nullptr; ctx->pinned_ev[i] = nullptr; }
     ctx->pinned_bytes = 0;
+    ctx->arena_hint = 0; ctx->arena_hint_key[0] = ctx->arena_hint_key[1] = ctx->arena_hint_key[2] = 0;
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+    {
+        // The sample store (GBs per sampler call) comes from the device's stream-ordered pool and goes back to it:
+        // keep freed memory in the pool, so that a process that samples repeatedly pays the driver's
+        // physical allocation once (cudaMalloc / cudaFree of GB-sized buffers were seen to take 100s of ms)
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long thr = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+        cudaGetLastError();
+    }
     *out = ctx;
     return BLIP_OK;
 }

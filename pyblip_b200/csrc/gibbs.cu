@@ -6,6 +6,7 @@
 // chain, in launches of `chunk_sweeps` sweeps.  Permutations for the next chunk
 // are generated on a second stream while the current chunk sweeps.
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <new>
@@ -327,14 +328,19 @@ static int sample_impl(blipgpu_ctx* ctx, blipgpu_design* design,
     const bool use_role = use_cl || use_ws || use_wb || use_wbc || use_ws2c || st_forced;   // double-buffered scratch, no work queue
 
     // ---- chunking
-    int S = opts && opts->chunk_sweeps > 0 ? opts->chunk_sweeps : 32;
+    // Sweeps per launch.  The gram-form kernels compute the visiting order themselves (no permutation buffers) and
+    // lose the tail of every launch (the last work items of a persistent grid, the last sweeps of the slowest chain):
+    // 128 sweeps per launch measured 2.6 % faster than 32 at C2 (12.54 vs 12.87 ms per 32 sweeps of 512 chains).
+    // The other kernels read pre-generated permutations and stay at 32, capped by the size of those buffers.
+    const bool inj_perm = streams && streams->perm;
+    const bool gram_default_chunk = mode == BLIPGPU_MODE_GRAM && !block && !inj_perm && !(streams && (streams->u || streams->z));
+    int S = opts && opts->chunk_sweeps > 0 ? opts->chunk_sweeps : (gram_default_chunk ? 128 : 32);
     {
         const double perm_bytes_per_sweep = 4.0 * (double)chains * (double)p;
         const int cap = (int)std::max(1.0, 1.0e9 / perm_bytes_per_sweep);
-        if (!(opts && opts->chunk_sweeps > 0)) S = std::min(S, cap);
+        if (!(opts && opts->chunk_sweeps > 0) && !gram_default_chunk) S = std::min(S, cap);
         S = (int)std::min<int64_t>(S, n_total);
     }
-    const bool inj_perm = streams && streams->perm;
     // Permutations are generated for PS sweeps at a time (a multiple of the launch chunk S):
     // 16-bit entries when p allows; <= 1.5 GB per buffer, two buffers.
     const bool perm16 = !inj_perm && p <= 65535;
@@ -357,6 +363,7 @@ static int sample_impl(blipgpu_ctx* ctx, blipgpu_design* design,
     }
 
     // ---- allocate
+    DevPoolScope pool_scope(ctx->stream);           // every DevBuf of this call: stream-ordered pool, on the sweep stream
     DevBuf d_beta, d_r, d_mu, d_ylat, d_q, d_h, d_mask, d_ev, d_q0, d_y, d_z, d_ovf, d_scrL, d_scrZ, d_scrP, d_queue;
     DevBuf d_perm[2], d_u, d_zn, d_ig, d_p0, d_g, d_scrI;
     DevBuf snap_beta, snap_r, snap_mu, snap_ylat, snap_q, snap_h, snap_mask, snap_ev;
@@ -395,6 +402,15 @@ static int sample_impl(blipgpu_ctx* ctx, blipgpu_design* design,
     if (inj_ig) BLIP_TRY(d_ig.alloc(sizeof(double) * chains * S));
     if (inj_p0) BLIP_TRY(d_p0.alloc(sizeof(double) * chains * S * nprop));
     if (inj_g) BLIP_TRY(d_g.alloc(sizeof(double) * chains * S));
+    {
+        // pool allocations are ordered on the sweep stream; the second stream (permutation generation) joins there
+        cudaEvent_t ev_alloc;
+        CUDA_TRY(cudaEventCreateWithFlags(&ev_alloc, cudaEventDisableTiming));
+        cudaError_t ea = cudaEventRecord(ev_alloc, ctx->stream);
+        if (ea == cudaSuccess) ea = cudaStreamWaitEvent(ctx->stream2, ev_alloc, 0);
+        cudaEventDestroy(ev_alloc);
+        CUDA_TRY(ea);
+    }
 
     blipgpu_samples* smp = new (std::nothrow) blipgpu_samples();
     if (!smp) { blip_set_error("host allocation failed"); return BLIP_ERR_NOMEM; }
@@ -410,14 +426,16 @@ static int sample_impl(blipgpu_ctx* ctx, blipgpu_design* design,
     CUDA_TRY(cudaEventRecord(ev_call0, ctx->stream));
     struct Guard { blipgpu_samples* s; ~Guard() { if (s) blipgpu_samples_free(s); } } guard{ smp };
     const bool keep_lat = probit && (!opts || opts->keep_latents != 0);
+    const auto t_alloc0 = std::chrono::steady_clock::now();
     {
         cudaError_t e;
-        if ((e = cudaMalloc(&smp->bits, sizeof(uint32_t) * words * smp->rows_pad)) != cudaSuccess ||
-            (e = cudaMalloc(&smp->row_off, sizeof(int64_t) * smp->rows)) != cudaSuccess ||
-            (e = cudaMalloc(&smp->row_nnz, sizeof(int32_t) * smp->rows)) != cudaSuccess ||
-            (e = cudaMalloc(&smp->hyper, sizeof(double) * 3 * smp->rows)) != cudaSuccess ||
-            (e = cudaMalloc(&smp->arena_used, sizeof(unsigned long long))) != cudaSuccess ||
-            (keep_lat && (e = cudaMalloc(&smp->latents, sizeof(double) * smp->rows * n)) != cudaSuccess)) {
+        cudaStream_t sa = ctx->stream;               // stream-ordered pool allocations (freed in blipgpu_samples_free)
+        if ((e = blip_store_alloc((void**)&smp->bits, sizeof(uint32_t) * words * smp->rows_pad, sa)) != cudaSuccess ||
+            (e = blip_store_alloc((void**)&smp->row_off, sizeof(int64_t) * smp->rows, sa)) != cudaSuccess ||
+            (e = blip_store_alloc((void**)&smp->row_nnz, sizeof(int32_t) * smp->rows, sa)) != cudaSuccess ||
+            (e = blip_store_alloc((void**)&smp->hyper, sizeof(double) * 3 * smp->rows, sa)) != cudaSuccess ||
+            (e = blip_store_alloc((void**)&smp->arena_used, sizeof(unsigned long long), sa)) != cudaSuccess ||
+            (keep_lat && (e = blip_store_alloc((void**)&smp->latents, sizeof(double) * smp->rows * n, sa)) != cudaSuccess)) {
             blip_set_error("sample_spikeslab: cannot allocate the sample store: %s", cudaGetErrorString(e));
             return BLIP_ERR_NOMEM;
         }
@@ -427,7 +445,14 @@ static int sample_impl(blipgpu_ctx* ctx, blipgpu_design* design,
     CUDA_TRY(cudaMemsetAsync(smp->arena_used, 0, sizeof(unsigned long long), st));
     if (keep_lat) CUDA_TRY(cudaMemsetAsync(smp->latents, 0, sizeof(double) * smp->rows * n, st));
     smp->arena_cap = std::max<int64_t>(chains * (int64_t)std::min<int64_t>(S, n_keep) * std::max<int64_t>(64, p / 16), 1 << 16);
-    CUDA_TRY(cudaMalloc(&smp->values, sizeof(double) * smp->arena_cap));
+    // a repeated job (same chains, sweeps, p on this context) starts with what the previous one ended up needing (+15 %):
+    // no mid-run growth, and every pool request has the size of a block the previous call returned
+    const bool hint_hit = ctx->arena_hint > 0 && ctx->arena_hint_key[0] == chains && ctx->arena_hint_key[1] == n_keep && ctx->arena_hint_key[2] == p;
+    if (hint_hit) smp->arena_cap = std::max<int64_t>(smp->arena_cap, ctx->arena_hint);
+    CUDA_TRY(blip_store_alloc((void**)&smp->values, sizeof(double) * smp->arena_cap, st));
+    if (getenv("BLIPGPU_LAUNCH_LOG"))
+        fprintf(stderr, "[blipgpu] sample store allocated in %.2f ms (host clock)\n",
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_alloc0).count());
 
     // ---- parameters
     SweepParams P;
@@ -663,13 +688,14 @@ static int sample_impl(blipgpu_ctx* ctx, blipgpu_design* design,
             const int64_t remaining_kept = n_total - std::max<int64_t>(sweep0, burn);
             int64_t newcap = (int64_t)used_before + std::max<int64_t>(min_free, (int64_t)(1.25 * max_per_sweep * (double)remaining_kept));
             double* nv = nullptr;
-            cudaError_t e = cudaMalloc(&nv, sizeof(double) * newcap);
+            const auto t_g0 = std::chrono::steady_clock::now();
+            cudaError_t e = blip_store_alloc((void**)&nv, sizeof(double) * newcap, st);
             if (e != cudaSuccess) { blip_set_error("sample_spikeslab: cannot grow the value arena to %lld doubles: %s", (long long)newcap, cudaGetErrorString(e)); return BLIP_ERR_NOMEM; }
             CUDA_TRY(cudaMemcpyAsync(nv, smp->values, sizeof(double) * used_before, cudaMemcpyDeviceToDevice, st));
-            CUDA_TRY(cudaStreamSynchronize(st));
-            CUDA_TRY(cudaFree(smp->values));
+            blip_store_free(smp->values, st);
             smp->values = nv; smp->arena_cap = newcap;
-            if (launch_log) fprintf(stderr, "[blipgpu] value arena grown to %lld doubles at sweep %lld\n", (long long)newcap, (long long)sweep0);
+            if (launch_log) fprintf(stderr, "[blipgpu] value arena grown to %lld doubles at sweep %lld (%.2f ms host clock)\n", (long long)newcap, (long long)sweep0,
+                                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_g0).count());
             return BLIP_OK;
         };
         BLIP_TRY(grow(need));
@@ -802,6 +828,10 @@ static int sample_impl(blipgpu_ctx* ctx, blipgpu_design* design,
         float ms = 0.f;
         CUDA_TRY(cudaEventElapsedTime(&ms, ev_call0, ev_call1));
         smp->total_ms = ms;
+        if (!hint_hit || (int64_t)used_before > ctx->arena_hint) {
+            ctx->arena_hint = (int64_t)(1.15 * (double)used_before) + 1024;
+            ctx->arena_hint_key[0] = chains; ctx->arena_hint_key[1] = n_keep; ctx->arena_hint_key[2] = p;
+        }
         std::vector<double> hs((size_t)chains * GB_HS);
         CUDA_TRY(cudaMemcpy(hs.data(), d_h.ptr, d_h.bytes, cudaMemcpyDeviceToHost));
         for (int64_t c = 0; c < chains; ++c) {

@@ -2,6 +2,7 @@
 #pragma once
 #include "../../include/blipgpu.h"
 #include "common.cuh"
+#include <cstdlib>
 
 struct blipgpu_ctx {
     int device;
@@ -17,6 +18,8 @@ struct blipgpu_ctx {
     cudaEvent_t ev[8];
     // pinned bounce buffers of blip_d2h (allocated on first use)
     void* pinned[4]; cudaEvent_t pinned_ev[4]; size_t pinned_bytes;
+    // value-arena size the last sampler call of shape (chains, n_keep, p) ended up needing (gibbs.cu)
+    int64_t arena_hint, arena_hint_key[3];
 };
 
 struct blipgpu_design {
@@ -71,22 +74,53 @@ int blip_xty(cudaStream_t st, const blipgpu_design* d, const double* d_y, double
 int blip_bits_alloc(blipgpu_ctx* ctx, int64_t N, int64_t p, blipgpu_bits** out);   // counting.cu
 static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
+// Sample-store allocations: stream-ordered (device memory pool, kept across calls) unless BLIPGPU_NO_POOL is set
+static inline bool blip_use_pool() { static const bool v = getenv("BLIPGPU_NO_POOL") == nullptr; return v; }
+static inline cudaError_t blip_store_alloc(void** p, size_t bytes, cudaStream_t st)
+{
+    return blip_use_pool() ? cudaMallocAsync(p, bytes, st) : cudaMalloc(p, bytes);
+}
+static inline void blip_store_free(void* p, cudaStream_t st)
+{
+    if (!p) return;
+    if (blip_use_pool() && cudaFreeAsync(p, st) == cudaSuccess) return;
+    cudaGetLastError();
+    cudaStreamSynchronize(st);
+    cudaFree(p);
+}
+
 // device allocation freed on scope exit
+// Inside a DevPoolScope the buffers come from the device's stream-ordered pool on the scope's stream (the sampler:
+// ~25 buffers per call, and cudaMalloc / cudaFree were seen to take up to 100s of ms each on a busy driver).
 struct DevBuf {
-    void* ptr = nullptr; size_t bytes = 0;
+    void* ptr = nullptr; size_t bytes = 0; cudaStream_t pool_st = nullptr; bool pooled = false;
+    static cudaStream_t& scope_stream() { static thread_local cudaStream_t st = nullptr; return st; }
+    static bool& scope_on() { static thread_local bool on = false; return on; }
     int alloc(size_t b) {
         bytes = b;
         if (b == 0) { ptr = nullptr; return BLIP_OK; }
-        cudaError_t e = cudaMalloc(&ptr, b);
+        pooled = scope_on() && blip_use_pool();
+        pool_st = scope_stream();
+        cudaError_t e = pooled ? cudaMallocAsync(&ptr, b, pool_st) : cudaMalloc(&ptr, b);
         if (e != cudaSuccess) {
             ptr = nullptr;
-            blip_set_error("cudaMalloc(%zu bytes) failed: %s", b, cudaGetErrorString(e));
+            blip_set_error("device allocation of %zu bytes failed: %s", b, cudaGetErrorString(e));
             return BLIP_ERR_NOMEM;
         }
         return BLIP_OK;
     }
-    ~DevBuf() { if (ptr) cudaFree(ptr); }
+    ~DevBuf() {
+        if (!ptr) return;
+        if (pooled && cudaFreeAsync(ptr, pool_st) == cudaSuccess) return;
+        cudaGetLastError();
+        cudaFree(ptr);
+    }
     template <class T> T* as() { return reinterpret_cast<T*>(ptr); }
+};
+struct DevPoolScope {
+    bool prev_on; cudaStream_t prev_st;
+    explicit DevPoolScope(cudaStream_t st) : prev_on(DevBuf::scope_on()), prev_st(DevBuf::scope_stream()) { DevBuf::scope_on() = true; DevBuf::scope_stream() = st; }
+    ~DevPoolScope() { DevBuf::scope_on() = prev_on; DevBuf::scope_stream() = prev_st; }
 };
 
 // event-timed region on ctx->stream

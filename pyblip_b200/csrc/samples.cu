@@ -169,8 +169,12 @@ extern "C" int blipgpu_samples_free(blipgpu_samples* s)
 {
     if (!s) return BLIP_OK;
     cudaSetDevice(s->ctx->device);
-    cudaFree(s->bits); cudaFree(s->row_off); cudaFree(s->row_nnz); cudaFree(s->values);
-    cudaFree(s->arena_used); cudaFree(s->hyper); cudaFree(s->latents);
+    // stream-ordered frees: the memory returns to the device pool (kept there, blipgpu_ctx_create) once everything
+    // queued on the library's streams has used it
+    cudaStreamSynchronize(s->ctx->stream2);
+    cudaStream_t st = s->ctx->stream;
+    void* ptrs[] = { s->bits, s->row_off, s->row_nnz, s->values, s->arena_used, s->hyper, s->latents };
+    for (void* ptr : ptrs) blip_store_free(ptr, st);
     delete s;
     return BLIP_OK;
 }

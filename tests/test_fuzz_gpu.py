@@ -296,14 +296,17 @@ def test_value_arena_overflow_replays_the_chunk(gpu):
     from oracle import gibbs_oracle as go
     from pyblip_b200 import _lib
     rng = np.random.default_rng(404 + SEED)
-    n, p, N, chains, seed = 700, 420, 8, 48, 77     # 48 chains x 4 sweeps x ~400 values > the 65536-value floor
+    n, p, N, seed = 700, 420, 8, 77     # >= 48 chains x 4 sweeps x ~400 values > the 65536-value floor
     X = rng.standard_normal((n, p))
     beta = 0.5 * rng.standard_normal(p)
     y = X @ beta + rng.standard_normal(n)
     legs = [("linear", _lib.MODE_RESIDUAL, 1), ("linear", _lib.MODE_GRAM, 1), ("probit", _lib.MODE_RESIDUAL, 1),
             ("linear", _lib.MODE_GRAM, 3)]
     design = _lib.Design.upload(X)
-    for kind, mode, bsize in legs:
+    for leg, (kind, mode, bsize) in enumerate(legs):
+        # a context remembers the arena a job of the same (chains, n_keep, p) ended up needing and starts the next
+        # one there: every leg gets its own chain count, so that each of them starts from the first guess
+        chains = 48 + leg
         probit = kind == "probit"
         hp = go.hparams(p0=0.05, update_p0=False, update_sigma2=not probit)
         cfg = _lib.SpikeSlabConfig(*[getattr(hp, f) for f, _ in hp._fields_])
@@ -314,6 +317,13 @@ def test_value_arena_overflow_replays_the_chunk(gpu):
         betas = smp.dense().reshape(chains, N, p)
         assert (betas != 0).mean() > 0.5
         smp.close()
+        if leg == 0:
+            # the same job again: the arena starts at the remembered size, nothing is replayed, same draws
+            again = _lib.sample_spikeslab(design, cfg, chains=chains, n_keep=N, burn=0, seed=seed, mode=mode,
+                                          bsize=bsize, chunk_sweeps=4, **data)
+            assert again.info.sweep_launches == 2
+            assert np.array_equal(again.dense().reshape(chains, N, p), betas)
+            again.close()
         for c in (0, 17, chains - 1):
             if bsize > 1:
                 ref = go.sample_spikeslab_multi(N, bsize, X, hp=hp, seed=seed, chain=c, **data)
