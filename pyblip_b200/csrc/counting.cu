@@ -360,20 +360,22 @@ __global__ void __launch_bounds__(CT_BLOCK) gap_hist_kernel(
                     if (xp) { tz += __clz(xp); done = true; } else tz += 32;
                 }
             }
-            int prev = -1 - tz;                         // the previous set bit, relative to column 32 w
-            while (__any_sync(0xffffffffu, x != 0u)) {
-                int key = -1;
-                if (x) {
+            // Rows of a tile are consecutive kept sweeps of one chain and mostly carry the SAME word (the persistently
+            // active columns): lanes are grouped ONCE by (word, zero run before it -- only what the cap can see), and
+            // one lane per group books the group's set bits with the group's size as the weight.
+            tz = min(tz, max_size - 1);
+            const unsigned peers = __match_any_sync(0xffffffffu, ((unsigned long long)(unsigned)tz << 32) | x);
+            if (x != 0u && lane == __ffs(peers) - 1) {
+                const int weight = __popc(peers);
+                int prev = -1 - tz;                     // the previous set bit, relative to column 32 w
+                do {
                     const int b = __ffs(x) - 1;
                     x &= x - 1;
-                    key = b * max_size + min(b - prev - 1, max_size - 1);
+                    const int key = b * max_size + min(b - prev - 1, max_size - 1);
                     prev = b;
-                }
-                const unsigned peers = __match_any_sync(0xffffffffu, key);
-                if (key >= 0 && lane == __ffs(peers) - 1) {
-                    if (SMEM_HIST) atomicAdd(&s_h[key], __popc(peers));
-                    else atomicAdd(Hw + key, (unsigned long long)__popc(peers));
-                }
+                    if (SMEM_HIST) atomicAdd(&s_h[key], weight);
+                    else atomicAdd(Hw + key, (unsigned long long)weight);
+                } while (x);
             }
         }
     }
