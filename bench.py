@@ -95,10 +95,18 @@ class ClockSampler:
               "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
+    """`nvidia-smi -lms 200` next to the run.  The process is started BEFORE the last warm-up step: attaching a
+    second client to the GPU was seen to stall the device for up to a second (3160 ms for the first timed step
+    against 2140 ms for the others); `mark()` at the start of the timed region drops the samples taken before it."""
+
     def __init__(self, gpu_index):
         self.gpu = gpu_index
         self.proc = None
         self.lines = []
+        self.t_mark = 0.0
+
+    def mark(self):
+        self.t_mark = time.perf_counter()
 
     def start(self):
         try:
@@ -113,7 +121,7 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
     def stop(self):
         if self.proc is None:
@@ -125,7 +133,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for t_line, ln in self.lines:
+            if t_line < self.t_mark:
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -385,12 +395,15 @@ def main():
                 print(f"[step] call {1e3 * (t1 - t0):.1f} ms  device {info.total_ms:.1f} ms  sweep kernels "
                       f"{info.sweep_ms:.1f} ms  nnz/row {info.nnz / max(info.rows, 1):.1f}", file=sys.stderr, flush=True)
             return out
-        for w in range(args.warmup):
-            step(1000 + w)
         clocks = ClockSampler(local_rank)
-        if want_clocks:
+        for w in range(args.warmup):
+            if want_clocks and w == args.warmup - 1:
+                clocks.start()
+            step(1000 + w)
+        if want_clocks and args.warmup == 0:
             clocks.start()
         barrier(dist, ctx)
+        clocks.mark()
         ctx.counters(reset=True)
         ctx.event_record(0)
         stats = [step(2000 + k) for k in range(args.steps)]
@@ -480,10 +493,15 @@ def main():
     e2e = e2e_pips = None
     if not args.no_e2e:
         def e2e_step(seed, with_pips):
+            t_0 = time.perf_counter()
             lm = LinearSpikeSlab(X, y)
             lm.sample(N=S, burn=B, chains=chains, seed=seed, mode=args.mode)
+            t_1 = time.perf_counter()
             indptr, indices, values = lm.samples_csr()
             out = dict(nnz=int(indptr[-1]), pip_s=0.0)
+            if args.debug and rank == 0:
+                print(f"[e2e step] construct + sample() {1e3 * (t_1 - t_0):.1f} ms  samples_csr() "
+                      f"{1e3 * (time.perf_counter() - t_1):.1f} ms  nnz {out['nnz']}", file=sys.stderr, flush=True)
             if with_pips:
                 t_p = time.perf_counter()
                 # the other half of the path, on the device-resident samples of every rank

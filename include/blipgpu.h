@@ -34,6 +34,7 @@
 #ifndef BLIPGPU_H
 #define BLIPGPU_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -78,6 +79,17 @@ int blipgpu_ctx_counters(blipgpu_ctx* ctx, int64_t* kernel_launches, int64_t* h2
  * timed regions with these because torch.cuda.Event only sees torch's stream. */
 int blipgpu_ctx_event_record(blipgpu_ctx* ctx, int slot);
 int blipgpu_ctx_event_elapsed_ms(blipgpu_ctx* ctx, int slot_begin, int slot_end, double* ms);
+
+/* ---- page-locked host blocks for results ---------------------------------
+ * The reference returns fresh NumPy arrays (`np.concatenate([...])`,
+ * pyblip/linear/linear.py:165-168).  A result written into page-locked memory is
+ * one DMA; into a fresh pageable array it is a bounce copy plus a page fault per
+ * page.  The host side therefore takes the arrays it returns from here and hands
+ * them back when the array is collected; blocks are recycled process-wide (up to
+ * BLIPGPU_HOST_CACHE_MB, default 8192, stay pinned while idle).  Every entry point
+ * that writes to host memory accepts either kind of destination. */
+int blipgpu_host_alloc(size_t bytes, void** out);
+int blipgpu_host_free(void* p);
 
 /* ---- design matrix ----------------------------------------------------- */
 #define BLIPGPU_DESIGN_DENSE 0        /* X given, column-major copy kept in HBM   */

@@ -8,6 +8,7 @@ opaque handles; the reference-facing API lives in ``linear/``, ``probit/``,
 import ctypes as C
 import os
 import threading
+import weakref
 
 import numpy as np
 
@@ -30,6 +31,7 @@ SYMBOLS = [
     "blipgpu_abi_version", "blipgpu_sizeof", "blipgpu_last_error", "blipgpu_device_count",
     "blipgpu_ctx_create", "blipgpu_ctx_destroy", "blipgpu_ctx_synchronize", "blipgpu_ctx_timing",
     "blipgpu_ctx_counters", "blipgpu_ctx_event_record", "blipgpu_ctx_event_elapsed_ms",
+    "blipgpu_host_alloc", "blipgpu_host_free",
     "blipgpu_design_upload", "blipgpu_design_changepoint", "blipgpu_design_build_gram",
     "blipgpu_design_get_gram", "blipgpu_design_get_xl2", "blipgpu_design_free",
     "blipgpu_sample_spikeslab", "blipgpu_sample_spikeslab_multi",
@@ -137,6 +139,33 @@ def check(rc):
     if rc == ERR_NUMERIC:        # the reference raises RuntimeError (dpotrf) in the same situations
         raise RuntimeError(msg)
     raise BlipGpuError(f"libblipgpu error {rc}: {msg}")
+
+
+_HOST_PINNED_MIN = 1 << 20
+
+
+def _host_release(ptr):
+    try:
+        load().blipgpu_host_free(C.c_void_p(ptr))
+    except Exception:      # interpreter shutdown
+        pass
+
+
+def host_empty(count, dtype):
+    """1-D result array.  From 1 MB up it lives in a page-locked block of the library
+    (``blipgpu_host_alloc``) that goes back to the library's cache when the array and
+    every view of it are collected: the device writes such a result with one DMA.
+    ``BLIPGPU_NO_PINNED_OUT=1`` (or a failed page-lock) gives a plain ``np.empty``."""
+    dtype = np.dtype(dtype)
+    nbytes = int(count) * dtype.itemsize
+    if nbytes < _HOST_PINNED_MIN or os.environ.get("BLIPGPU_NO_PINNED_OUT"):
+        return np.empty(count, dtype=dtype)
+    ptr = C.c_void_p()
+    if load().blipgpu_host_alloc(C.c_size_t(nbytes), C.byref(ptr)) != 0 or not ptr.value:
+        return np.empty(count, dtype=dtype)
+    block = type("HostBlock", (C.c_char * nbytes,), {}).from_address(ptr.value)
+    weakref.finalize(block, _host_release, ptr.value)
+    return np.frombuffer(block, dtype=dtype, count=count)
 
 
 def device_count():
@@ -295,7 +324,7 @@ class Samples:
 
     def hyper(self):
         rows = self.info.rows
-        p0s, tau2s, sigma2s = np.empty(rows), np.empty(rows), np.empty(rows)
+        p0s, tau2s, sigma2s = (host_empty(rows, np.float64) for _ in range(3))
         check(load().blipgpu_samples_hyper(self._h, C.c_void_p(p0s.ctypes.data),
                                            C.c_void_p(tau2s.ctypes.data),
                                            C.c_void_p(sigma2s.ctypes.data)))
@@ -312,8 +341,8 @@ class Samples:
         rows = self.info.rows
         indptr = np.empty(rows + 1, dtype=np.int64)
         nnz = self.info.nnz
-        indices = np.empty(max(nnz, 1), dtype=np.int32)
-        values = np.empty(max(nnz, 1), dtype=np.float64)
+        indices = host_empty(max(nnz, 1), np.int32)
+        values = host_empty(max(nnz, 1), np.float64)
         check(load().blipgpu_samples_csr(self._h, C.c_void_p(indptr.ctypes.data),
                                          C.c_void_p(indices.ctypes.data),
                                          C.c_void_p(values.ctypes.data)))

@@ -8,7 +8,9 @@
 #include <sched.h>
 #include <cstdlib>
 #include <sys/mman.h>
+#include <mutex>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 #include "internal.cuh"
 
@@ -52,10 +54,110 @@ int blip_ctx_activate(blipgpu_ctx* ctx)
     return BLIP_OK;
 }
 
+// ---- page-locked host blocks for results, kept across calls --------------------------------------------
+// A result that goes into page-locked memory is one DMA; into a fresh pageable array it is a bounce through
+// a pinned buffer plus a host copy that takes a page fault per page (0.12 - 0.3 s for the 1.6 GB CSR of C2).
+// Pinning itself is slow (~0.25 ms per MB), so blocks are recycled: the host side wraps a block in a NumPy
+// array whose finaliser hands it back (pyblip_b200/_lib.py: host_empty).  Process-wide, not per context: a
+// finaliser may run after the context is gone.
+namespace {
+struct HostBlock { void* ptr; size_t bytes; int device; };
+struct HostCache {
+    std::mutex mu;
+    std::unordered_map<void*, HostBlock> live;
+    std::vector<HostBlock> idle;                    // oldest first
+    size_t idle_bytes = 0;
+};
+HostCache& host_cache() { static HostCache* c = new HostCache(); return *c; }   // never destroyed (finalisers at exit)
+size_t host_cache_limit()
+{
+    static const size_t v = [] {
+        const char* e = getenv("BLIPGPU_HOST_CACHE_MB");
+        return (size_t)(e ? std::max(0, atoi(e)) : 8192) << 20;
+    }();
+    return v;
+}
+void host_block_release(const HostBlock& b)
+{
+    int cur = 0;
+    cudaGetDevice(&cur);
+    if (cur != b.device) cudaSetDevice(b.device);
+    cudaFreeHost(b.ptr);
+    if (cur != b.device) cudaSetDevice(cur);
+    cudaGetLastError();
+}
+} // namespace
+
+extern "C" int blipgpu_host_alloc(size_t bytes, void** out)
+{
+    if (!out) { blip_set_error("host_alloc: out is NULL"); return BLIP_ERR_ARG; }
+    const size_t want = (size_t)round_up((int64_t)std::max<size_t>(bytes, 1), (int64_t)2 << 20);
+    HostCache& hc = host_cache();
+    std::lock_guard<std::mutex> lock(hc.mu);
+    int best = -1;
+    for (int i = 0; i < (int)hc.idle.size(); ++i)   // best fit, and no block more than twice the request
+        if (hc.idle[i].bytes >= want && hc.idle[i].bytes <= 2 * want + ((size_t)8 << 20) &&
+            (best < 0 || hc.idle[i].bytes < hc.idle[best].bytes)) best = i;
+    if (best >= 0) {
+        HostBlock b = hc.idle[best];
+        hc.idle.erase(hc.idle.begin() + best);
+        hc.idle_bytes -= b.bytes;
+        hc.live[b.ptr] = b;
+        *out = b.ptr;
+        return BLIP_OK;
+    }
+    HostBlock b{ nullptr, want + want / 16, 0 };    // head-room: the next job's result is rarely the same size to the byte
+    b.bytes = (size_t)round_up((int64_t)b.bytes, (int64_t)2 << 20);
+    cudaGetDevice(&b.device);
+    cudaError_t e = cudaHostAlloc(&b.ptr, b.bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess && !hc.idle.empty()) {     // give the idle blocks back and try once more
+        cudaGetLastError();
+        for (const HostBlock& i : hc.idle) host_block_release(i);
+        hc.idle.clear(); hc.idle_bytes = 0;
+        e = cudaHostAlloc(&b.ptr, b.bytes, cudaHostAllocPortable);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        blip_set_error("host_alloc: cannot page-lock %zu bytes: %s", b.bytes, cudaGetErrorString(e));
+        return BLIP_ERR_NOMEM;
+    }
+    hc.live[b.ptr] = b;
+    *out = b.ptr;
+    return BLIP_OK;
+}
+
+extern "C" int blipgpu_host_free(void* p)
+{
+    if (!p) return BLIP_OK;
+    HostCache& hc = host_cache();
+    std::lock_guard<std::mutex> lock(hc.mu);
+    auto it = hc.live.find(p);
+    if (it == hc.live.end()) { blip_set_error("host_free: not a block of blipgpu_host_alloc"); return BLIP_ERR_ARG; }
+    const HostBlock b = it->second;
+    hc.live.erase(it);
+    hc.idle.push_back(b);
+    hc.idle_bytes += b.bytes;
+    while (hc.idle_bytes > host_cache_limit() && !hc.idle.empty()) {
+        const HostBlock old = hc.idle.front();
+        hc.idle.erase(hc.idle.begin());
+        hc.idle_bytes -= old.bytes;
+        host_block_release(old);
+    }
+    return BLIP_OK;
+}
+
+bool blip_host_is_pinned(const void* p)
+{
+    cudaPointerAttributes attr;
+    const cudaError_t e = cudaPointerGetAttributes(&attr, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    return attr.type == cudaMemoryTypeHost;
+}
+
 int blip_d2h(blipgpu_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes)
 {
     const size_t kChunk = (size_t)32 << 20;
-    if (bytes < 2 * kChunk) {                      // small: the driver's own staging is fine
+    if (bytes < 2 * kChunk || blip_host_is_pinned(dst_host)) {   // small (the driver's own staging is fine) or one DMA
         CUDA_TRY(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         return BLIP_OK;

@@ -71,6 +71,7 @@ int blip_d2h(blipgpu_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes
 int blip_fill_perms(cudaStream_t st, void* buf, int perm16, int64_t chains, int S, int64_t p,
                     int64_t sweep0, uint32_t k0, uint32_t k1, uint32_t chain_offset);
 int blip_xty(cudaStream_t st, const blipgpu_design* d, const double* d_y, double* d_q0);
+bool blip_host_is_pinned(const void* p);                                            // api.cu
 int blip_bits_alloc(blipgpu_ctx* ctx, int64_t N, int64_t p, blipgpu_bits** out);   // counting.cu
 static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 

@@ -40,10 +40,10 @@ __global__ void __launch_bounds__(GB_BLOCK) dense_rows_kernel(
 __global__ void __launch_bounds__(GB_BLOCK) csr_rows_kernel(
     const uint32_t* __restrict__ bits, const int64_t* __restrict__ row_off,
     const double* __restrict__ values, const int64_t* __restrict__ indptr, int64_t rows_pad,
-    int words, int32_t* __restrict__ out_idx, double* __restrict__ out_val)
+    int words, int64_t row0, int32_t* __restrict__ out_idx, double* __restrict__ out_val)
 {
     __shared__ int s_scan[GB_NWARP + 2];
-    const int64_t row = blockIdx.x;
+    const int64_t row = row0 + blockIdx.x;
     const int64_t off = row_off[row], dst0 = indptr[row];
     int base = 0;
     for (int w0 = 0; w0 < words; w0 += GB_BLOCK) {
@@ -132,28 +132,57 @@ extern "C" int blipgpu_samples_csr(blipgpu_samples* s, int64_t* indptr, int32_t*
     const int64_t total = indptr[s->rows];
     if (!indices || !values || total == 0) return BLIP_OK;
     int64_t* d_indptr = nullptr; int32_t* d_idx = nullptr; double* d_val = nullptr;
+    cudaStream_t st = s->ctx->stream, st2 = s->ctx->stream2;
     cudaError_t e;
-    if ((e = cudaMalloc(&d_indptr, sizeof(int64_t) * (s->rows + 1))) != cudaSuccess ||
-        (e = cudaMalloc(&d_idx, sizeof(int32_t) * total)) != cudaSuccess ||
-        (e = cudaMalloc(&d_val, sizeof(double) * total)) != cudaSuccess) {
-        cudaFree(d_indptr); cudaFree(d_idx); cudaFree(d_val);
+    if ((e = blip_store_alloc((void**)&d_indptr, sizeof(int64_t) * (s->rows + 1), st)) != cudaSuccess ||
+        (e = blip_store_alloc((void**)&d_idx, sizeof(int32_t) * total, st)) != cudaSuccess ||
+        (e = blip_store_alloc((void**)&d_val, sizeof(double) * total, st)) != cudaSuccess) {
+        blip_store_free(d_indptr, st); blip_store_free(d_idx, st); blip_store_free(d_val, st);
         blip_set_error("samples_csr: allocation failed: %s", cudaGetErrorString(e));
         return BLIP_ERR_NOMEM;
     }
-    cudaStream_t st = s->ctx->stream;
-    int rc = BLIP_OK;
-    e = cudaMemcpyAsync(d_indptr, indptr, sizeof(int64_t) * (s->rows + 1), cudaMemcpyHostToDevice, st);
-    csr_rows_kernel<<<(unsigned)s->rows, GB_BLOCK, 0, st>>>(s->bits, s->row_off, s->values, d_indptr, s->rows_pad,
-                                                           (int)s->words, d_idx, d_val);
-    s->ctx->kernel_launches += 1;
+    struct Temps { void* a; void* b; void* c; cudaStream_t st; ~Temps() { blip_store_free(a, st); blip_store_free(b, st); blip_store_free(c, st); } }
+        temps{ d_indptr, d_idx, d_val, st };
     s->ctx->d2h_bytes += (int64_t)(sizeof(int32_t) + sizeof(double)) * total + (int64_t)sizeof(int32_t) * s->rows;
     s->ctx->h2d_bytes += (int64_t)sizeof(int64_t) * (s->rows + 1);
-    if (e == cudaSuccess) e = cudaGetLastError();
-    if (e != cudaSuccess) { blip_set_error("samples_csr: %s", cudaGetErrorString(e)); rc = BLIP_ERR_CUDA; }
-    if (rc == BLIP_OK) rc = blip_d2h(s->ctx, indices, d_idx, sizeof(int32_t) * total);
-    if (rc == BLIP_OK) rc = blip_d2h(s->ctx, values, d_val, sizeof(double) * total);
-    cudaFree(d_indptr); cudaFree(d_idx); cudaFree(d_val);
-    return rc;
+    CUDA_TRY(cudaMemcpyAsync(d_indptr, indptr, sizeof(int64_t) * (s->rows + 1), cudaMemcpyHostToDevice, st));
+    const bool direct = blip_host_is_pinned(indices) && blip_host_is_pinned(values);
+    if (!direct) {
+        // pageable destination: gather everything, then the bounce-buffer copy of blip_d2h
+        csr_rows_kernel<<<(unsigned)s->rows, GB_BLOCK, 0, st>>>(s->bits, s->row_off, s->values, d_indptr, s->rows_pad,
+                                                               (int)s->words, 0, d_idx, d_val);
+        s->ctx->kernel_launches += 1;
+        CUDA_TRY(cudaGetLastError());
+        BLIP_TRY(blip_d2h(s->ctx, indices, d_idx, sizeof(int32_t) * total));
+        BLIP_TRY(blip_d2h(s->ctx, values, d_val, sizeof(double) * total));
+        return BLIP_OK;
+    }
+    // page-locked destination (blipgpu_host_alloc): slabs of rows, the DMA of a slab runs under the gather of the next
+    const int nslab = (int)std::min<int64_t>(8, s->rows);
+    cudaEvent_t ev[8] = {};
+    cudaError_t err = cudaSuccess;
+    for (int k = 0; k < nslab && err == cudaSuccess; ++k) err = cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming);
+    for (int k = 0; k < nslab && err == cudaSuccess; ++k) {
+        const int64_t r0 = s->rows * k / nslab, r1 = s->rows * (k + 1) / nslab;
+        const int64_t a = indptr[r0], b = indptr[r1];
+        csr_rows_kernel<<<(unsigned)(r1 - r0), GB_BLOCK, 0, st>>>(s->bits, s->row_off, s->values, d_indptr, s->rows_pad,
+                                                                 (int)s->words, r0, d_idx, d_val);
+        s->ctx->kernel_launches += 1;
+        if ((err = cudaGetLastError()) != cudaSuccess) break;
+        if ((err = cudaEventRecord(ev[k], st)) != cudaSuccess) break;
+        if ((err = cudaStreamWaitEvent(st2, ev[k], 0)) != cudaSuccess) break;
+        if (b > a) {
+            if ((err = cudaMemcpyAsync(indices + a, d_idx + a, sizeof(int32_t) * (b - a), cudaMemcpyDeviceToHost, st2)) != cudaSuccess) break;
+            if ((err = cudaMemcpyAsync(values + a, d_val + a, sizeof(double) * (b - a), cudaMemcpyDeviceToHost, st2)) != cudaSuccess) break;
+        }
+    }
+    cudaError_t e2 = cudaStreamSynchronize(st2);       // the temporaries are freed on `st` after this
+    if (err == cudaSuccess) err = e2;
+    e2 = cudaStreamSynchronize(st);
+    if (err == cudaSuccess) err = e2;
+    for (int k = 0; k < nslab; ++k) if (ev[k]) cudaEventDestroy(ev[k]);
+    if (err != cudaSuccess) { blip_set_error("samples_csr: %s", cudaGetErrorString(err)); return BLIP_ERR_CUDA; }
+    return BLIP_OK;
 }
 
 extern "C" int blipgpu_samples_latents(blipgpu_samples* s, int64_t row0, int64_t row1, double* out)

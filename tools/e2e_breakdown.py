@@ -1,34 +1,22 @@
-"""Host-clock breakdown of the end-to-end path bench.py times (LinearSpikeSlab(X, y).sample + samples_csr)."""
-import os
-import sys
-import time
-
+"""Where the end-to-end step (bench.py `e2e`) spends its time outside the sweep kernels: host clock around each
+stage of LinearSpikeSlab(X, y).sample(...) + samples_csr() at BASELINE configs[1].   python tools/e2e_breakdown.py"""
+import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import bench  # noqa: E402
-from pyblip_b200.linear import LinearSpikeSlab  # noqa: E402
-
+import numpy as np
+import bench
+from pyblip_b200 import _lib
+from pyblip_b200.linear import LinearSpikeSlab
 X, y, _ = bench.make_data()
-for rep in range(3):
-    t0 = time.perf_counter()
+ctx = _lib.Context.get(0)
+for rep in range(4):
+    t = [time.perf_counter()]
     lm = LinearSpikeSlab(X, y)
-    lm.sample(N=5000, burn=100, chains=512, seed=4000 + rep, mode="gram")
-    t1 = time.perf_counter()
-    indptr, indices, values = lm.samples_csr()
-    t2 = time.perf_counter()
-    if rep == 0:                          # integrity of the large pipelined copy: CSR rows == dense rows
-        import numpy as np
-        rows = lm._samples.info.rows
-        for r0 in (0, rows // 2 - 7, rows - 16):
-            dense = lm._samples.dense(row0=r0, row1=r0 + 16)
-            rec = np.zeros_like(dense)
-            for k in range(16):
-                a, b = indptr[r0 + k], indptr[r0 + k + 1]
-                rec[k, indices[a:b]] = values[a:b]
-            assert np.array_equal(rec, dense), r0
-        print("CSR rows equal dense rows at the head, middle and tail")
-    lm._release()
-    lm._design.close()
-    t3 = time.perf_counter()
-    i = None
-    print(f"rep {rep}: construct+sample {1e3 * (t1 - t0):.0f} ms   samples_csr {1e3 * (t2 - t1):.0f} ms "
-          f"({(indices.nbytes + values.nbytes + indptr.nbytes) / 1e9:.2f} GB)   release {1e3 * (t3 - t2):.0f} ms", flush=True)
+    d = lm._get_design(); ctx.synchronize(); t.append(time.perf_counter())
+    d.build_gram(); ctx.synchronize(); t.append(time.perf_counter())
+    lm.sample(N=5000, burn=100, chains=512, seed=50 + rep, mode="gram"); t.append(time.perf_counter())
+    info = lm._samples.info
+    indptr, indices, values = lm.samples_csr(); t.append(time.perf_counter())
+    lm._release(); lm._design.close(); t.append(time.perf_counter())
+    names = ["upload X", "build gram", "sample() call", "samples_csr()", "release"]
+    print(f"rep {rep}: " + "  ".join(f"{n} {1e3 * (b - a):.1f}" for n, a, b in zip(names, t[:-1], t[1:]))
+          + f"  | device {info.total_ms:.1f} kernels {info.sweep_ms:.1f}  nnz {info.nnz}  total {1e3 * (t[-1] - t[0]):.1f} ms", flush=True)
