@@ -91,13 +91,12 @@ def make_data(cfg=CONFIG):
 # clocks (recipe in /opt/skills/guides/B200_PROFILING.md)
 # ---------------------------------------------------------------------------
 class ClockSampler:
-    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-
     """`nvidia-smi -lms 200` next to the run.  The process is started BEFORE the last warm-up step: attaching a
     second client to the GPU was seen to stall the device for up to a second (3160 ms for the first timed step
     against 2140 ms for the others); `mark()` at the start of the timed region drops the samples taken before it."""
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index

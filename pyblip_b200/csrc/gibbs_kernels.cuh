@@ -20,8 +20,17 @@
 #include "internal.cuh"
 #include <cstdio>
 
-constexpr int GB_BLOCK = 256;
+#ifndef BLIP_GB_BLOCK
+#define BLIP_GB_BLOCK 256
+#endif
+constexpr int GB_BLOCK = BLIP_GB_BLOCK;   // (tuning variants only: the residual and role-specialised kernels assume 256)
 constexpr int GB_NWARP = GB_BLOCK / 32;
+// x modulo the block size, x >= -GB_BLOCK (the sliding window's position <-> thread map)
+__device__ __forceinline__ int gb_mod(int x)
+{
+    if ((GB_BLOCK & (GB_BLOCK - 1)) == 0) return x & (GB_BLOCK - 1);
+    return (x + GB_BLOCK) % GB_BLOCK;
+}
 constexpr int GB_ROUND = 32;      // residual mode: columns speculated per window (64 with two scoring warps was
                                   // measured: no gain on probit C3, -20 % on linear C2 -- more columns redone after a change)
 constexpr int GB_HS = 6;          // doubles of per-chain scalar state: sigma2 tau2 p0 rr n_changes n_windows
@@ -594,7 +603,10 @@ constexpr int GB_AXU = BLIP_GB_AXU;    // 16-byte Gram loads a thread keeps in f
 #endif
 constexpr int GB_PEND = BLIP_GB_PEND;   // changes whose Gram columns are applied to q in one pass
 constexpr int GB_FLUSH_SLOTS = GB_AXU / GB_PEND;
-constexpr int GB_GRAM_REGS = 128;  // 2 CTAs x 256 threads x 128 registers = the whole register file
+#ifndef BLIP_GB_GRAM_REGS
+#define BLIP_GB_GRAM_REGS 128
+#endif
+constexpr int GB_GRAM_REGS = BLIP_GB_GRAM_REGS;  // 2 CTAs x 256 threads x 128 registers = the whole register file
 
 template <int DESIGN> __device__ __forceinline__ double2 gram_pair(const SweepParams& P, int jstar, int k)
 {
@@ -937,7 +949,7 @@ __global__ void __maxnreg__(GB_GRAM_REGS) gibbs_gram_kernel(SweepParams P)
         int pos0 = 0;
         while (pos0 < p) {
             ++n_windows;
-            const int off = (tid - pos0) & (GB_BLOCK - 1);
+            const int off = (GB_BLOCK & (GB_BLOCK - 1)) == 0 ? ((tid - pos0) & (GB_BLOCK - 1)) : gb_mod(tid - pos0 % GB_BLOCK);
             const int pos = pos0 + off;
             bool change = false, spike = true;
             double XjTr = 0.0;
@@ -965,14 +977,14 @@ __global__ void __maxnreg__(GB_GRAM_REGS) gibbs_gram_kernel(SweepParams P)
             // first changed position in window order (= smallest cyclic offset from pos0): every
             // warp posts the smallest offset among its lanes with one shared-memory atomicMin
             const unsigned m = __ballot_sync(0xffffffffu, change);
-            const int r = pos0 & (GB_BLOCK - 1);
+            const int r = gb_mod(pos0);
             if (m && lane == 0) {
                 int l;
                 if (warp == (r >> 5)) {                 // the warp that holds the window start: lanes
                     const unsigned hi = m & (0xffffffffu << (r & 31));   // at/after it come first
                     l = hi ? __ffs(hi) - 1 : __ffs(m) - 1;
                 } else l = __ffs(m) - 1;
-                atomicMin(&s_first[parity], (32 * warp + l - r) & (GB_BLOCK - 1));
+                atomicMin(&s_first[parity], gb_mod(32 * warp + l - r));
             }
             PH(2);
             __syncthreads();
@@ -992,7 +1004,7 @@ __global__ void __maxnreg__(GB_GRAM_REGS) gibbs_gram_kernel(SweepParams P)
             // Everybody knows the changing coordinate without waiting for its owner: the Gram
             // entry that corrects this thread's own q_pos is requested before the slab draw and
             // before the leaving positions are re-filled, so its latency hides behind that math.
-            const int jstar = sj[(pos0 + first) & (GB_BLOCK - 1)];
+            const int jstar = sj[gb_mod(pos0 + first)];
             double gj = 0.0;
             PH(6);
             if (off > first) {
