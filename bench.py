@@ -505,9 +505,13 @@ def main():
                 t_p = time.perf_counter()
                 # the other half of the path, on the device-resident samples of every rank
                 seq = create_groups.sequential_groups(lm, q=0.1, max_pep=0.25, max_size=25, prenarrow=True)
+                if args.debug:
+                    print(f"[e2e step rank {rank}] sequential_groups {1e3 * (time.perf_counter() - t_p):.1f} ms", file=sys.stderr, flush=True)
                 allg = create_groups.all_cand_groups(lm, q=0.1, max_pep=0.25, max_size=25,
                                                      prefilter_thresholds=[0.01, 0.02, 0.03, 0.05, 0.1, 0.2])
                 out.update(n_seq=len(seq), n_all=len(allg), pip_s=time.perf_counter() - t_p)
+                if args.debug:
+                    print(f"[e2e step rank {rank}] PIP stage {1e3 * out['pip_s']:.1f} ms", file=sys.stderr, flush=True)
             lm._release()
             lm._design.close()
             return out

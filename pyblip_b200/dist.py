@@ -13,7 +13,13 @@ SUM all-reduce (NCCL over NVLink on GPUs; gloo on a host buffer in the CPU tests
 (marginal counts -> per-threshold window and pair counts -> tree-group counts), because each
 stage's requests depend on the merged result of the one before.
 """
+import os
+import sys
+import time
+
 import numpy as np
+
+_DEBUG = bool(os.environ.get("BLIPGPU_DIST_DEBUG"))
 
 # number of collectives issued by this module since import (tests assert on it)
 STATS = dict(all_reduce=0, all_gather=0, device_merges=0)
@@ -132,11 +138,13 @@ class CountBatch:
             index = (self.reqs[0][0] if self.reqs else self.roots[0]).device_index
             # torch.empty launches nothing; every counting call zero-fills its own slice on the
             # library's stream and synchronises that stream before it returns
+            t_0 = time.perf_counter()
             buf = torch.empty(max(total, 1), dtype=torch.int64, device=_torch_device(index))
             base = buf.data_ptr()
             for dev, kind, args, off, _, size in self.reqs:
                 if size:
                     dev.local_into(kind, base + 8 * (head + off), *args)
+            t_1 = time.perf_counter()
             if head:
                 hv = np.zeros(head, dtype=np.int64)
                 for i, r in enumerate(self.roots):
@@ -146,6 +154,10 @@ class CountBatch:
             STATS["device_merges"] += 1
             d.all_reduce(buf, op=d.ReduceOp.SUM)
             merged = buf.cpu().numpy()
+            if _DEBUG:
+                print(f"[dist rank {rank}] stage of {len(self.reqs)} requests, {total} int64: local counts "
+                      f"{1e3 * (t_1 - t_0):.1f} ms, all-reduce + read back {1e3 * (time.perf_counter() - t_1):.1f} ms",
+                      file=sys.stderr, flush=True)
         else:
             host = np.zeros(max(total, 1), dtype=np.int64)
             for i, r in enumerate(self.roots):
