@@ -91,7 +91,7 @@ def make_data(cfg=CONFIG):
 # clocks (recipe in /opt/skills/guides/B200_PROFILING.md)
 # ---------------------------------------------------------------------------
 class ClockSampler:
-    """`nvidia-smi -lms 200` next to the run.  The process is started BEFORE the last warm-up step: attaching a
+    """`nvidia-smi -lms 200` next to the run.  The process is started BEFORE the warm-up steps: attaching a
     second client to the GPU was seen to stall the device for up to a second (3160 ms for the first timed step
     against 2140 ms for the others); `mark()` at the start of the timed region drops the samples taken before it."""
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -395,12 +395,10 @@ def main():
                       f"{info.sweep_ms:.1f} ms  nnz/row {info.nnz / max(info.rows, 1):.1f}", file=sys.stderr, flush=True)
             return out
         clocks = ClockSampler(local_rank)
+        if want_clocks:
+            clocks.start()                       # before the warm-up steps: see ClockSampler
         for w in range(args.warmup):
-            if want_clocks and w == args.warmup - 1:
-                clocks.start()
             step(1000 + w)
-        if want_clocks and args.warmup == 0:
-            clocks.start()
         barrier(dist, ctx)
         clocks.mark()
         ctx.counters(reset=True)
@@ -498,8 +496,8 @@ def main():
             t_1 = time.perf_counter()
             indptr, indices, values = lm.samples_csr()
             out = dict(nnz=int(indptr[-1]), pip_s=0.0)
-            if args.debug and rank == 0:
-                print(f"[e2e step] construct + sample() {1e3 * (t_1 - t_0):.1f} ms  samples_csr() "
+            if args.debug:
+                print(f"[e2e step rank {rank}] construct + sample() {1e3 * (t_1 - t_0):.1f} ms  samples_csr() "
                       f"{1e3 * (time.perf_counter() - t_1):.1f} ms  nnz {out['nnz']}", file=sys.stderr, flush=True)
             if with_pips:
                 t_p = time.perf_counter()
@@ -512,12 +510,17 @@ def main():
                 out.update(n_seq=len(seq), n_all=len(allg), pip_s=time.perf_counter() - t_p)
                 if args.debug:
                     print(f"[e2e step rank {rank}] PIP stage {1e3 * out['pip_s']:.1f} ms", file=sys.stderr, flush=True)
+            t_r = time.perf_counter()
             lm._release()
             lm._design.close()
+            if args.debug:
+                print(f"[e2e step rank {rank}] release {1e3 * (time.perf_counter() - t_r):.1f} ms  whole step "
+                      f"{1e3 * (time.perf_counter() - t_0):.1f} ms", file=sys.stderr, flush=True)
             return out
 
         def timed_e2e(with_pips, ev0, ev1):
-            e2e_step(3000, with_pips)                    # warm-up (allocator, page-in)
+            for w in range(2):                           # warm-up: page-locked result blocks, the device pool's steady state
+                e2e_step(3000 + w, with_pips)
             barrier(dist, ctx)
             ctx.counters(reset=True)
             c_before = dict(bdist.STATS)

@@ -7,7 +7,9 @@ opaque handles; the reference-facing API lives in ``linear/``, ``probit/``,
 """
 import ctypes as C
 import os
+import sys
 import threading
+import time
 import weakref
 
 import numpy as np
@@ -339,10 +341,13 @@ class Samples:
 
     def csr(self):
         rows = self.info.rows
+        t0 = time.perf_counter()
         indptr = np.empty(rows + 1, dtype=np.int64)
         nnz = self.info.nnz
         indices = host_empty(max(nnz, 1), np.int32)
         values = host_empty(max(nnz, 1), np.float64)
+        if os.environ.get("BLIPGPU_LAUNCH_LOG"):
+            print(f"[blipgpu] csr(): result arrays in {1e3 * (time.perf_counter() - t0):.1f} ms", file=sys.stderr, flush=True)
         check(load().blipgpu_samples_csr(self._h, C.c_void_p(indptr.ctypes.data),
                                          C.c_void_p(indices.ctypes.data),
                                          C.c_void_p(values.ctypes.data)))

@@ -376,12 +376,13 @@ extern "C" int blipgpu_design_upload(blipgpu_ctx* ctx, const double* X, int64_t 
     d->ctx = ctx; d->kind = BLIPGPU_DESIGN_DENSE; d->n = n; d->p = p;
     d->ldx = round_up(n, 4); d->G = nullptr; d->ldg = 0; d->XT = nullptr; d->Xl2 = nullptr;
     struct DesignGuard { blipgpu_design* d; ~DesignGuard() { if (d) blipgpu_design_free(d); } } guard{ d };
+    DevPoolScope pool_scope(ctx->stream);          // design buffers: stream-ordered pool, like the sampler's (internal.cuh)
     DevBuf Xrow;                                   // row-major staging copy, freed on every exit
     BLIP_TRY(Xrow.alloc(sizeof(double) * n * p));
     cudaError_t e;
-    if ((e = cudaMalloc(&d->XT, sizeof(double) * p * d->ldx)) != cudaSuccess ||
-        (e = cudaMalloc(&d->Xl2, sizeof(double) * p)) != cudaSuccess) {
-        blip_set_error("design_upload: cudaMalloc failed: %s", cudaGetErrorString(e));
+    if ((e = blip_store_alloc((void**)&d->XT, sizeof(double) * p * d->ldx, ctx->stream)) != cudaSuccess ||
+        (e = blip_store_alloc((void**)&d->Xl2, sizeof(double) * p, ctx->stream)) != cudaSuccess) {
+        blip_set_error("design_upload: device allocation failed: %s", cudaGetErrorString(e));
         return BLIP_ERR_NOMEM;
     }
     CUDA_TRY(cudaMemcpyAsync(Xrow.ptr, X, sizeof(double) * n * p, cudaMemcpyHostToDevice, ctx->stream));
@@ -411,7 +412,7 @@ extern "C" int blipgpu_design_changepoint(blipgpu_ctx* ctx, int64_t T, blipgpu_d
     d->ctx = ctx; d->kind = BLIPGPU_DESIGN_CHANGEPOINT; d->n = T; d->p = T; d->ldx = 0;
     d->XT = nullptr; d->G = nullptr; d->ldg = 0; d->Xl2 = nullptr;
     struct DesignGuard { blipgpu_design* d; ~DesignGuard() { if (d) blipgpu_design_free(d); } } guard{ d };
-    CUDA_TRY(cudaMalloc(&d->Xl2, sizeof(double) * T));
+    CUDA_TRY(blip_store_alloc((void**)&d->Xl2, sizeof(double) * T, ctx->stream));
     changepoint_xl2_kernel<<<(unsigned)((T + 255) / 256), 256, 0, ctx->stream>>>(d->Xl2, T);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -453,7 +454,11 @@ extern "C" int blipgpu_design_free(blipgpu_design* d)
 {
     if (!d) return BLIP_OK;
     cudaSetDevice(d->ctx->device);
-    cudaFree(d->XT); cudaFree(d->Xl2); cudaFree(d->G);
+    // stream-ordered frees on the stream every user of these buffers ran on (the sampler joins its second
+    // stream before it returns); a cudaFree of the 0.8 GB Gram matrix synchronises the device and was seen to
+    // take > 100 ms
+    cudaStream_t st = d->ctx->stream;
+    blip_store_free(d->XT, st); blip_store_free(d->Xl2, st); blip_store_free(d->G, st);
     delete d;
     return BLIP_OK;
 }

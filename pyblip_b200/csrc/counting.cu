@@ -23,6 +23,12 @@ namespace {
 constexpr int CT_BLOCK = 256;
 constexpr int CT_NWARP = CT_BLOCK / 32;
 
+// Device buffers of the counting calls come from the device's stream-ordered pool on the context's stream, like the
+// sampler's (internal.cuh): a plain cudaMalloc / cudaFree of the GB-sized ones (the column-major copy of the bit
+// matrix, selected-column sets) was seen to take hundreds of ms now and then, and every cudaFree synchronises the device.
+inline cudaError_t dev_alloc(blipgpu_ctx* ctx, void** p, size_t bytes) { return blip_store_alloc(p, bytes, ctx->stream); }
+inline void dev_free(blipgpu_ctx* ctx, void* p) { blip_store_free(p, ctx->stream); }
+
 // In-warp 32x32 bit-matrix transpose: on entry lane r holds row r (bit c = column c);
 // on exit lane c holds column c (bit r = row r).
 __device__ __forceinline__ uint32_t warp_transpose32(uint32_t x)
@@ -624,10 +630,10 @@ int alloc_bits(blipgpu_ctx* ctx, int64_t N, int64_t p, blipgpu_bits** out)
     b->ctx = ctx; b->N = N; b->N_pad = round_up(std::max<int64_t>(N, 1), 32); b->p = p;
     b->words = (p + 31) / 32; b->owns = true; b->bits = nullptr; b->colbits = nullptr; b->NW = 0;
     const size_t bytes = sizeof(uint32_t) * std::max<int64_t>(b->words, 1) * b->N_pad;
-    cudaError_t e = cudaMalloc(&b->bits, bytes);
+    cudaError_t e = dev_alloc(ctx, (void**)&b->bits, bytes);
     if (e != cudaSuccess) { delete b; blip_set_error("bits allocation (%zu bytes) failed: %s", bytes, cudaGetErrorString(e)); return BLIP_ERR_NOMEM; }
     e = cudaMemsetAsync(b->bits, 0, bytes, ctx->stream);
-    if (e != cudaSuccess) { cudaFree(b->bits); delete b; blip_set_error("memset failed: %s", cudaGetErrorString(e)); return BLIP_ERR_CUDA; }
+    if (e != cudaSuccess) { dev_free(ctx, b->bits); delete b; blip_set_error("memset failed: %s", cudaGetErrorString(e)); return BLIP_ERR_CUDA; }
     *out = b;
     return BLIP_OK;
 }
@@ -650,7 +656,7 @@ int with_output(blipgpu_ctx* ctx, int64_t count, int64_t* out, int out_is_device
     unsigned long long* dev = nullptr;
     bool temp = !out_is_device;
     if (temp) {
-        cudaError_t e = cudaMalloc(&dev, sizeof(unsigned long long) * std::max<int64_t>(count, 1));
+        cudaError_t e = dev_alloc(ctx, (void**)&dev, sizeof(unsigned long long) * std::max<int64_t>(count, 1));
         if (e != cudaSuccess) { blip_set_error("count buffer allocation failed: %s", cudaGetErrorString(e)); return BLIP_ERR_NOMEM; }
     } else dev = reinterpret_cast<unsigned long long*>(out);
     int rc = BLIP_OK;
@@ -664,7 +670,7 @@ int with_output(blipgpu_ctx* ctx, int64_t count, int64_t* out, int out_is_device
     if (e == cudaSuccess && temp) e = cudaMemcpyAsync(out, dev, sizeof(int64_t) * count, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) { blip_set_error("counting kernel failed: %s", cudaGetErrorString(e)); rc = BLIP_ERR_CUDA; }
-    if (temp) cudaFree(dev);
+    if (temp) dev_free(ctx, dev);
     return rc;
 }
 
@@ -718,7 +724,7 @@ extern "C" int blipgpu_bits_from_dense(blipgpu_ctx* ctx, const void* samples, in
     const size_t esz = dtype == BLIPGPU_DTYPE_F64 ? 8 : 1;
     const int64_t stage_rows = std::min<int64_t>(N, std::max<int64_t>(1, (int64_t)(256 << 20) / (int64_t)(esz * p)));
     void* stage = nullptr;
-    cudaError_t e = cudaMalloc(&stage, esz * stage_rows * p);
+    cudaError_t e = dev_alloc(ctx, &stage, esz * stage_rows * p);
     if (e != cudaSuccess) { blipgpu_bits_free(b); blip_set_error("bits_from_dense: staging allocation failed: %s", cudaGetErrorString(e)); return BLIP_ERR_NOMEM; }
     cudaStream_t st = ctx->stream;
     for (int64_t r = 0; r < N && e == cudaSuccess; r += stage_rows) {
@@ -733,7 +739,7 @@ extern "C" int blipgpu_bits_from_dense(blipgpu_ctx* ctx, const void* samples, in
         if (e == cudaSuccess) e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     }
-    cudaFree(stage);
+    dev_free(ctx, stage);
     if (e != cudaSuccess) { blipgpu_bits_free(b); blip_set_error("bits_from_dense: %s", cudaGetErrorString(e)); return BLIP_ERR_CUDA; }
     *out = b;
     return BLIP_OK;
@@ -760,7 +766,7 @@ extern "C" int blipgpu_bits_select_columns(blipgpu_bits* b, const int64_t* cols,
     BLIP_TRY(alloc_bits(b->ctx, b->N, ncols, &o));
     int32_t* d_cols = nullptr;
     cudaStream_t st = b->ctx->stream;
-    cudaError_t e = cudaMalloc(&d_cols, sizeof(int32_t) * ncols);
+    cudaError_t e = dev_alloc(b->ctx, (void**)&d_cols, sizeof(int32_t) * ncols);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_cols, c32.data(), sizeof(int32_t) * ncols, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess && b->N > 0) {
         dim3 grid((unsigned)((b->N + 255) / 256), (unsigned)o->words);
@@ -768,7 +774,7 @@ extern "C" int blipgpu_bits_select_columns(blipgpu_bits* b, const int64_t* cols,
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(d_cols);
+    dev_free(b->ctx, d_cols);
     if (e != cudaSuccess) { blipgpu_bits_free(o); blip_set_error("select_columns: %s", cudaGetErrorString(e)); return BLIP_ERR_CUDA; }
     *out = o;
     return BLIP_OK;
@@ -781,7 +787,7 @@ extern "C" int blipgpu_bits_to_dense(blipgpu_bits* b, uint8_t* out)
     if (b->N == 0) return BLIP_OK;
     const int64_t stage_rows = std::min<int64_t>(b->N, std::max<int64_t>(1, (int64_t)(256 << 20) / b->p));
     uint8_t* stage = nullptr;
-    CUDA_TRY(cudaMalloc(&stage, (size_t)stage_rows * b->p));
+    CUDA_TRY(dev_alloc(b->ctx, (void**)&stage, (size_t)stage_rows * b->p));
     cudaStream_t st = b->ctx->stream;
     cudaError_t e = cudaSuccess;
     for (int64_t r = 0; r < b->N && e == cudaSuccess; r += stage_rows) {
@@ -790,7 +796,7 @@ extern "C" int blipgpu_bits_to_dense(blipgpu_bits* b, uint8_t* out)
         e = cudaMemcpyAsync(out + r * b->p, stage, (size_t)nr * b->p, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     }
-    cudaFree(stage);
+    dev_free(b->ctx, stage);
     if (e != cudaSuccess) { blip_set_error("bits_to_dense: %s", cudaGetErrorString(e)); return BLIP_ERR_CUDA; }
     return BLIP_OK;
 }
@@ -821,6 +827,7 @@ extern "C" int blipgpu_count_sequential(blipgpu_bits* b, int32_t max_size, int64
     // a heavy word then spread over all SMs instead of queueing on a few (0.78 ms with three chunks).
     const int64_t rpb_gap = 16384;      // 2048 / 4096 / 8192 / 16384 rows measured: 0.54 / 0.44 / 0.39 / 0.38 ms at C2
     const unsigned chunks_gap = (unsigned)std::max<int64_t>(1, (b->N + rpb_gap - 1) / rpb_gap);
+    DevPoolScope pool_scope(b->ctx->stream);
     DevBuf hist;
     if (!legacy && b->N > 0) BLIP_TRY(hist.alloc(sizeof(unsigned long long) * 32 * (size_t)b->words * (size_t)eff));
     return with_output(b->ctx, (int64_t)max_size * b->p, zero_counts, out_is_device, [&](unsigned long long* dev) {
@@ -906,7 +913,7 @@ static void ensure_colbits(blipgpu_bits* b, cudaStream_t st)
     if (b->colbits || b->N <= 0) return;
     const int64_t NW = round_up((b->N + 31) / 32, 8);
     uint32_t* cb = nullptr;
-    if (cudaMalloc(&cb, sizeof(uint32_t) * 32 * b->words * NW) != cudaSuccess) { cudaGetLastError(); return; }
+    if (dev_alloc(b->ctx, (void**)&cb, sizeof(uint32_t) * 32 * b->words * NW) != cudaSuccess) { cudaGetLastError(); return; }
     const unsigned ty = (unsigned)((NW / 8 + CT_NWARP - 1) / CT_NWARP);
     transpose_bits_kernel<<<dim3((unsigned)b->words, ty), CT_BLOCK, 0, st>>>(b->bits, b->N, b->N_pad, NW, cb);
     b->ctx->kernel_launches += 1;
@@ -927,11 +934,11 @@ extern "C" int blipgpu_count_groups(blipgpu_bits* b, const int64_t* offsets, con
     }
     int64_t* d_off = nullptr; int32_t* d_mem = nullptr;
     cudaStream_t st = b->ctx->stream;
-    cudaError_t e = cudaMalloc(&d_off, sizeof(int64_t) * (n_groups + 1));
-    if (e == cudaSuccess) e = cudaMalloc(&d_mem, sizeof(int32_t) * std::max<int64_t>(total, 1));
+    cudaError_t e = dev_alloc(b->ctx, (void**)&d_off, sizeof(int64_t) * (n_groups + 1));
+    if (e == cudaSuccess) e = dev_alloc(b->ctx, (void**)&d_mem, sizeof(int32_t) * std::max<int64_t>(total, 1));
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_off, offsets, sizeof(int64_t) * (n_groups + 1), cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess && total > 0) e = cudaMemcpyAsync(d_mem, m32.data(), sizeof(int32_t) * total, cudaMemcpyHostToDevice, st);
-    if (e != cudaSuccess) { cudaFree(d_off); cudaFree(d_mem); blip_set_error("count_groups: %s", cudaGetErrorString(e)); return BLIP_ERR_CUDA; }
+    if (e != cudaSuccess) { dev_free(b->ctx, d_off); dev_free(b->ctx, d_mem); blip_set_error("count_groups: %s", cudaGetErrorString(e)); return BLIP_ERR_CUDA; }
     const int64_t rpb = pick_rows_per_block(b->N, n_groups, b->ctx->sm_count);
     const unsigned chunks = (unsigned)std::max<int64_t>(1, (b->N + rpb - 1) / rpb);
     // With enough members to pay for it (the transposition moves 2 N p / 8 bytes once per handle) the
@@ -951,7 +958,7 @@ extern "C" int blipgpu_count_groups(blipgpu_bits* b, const int64_t* offsets, con
             count_groups_kernel<<<dim3((unsigned)n_groups, chunks), CT_BLOCK, 0, st>>>(b->bits, b->N, b->N_pad, d_off, d_mem, rpb, dev);
         }
     });
-    cudaFree(d_off); cudaFree(d_mem);
+    dev_free(b->ctx, d_off); dev_free(b->ctx, d_mem);
     return rc;
 }
 
@@ -968,12 +975,12 @@ extern "C" int blipgpu_count_false_rows(blipgpu_bits* b, const int64_t* offsets,
     }
     int64_t* d_off = nullptr; int32_t* d_mem = nullptr;
     cudaStream_t st = b->ctx->stream;
-    cudaError_t e = cudaMalloc(&d_off, sizeof(int64_t) * (n_groups + 1));
-    if (e == cudaSuccess) e = cudaMalloc(&d_mem, sizeof(int32_t) * std::max<int64_t>(total, 1));
+    cudaError_t e = dev_alloc(b->ctx, (void**)&d_off, sizeof(int64_t) * (n_groups + 1));
+    if (e == cudaSuccess) e = dev_alloc(b->ctx, (void**)&d_mem, sizeof(int32_t) * std::max<int64_t>(total, 1));
     const int64_t zero = 0;
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_off, n_groups > 0 ? offsets : &zero, sizeof(int64_t) * (n_groups + 1), cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess && total > 0) e = cudaMemcpyAsync(d_mem, m32.data(), sizeof(int32_t) * total, cudaMemcpyHostToDevice, st);
-    if (e != cudaSuccess) { cudaFree(d_off); cudaFree(d_mem); blip_set_error("count_false_rows: %s", cudaGetErrorString(e)); return BLIP_ERR_CUDA; }
+    if (e != cudaSuccess) { dev_free(b->ctx, d_off); dev_free(b->ctx, d_mem); blip_set_error("count_false_rows: %s", cudaGetErrorString(e)); return BLIP_ERR_CUDA; }
     const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((b->N + CT_BLOCK - 1) / CT_BLOCK, 8LL * b->ctx->sm_count));
     int rc = with_output(b->ctx, 1, count, out_is_device, [&](unsigned long long* dev) {
         if (b->N == 0 || n_groups == 0) return;
@@ -984,7 +991,7 @@ extern "C" int blipgpu_count_false_rows(blipgpu_bits* b, const int64_t* offsets,
             count_false_rows_kernel<<<grid, CT_BLOCK, 0, st>>>(b->bits, b->N, b->N_pad, d_off, d_mem, (int)n_groups, dev);
         }
     });
-    cudaFree(d_off); cudaFree(d_mem);
+    dev_free(b->ctx, d_off); dev_free(b->ctx, d_mem);
     return rc;
 }
 
@@ -992,8 +999,8 @@ extern "C" int blipgpu_bits_free(blipgpu_bits* b)
 {
     if (!b) return BLIP_OK;
     cudaSetDevice(b->ctx->device);
-    if (b->owns) cudaFree(b->bits);
-    if (b->colbits) cudaFree(b->colbits);
+    if (b->owns) dev_free(b->ctx, b->bits);
+    if (b->colbits) dev_free(b->ctx, b->colbits);
     delete b;
     return BLIP_OK;
 }

@@ -327,6 +327,7 @@ static int sample_impl(blipgpu_ctx* ctx, blipgpu_design* design,
     const bool st_auto = use_ws && st_possible && 2 * chains <= ctx->sm_count && want_kernel == BLIPGPU_GRAM_KERNEL_AUTO && getenv("BLIPGPU_STREAM") != nullptr;
     const bool use_role = use_cl || use_ws || use_wb || use_wbc || use_ws2c || st_forced;   // double-buffered scratch, no work queue
 
+    const auto t_call0 = std::chrono::steady_clock::now();
     // ---- chunking
     // Sweeps per launch.  The gram-form kernels compute the visiting order themselves (no permutation buffers) and
     // lose the tail of every launch (the last work items of a persistent grid, the last sweeps of the slowest chain):
@@ -769,8 +770,9 @@ static int sample_impl(blipgpu_ctx* ctx, blipgpu_design* design,
                 const double ms = timer.stop(1);
                 smp->sweep_ms += ms;
                 smp->sweep_launches += 1;
-                if (launch_log) fprintf(stderr, "[blipgpu] launch sweeps %lld..%lld grid %u: %.3f ms%s\n",
-                                        (long long)sweep0, (long long)(sweep0 + Sc), grid, ms, st_now ? " (stream)" : "");
+                if (launch_log) fprintf(stderr, "[blipgpu] launch sweeps %lld..%lld grid %u: %.3f ms%s  (host clock since the call began: %.1f ms)\n",
+                                        (long long)sweep0, (long long)(sweep0 + Sc), grid, ms, st_now ? " (stream)" : "",
+                                        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call0).count());
             }
             int ovf = 0, nerr = 0;
             unsigned long long used = 0;

@@ -129,7 +129,7 @@ int blip_gram_build(blipgpu_design* d)
     blipgpu_ctx* ctx = d->ctx;
     const int64_t p = d->p;
     d->ldg = round_up(p, 4);
-    cudaError_t e = cudaMalloc(&d->G, sizeof(double) * (size_t)p * d->ldg);
+    cudaError_t e = blip_store_alloc((void**)&d->G, sizeof(double) * (size_t)p * d->ldg, ctx->stream);
     if (e != cudaSuccess) {
         d->G = nullptr;
         blip_set_error("gram build: cannot allocate %.2f GB for the %lld x %lld Gram matrix: %s",
@@ -138,7 +138,7 @@ int blip_gram_build(blipgpu_design* d)
     }
     // anything that fails below must not leave a half-built matrix behind: a later
     // blipgpu_design_build_gram would take a non-NULL G for a finished one
-    struct GramGuard { blipgpu_design* d; bool ok; ~GramGuard() { if (!ok) { cudaFree(d->G); d->G = nullptr; } } } guard{ d, false };
+    struct GramGuard { blipgpu_design* d; bool ok; ~GramGuard() { if (!ok) { blip_store_free(d->G, d->ctx->stream); d->G = nullptr; } } } guard{ d, false };
     CUDA_TRY(cudaMemsetAsync(d->G, 0, sizeof(double) * (size_t)p * d->ldg, ctx->stream));
     const int ntile = (int)((p + TILE - 1) / TILE);
     const int64_t nblocks = (int64_t)ntile * (ntile + 1) / 2;
