@@ -54,6 +54,122 @@ int blip_ctx_activate(blipgpu_ctx* ctx)
     return BLIP_OK;
 }
 
+// ---- device blocks, cached per stream (internal.cuh) ------------------------------------------------------
+// The driver's stream-ordered pool alone was not enough: with identical request sequences it still went to the
+// driver for fresh memory now and then (0.08 - 1.1 s inside the first timed sampler call of a bench run, 0.5 s in a
+// samples_csr()), which a size-keyed free list in front of it does not.
+namespace {
+struct DevBlock { void* ptr; size_t bytes; };
+struct DevCache { std::vector<DevBlock> idle; size_t idle_bytes = 0; };        // oldest first
+struct DevCaches {
+    std::mutex mu;
+    std::unordered_map<cudaStream_t, DevCache> by_stream;
+    std::unordered_map<void*, size_t> live;
+};
+DevCaches& dev_caches() { static DevCaches* c = new DevCaches(); return *c; }
+constexpr size_t kDevCacheMin = (size_t)1 << 20;
+size_t dev_cache_limit()
+{
+    static const size_t v = [] {
+        const char* e = getenv("BLIPGPU_DEVICE_CACHE_MB");
+        return (size_t)(e ? std::max(0, atoi(e)) : 65536) << 20;
+    }();
+    return v;
+}
+cudaError_t raw_dev_alloc(void** p, size_t bytes, cudaStream_t st)
+{
+    return blip_use_pool() ? cudaMallocAsync(p, bytes, st) : cudaMalloc(p, bytes);
+}
+void raw_dev_free(void* p, cudaStream_t st)
+{
+    if (blip_use_pool() && cudaFreeAsync(p, st) == cudaSuccess) return;
+    cudaGetLastError();
+    cudaStreamSynchronize(st);
+    cudaFree(p);
+}
+} // namespace
+
+cudaError_t blip_store_alloc(void** p, size_t bytes, cudaStream_t st)
+{
+    if (bytes < kDevCacheMin || !blip_use_pool()) return raw_dev_alloc(p, bytes, st);
+    const size_t want = (size_t)round_up((int64_t)bytes, (int64_t)2 << 20);
+    DevCaches& dc = dev_caches();
+    {
+        std::lock_guard<std::mutex> lock(dc.mu);
+        DevCache& c = dc.by_stream[st];
+        int best = -1;
+        for (int i = 0; i < (int)c.idle.size(); ++i)      // best fit, at most a quarter (+ 8 MB) larger than asked
+            if (c.idle[i].bytes >= want && c.idle[i].bytes <= want + want / 4 + ((size_t)8 << 20) &&
+                (best < 0 || c.idle[i].bytes < c.idle[best].bytes)) best = i;
+        if (best >= 0) {
+            const DevBlock b = c.idle[best];
+            c.idle.erase(c.idle.begin() + best);
+            c.idle_bytes -= b.bytes;
+            dc.live[b.ptr] = b.bytes;
+            *p = b.ptr;
+            return cudaSuccess;
+        }
+    }
+    cudaError_t e = raw_dev_alloc(p, want, st);
+    if (e != cudaSuccess) {                                // out of memory: give every idle block back and try again
+        cudaGetLastError();
+        std::vector<std::pair<cudaStream_t, DevBlock>> drop;
+        {
+            std::lock_guard<std::mutex> lock(dc.mu);
+            for (auto& kv : dc.by_stream) {
+                for (const DevBlock& b : kv.second.idle) drop.push_back({ kv.first, b });
+                kv.second.idle.clear(); kv.second.idle_bytes = 0;
+            }
+        }
+        for (auto& d : drop) raw_dev_free(d.second.ptr, d.first);
+        cudaStreamSynchronize(st);
+        e = raw_dev_alloc(p, want, st);
+    }
+    if (e == cudaSuccess) {
+        std::lock_guard<std::mutex> lock(dc.mu);
+        dc.live[*p] = want;
+    }
+    return e;
+}
+
+void blip_store_free(void* p, cudaStream_t st)
+{
+    if (!p) return;
+    DevCaches& dc = dev_caches();
+    std::vector<DevBlock> drop;
+    {
+        std::lock_guard<std::mutex> lock(dc.mu);
+        auto it = dc.live.find(p);
+        if (it == dc.live.end()) drop.push_back({ p, 0 });                      // a small block, or from before the cache
+        else {
+            DevCache& c = dc.by_stream[st];
+            c.idle.push_back({ p, it->second });
+            c.idle_bytes += it->second;
+            dc.live.erase(it);
+            while (c.idle_bytes > dev_cache_limit() && !c.idle.empty()) {
+                drop.push_back(c.idle.front());
+                c.idle_bytes -= c.idle.front().bytes;
+                c.idle.erase(c.idle.begin());
+            }
+        }
+    }
+    for (const DevBlock& b : drop) raw_dev_free(b.ptr, st);
+}
+
+void blip_store_release(cudaStream_t st)
+{
+    DevCaches& dc = dev_caches();
+    std::vector<DevBlock> drop;
+    {
+        std::lock_guard<std::mutex> lock(dc.mu);
+        auto it = dc.by_stream.find(st);
+        if (it == dc.by_stream.end()) return;
+        drop.swap(it->second.idle);
+        dc.by_stream.erase(it);
+    }
+    for (const DevBlock& b : drop) raw_dev_free(b.ptr, st);
+}
+
 // ---- page-locked host blocks for results, kept across calls --------------------------------------------
 // A result that goes into page-locked memory is one DMA; into a fresh pageable array it is a bounce through
 // a pinned buffer plus a host copy that takes a page fault per page (0.12 - 0.3 s for the 1.6 GB CSR of C2).
@@ -268,6 +384,8 @@ extern "C" int blipgpu_ctx_destroy(blipgpu_ctx* ctx)
 {
     if (!ctx) return BLIP_OK;
     cudaSetDevice(ctx->device);
+    blip_store_release(ctx->stream);
+    blip_store_release(ctx->stream2);
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->stream2);
     cudaStreamDestroy(ctx->stream);

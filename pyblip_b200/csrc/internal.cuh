@@ -75,20 +75,15 @@ bool blip_host_is_pinned(const void* p);                                        
 int blip_bits_alloc(blipgpu_ctx* ctx, int64_t N, int64_t p, blipgpu_bits** out);   // counting.cu
 static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
-// Sample-store allocations: stream-ordered (device memory pool, kept across calls) unless BLIPGPU_NO_POOL is set
+// Device buffers of a call (sample store, sampler and counting buffers, design): stream-ordered.  A freed block of
+// 1 MB or more goes to a per-stream cache of the library and is handed to the next request of (nearly) that size
+// on the same stream -- stream order makes that safe -- so that a repeated job issues no driver allocation at all;
+// misses and small blocks come from the device's stream-ordered pool (cudaMallocAsync, release threshold lifted).
+// BLIPGPU_NO_POOL=1: plain cudaMalloc / cudaFree, no cache.  (api.cu)
 static inline bool blip_use_pool() { static const bool v = getenv("BLIPGPU_NO_POOL") == nullptr; return v; }
-static inline cudaError_t blip_store_alloc(void** p, size_t bytes, cudaStream_t st)
-{
-    return blip_use_pool() ? cudaMallocAsync(p, bytes, st) : cudaMalloc(p, bytes);
-}
-static inline void blip_store_free(void* p, cudaStream_t st)
-{
-    if (!p) return;
-    if (blip_use_pool() && cudaFreeAsync(p, st) == cudaSuccess) return;
-    cudaGetLastError();
-    cudaStreamSynchronize(st);
-    cudaFree(p);
-}
+cudaError_t blip_store_alloc(void** p, size_t bytes, cudaStream_t st);
+void blip_store_free(void* p, cudaStream_t st);
+void blip_store_release(cudaStream_t st);          // give a stream's idle blocks back to the driver
 
 // device allocation freed on scope exit
 // Inside a DevPoolScope the buffers come from the device's stream-ordered pool on the scope's stream (the sampler:
@@ -102,7 +97,7 @@ struct DevBuf {
         if (b == 0) { ptr = nullptr; return BLIP_OK; }
         pooled = scope_on() && blip_use_pool();
         pool_st = scope_stream();
-        cudaError_t e = pooled ? cudaMallocAsync(&ptr, b, pool_st) : cudaMalloc(&ptr, b);
+        cudaError_t e = pooled ? blip_store_alloc(&ptr, b, pool_st) : cudaMalloc(&ptr, b);
         if (e != cudaSuccess) {
             ptr = nullptr;
             blip_set_error("device allocation of %zu bytes failed: %s", b, cudaGetErrorString(e));
@@ -112,9 +107,8 @@ struct DevBuf {
     }
     ~DevBuf() {
         if (!ptr) return;
-        if (pooled && cudaFreeAsync(ptr, pool_st) == cudaSuccess) return;
-        cudaGetLastError();
-        cudaFree(ptr);
+        if (pooled) blip_store_free(ptr, pool_st);
+        else cudaFree(ptr);
     }
     template <class T> T* as() { return reinterpret_cast<T*>(ptr); }
 };
