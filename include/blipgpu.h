@@ -17,7 +17,14 @@
  *   - "device pointer" arguments must belong to the context's device.
  *
  * Environment (diagnostics; none changes a result)
- *   BLIPGPU_LAUNCH_LOG=1             every sweep-kernel launch with its CUDA-event time on stderr
+ *   BLIPGPU_LAUNCH_LOG=1             every sweep-kernel launch with its CUDA-event time and a host time stamp,
+ *                                    allocation times and the stages of samples_csr on stderr
+ *   BLIPGPU_NO_POOL=1                device buffers from cudaMalloc / cudaFree instead of the library's cached,
+ *                                    stream-ordered blocks
+ *   BLIPGPU_DEVICE_CACHE_MB=x        idle device blocks kept per stream for the next call (default 65536)
+ *   BLIPGPU_HOST_CACHE_MB=x          idle page-locked host blocks kept for the next result (default 8192)
+ *   BLIPGPU_NO_PINNED_OUT=1          (host side, pyblip_b200/_lib.py) results in plain NumPy arrays
+ *   BLIPGPU_DIST_DEBUG=1             (host side, pyblip_b200/dist.py) timing of every count merge on stderr
  *   BLIPGPU_NO_L2_PIN=1              residual-form sweeps: do not pin the design matrix in L2
  *   BLIPGPU_NO_WS=1                  gram form: never pick the role-specialised few-chains kernels
  *   BLIPGPU_WS_CLUSTER=1             gram form: AUTO picks the 2-CTA cluster placement when chains <= SMs/2

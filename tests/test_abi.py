@@ -60,3 +60,20 @@ def test_product_does_not_import_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "gibbs_oracle" not in text.replace("oracle/gibbs_oracle.c", ""), f
+
+
+def test_result_arrays_degrade_to_pageable_memory_when_nothing_can_be_pinned():
+    """`host_empty` is only where RESULTS land: if the library cannot page-lock a block (no driver here), the caller
+    gets a plain array of the same shape and dtype -- the compute path still has no fallback (test above)."""
+    try:
+        n = _lib.device_count()
+    except _lib.BlipGpuError:
+        n = 0
+    if n > 0:
+        return   # GPU box: tests/test_host_blocks_gpu.py covers the pinned path
+    import numpy as np
+    a = _lib.host_empty(3 << 20, np.uint8)
+    assert isinstance(a, np.ndarray) and a.shape == (3 << 20,) and a.dtype == np.uint8 and a.base is None
+    b = _lib.host_empty(7, np.float64)
+    assert b.shape == (7,) and b.dtype == np.float64
+    assert _lib.load().blipgpu_host_free(ctypes.c_void_p(0)) == 0
